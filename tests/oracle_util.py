@@ -1,0 +1,66 @@
+"""ctypes access to the CPU oracle (oracle/libtrre_oracle.so) and to the real reference binaries
+(oracle/_ref/trre, oracle/_ref/trre_dft).  Test infrastructure only."""
+import ctypes, os, subprocess
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ORACLE_SO = os.path.join(ROOT, "oracle", "libtrre_oracle.so")
+REF_NFT = os.path.join(ROOT, "oracle", "_ref", "trre")
+REF_DFT = os.path.join(ROOT, "oracle", "_ref", "trre_dft")
+
+NFT, DFT = 0, 1
+SCAN, MATCH = 0, 1
+
+_lib = None
+
+
+def build_oracle():
+    subprocess.run(["make", "-s", "-C", os.path.join(ROOT, "oracle")], check=True,
+                   stdout=subprocess.DEVNULL)
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        if not os.path.exists(ORACLE_SO):
+            build_oracle()
+        L = ctypes.CDLL(ORACLE_SO)
+        L.trre_oracle_run.restype = ctypes.c_int
+        L.trre_oracle_run.argtypes = [ctypes.c_char_p, ctypes.c_int, ctypes.c_int, ctypes.c_int,
+                                      ctypes.c_char_p, ctypes.c_size_t,
+                                      ctypes.POINTER(ctypes.c_void_p), ctypes.POINTER(ctypes.c_size_t),
+                                      ctypes.c_char_p, ctypes.c_size_t]
+        L.trre_oracle_free.argtypes = [ctypes.c_void_p]
+        L.trre_oracle_last_nstates.restype = ctypes.c_size_t
+        L.trre_oracle_last_dstates.restype = ctypes.c_size_t
+        _lib = L
+    return _lib
+
+
+def oracle_run(expr: bytes, data: bytes, flavor=NFT, mode=SCAN, all_=False):
+    """-> (rc, stdout bytes, stderr text)"""
+    L = lib()
+    out = ctypes.c_void_p()
+    out_n = ctypes.c_size_t()
+    err = ctypes.create_string_buffer(512)
+    rc = L.trre_oracle_run(expr, flavor, mode, int(all_), data, len(data),
+                           ctypes.byref(out), ctypes.byref(out_n), err, len(err))
+    res = ctypes.string_at(out, out_n.value) if out.value else b""
+    if out.value:
+        L.trre_oracle_free(out)
+    return rc, res, err.value.decode("latin1")
+
+
+def have_ref():
+    return os.access(REF_NFT, os.X_OK) and os.access(REF_DFT, os.X_OK)
+
+
+def ref_run(expr: bytes, data: bytes, flavor=NFT, mode=SCAN, all_=False, timeout=60):
+    """Run the real reference binary. -> (rc, stdout, stderr)"""
+    argv = [REF_NFT if flavor == NFT else REF_DFT]
+    if mode == MATCH:
+        argv.append("-m")
+    if all_:
+        argv.append("-a")
+    argv.append(expr)
+    p = subprocess.run(argv, input=data, stdout=subprocess.PIPE, stderr=subprocess.PIPE, timeout=timeout)
+    return p.returncode, p.stdout, p.stderr.decode("latin1")
