@@ -58,9 +58,10 @@ static void *take(Run *R, size_t n) {
     return (void *)(b + 1);
 }
 
-static void release_all(Run *R) {
-    while (R->blocks) { Block *p = R->blocks->prev; free(R->blocks); R->blocks = p; }
+static void release_to(Run *R, Block *mark) {
+    while (R->blocks != mark) { Block *p = R->blocks->prev; free(R->blocks); R->blocks = p; }
 }
+static void release_all(Run *R) { release_to(R, NULL); }
 
 static void emit(Run *R, const uint8_t *p, size_t n) {
     if (!n) return;
@@ -556,6 +557,7 @@ typedef struct {
     int *chain; size_t cap_chain;
     Str *acc;                                                 /* per-attempt output accumulator, reused */
     int depth;
+    unsigned long long work;
 } Dft;
 
 static Str *str_new(Run *R) { Str *s = (Str *)take(R, sizeof(Str)); s->p = NULL; s->n = s->cap = 0; return s; }
@@ -592,7 +594,9 @@ static void list_push(Run *R, List *l, int s, Str *w) {
 static void closure_(Dft *D, int s, Str *o, int c, List *sl);
 static void closure(Dft *D, int s, Str *o, int c, List *sl) {
     /* an epsilon cycle recurses until the reference's C stack overflows (SIGSEGV); refuse instead */
-    if (++D->depth > 60000) die(D->R, 2, "error: epsilon cycle (the reference overflows its C stack here)\n");
+    /* generators such as a:(....) enumerate every output string; the reference runs out of memory */
+    if (++D->work > 4000000ull) die(D->R, 2, "error: closure does not finish in the reference (output enumeration)\n");
+    if (++D->depth > 30000) die(D->R, 2, "error: epsilon cycle (the reference overflows its C stack here)\n");
     closure_(D, s, o, c, sl);
     D->depth--;
 }
@@ -615,6 +619,7 @@ static void closure_(Dft *D, int s, Str *o, int c, List *sl) {
 
 static List *step(Dft *D, const List *from, int c) {          /* nft_step(), trre_dft.c:910-923 */
     List *sl = list_new(D->R);
+    D->work = 0;                                              /* budget is per step */
     for (size_t k = 0; k < from->n; k++)
         closure(D, D->N->st[from->it[k].s].a, str_dup(D->R, from->it[k].w), c, sl);
     for (size_t k = 0; k < sl->n; k++) D->N->st[sl->it[k].s].visited = 0;
@@ -694,21 +699,71 @@ static long walk_dft(Dft *D, int dstart, const uint8_t *p, const uint8_t *e) {
         } else if (d->out[*c] != NULL) {                      /* explored, dead (:1132-1134) */
             break;
         } else {                                              /* explore (:1135-1175) */
+            /* build into a scratch region, keep copies of what survives, drop the rest */
+                    Block *mark;
+            {   /* make sure acc cannot grow inside the scratch region */
+                size_t need = acc->n + 4096;
+                if (acc->cap < need) { uint8_t *q = (uint8_t *)take(R, need); if (acc->n) memcpy(q, acc->p, acc->n); acc->p = q; acc->cap = need; }
+            }
+            mark = R->blocks;
             List *sl = step(D, d->states, *c);
-            if (sl->n == 0) { d->out[*c] = DEAD_MARK; break; }
+            if (sl->n == 0) { release_to(R, mark); d->out[*c] = DEAD_MARK; break; }
             Str *prefix = str_new(R);
             strip_common_prefix(D, sl, prefix);
             int nx = dst_find(D, sl);
-            if (nx < 0) nx = dst_new(D, sl);
+            /* copy survivors out of the scratch region */
+            size_t plen = prefix->n;
+            uint8_t *ptmp = (uint8_t *)malloc(plen ? plen : 1);
+            if (plen) memcpy(ptmp, prefix->p, plen);
+            List *keep = NULL;
+            if (nx < 0) {
+                /* serialise the list outside the arena */
+                size_t tot = 0;
+                for (size_t k = 0; k < sl->n; k++) tot += sl->it[k].w->n;
+                uint8_t *bytes = (uint8_t *)malloc(tot ? tot : 1);
+                size_t *lens = (size_t *)malloc(sl->n * sizeof(size_t));
+                int *sts = (int *)malloc(sl->n * sizeof(int));
+                size_t off = 0, cnt = sl->n;
+                for (size_t k = 0; k < cnt; k++) {
+                    lens[k] = sl->it[k].w->n; sts[k] = sl->it[k].s;
+                    if (lens[k]) memcpy(bytes + off, sl->it[k].w->p, lens[k]);
+                    off += lens[k];
+                }
+                release_to(R, mark);
+                keep = list_new(R);
+                off = 0;
+                for (size_t k = 0; k < cnt; k++) {
+                    Str *w = str_new(R);
+                    for (size_t j = 0; j < lens[k]; j++) str_push(R, w, bytes[off + j]);
+                    off += lens[k];
+                    list_push(R, keep, sts[k], w);
+                }
+                free(bytes); free(lens); free(sts);
+                nx = dst_new(D, keep);
+            } else {
+                release_to(R, mark);
+            }
+            prefix = str_new(R);
+            for (size_t j = 0; j < plen; j++) str_push(R, prefix, ptmp[j]);
+            free(ptmp);
             d = D->ds[ds];
             d->next[*c] = nx; d->out[*c] = prefix;
-            str_cat(R, acc, prefix);
+            if (acc->n + prefix->n > acc->cap) str_cat(R, acc, prefix);      /* rare: very long prefix */
+            else { if (prefix->n) memcpy(acc->p + acc->n, prefix->p, prefix->n); acc->n += prefix->n; }
             ds = nx;
             Dst *t = D->ds[ds];
             if (t->final < 0) {                               /* finality probe with c = '\0' (:1164-1174); a CONS(0) counts */
+                Block *m2 = R->blocks;
                 List *fl = step(D, t->states, 0);
-                if (fl->n) { t->final = 1; t->final_out = str_dup(R, fl->it[0].w); }
-                else t->final = 0;
+                if (fl->n) {
+                    size_t fn = fl->it[0].w->n;
+                    uint8_t *ft = (uint8_t *)malloc(fn ? fn : 1);
+                    if (fn) memcpy(ft, fl->it[0].w->p, fn);
+                    release_to(R, m2);
+                    t->final = 1; t->final_out = str_new(R);
+                    for (size_t j = 0; j < fn; j++) str_push(R, t->final_out, ft[j]);
+                    free(ft);
+                } else { release_to(R, m2); t->final = 0; }
             }
         }
     }
@@ -722,7 +777,7 @@ static long walk_dft(Dft *D, int dstart, const uint8_t *p, const uint8_t *e) {
 static void run_dft(Run *R, Nft *N, int init, int mode, const uint8_t *in, size_t n) {
     Dft D;
     D.R = R; D.N = N; D.ds = NULL; D.n_ds = D.cap_ds = 0; D.chain = NULL;
-    D.acc = str_new(R); D.depth = 0;
+    D.acc = str_new(R); D.depth = 0; D.work = 0;
     D.n_bucket = 1u << 16;
     D.bucket = (int *)take(R, D.n_bucket * sizeof(int));
     for (size_t k = 0; k < D.n_bucket; k++) D.bucket[k] = -1;

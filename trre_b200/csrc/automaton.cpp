@@ -1,0 +1,646 @@
+// automaton.cpp - flat NFT -> deterministic scan automaton -> blob (host, cold path).
+//
+// Two subset constructions over the same flat NFT, one per reference binary:
+//
+//  * DFT flavour: what trre_dft.c builds lazily (nft_step/_step_ 874-923, truncate_lcp 988-1010,
+//    finality probe 1164-1174), built EAGERLY here over every reachable state x byte, including the
+//    reference's observable quirks: the output string is shared down the preferred branch and only
+//    copied afterwards (874-891), and a CONS(0) state counts as accepting in the probe (893-897).
+//  * NFT flavour: trre's backtracking DFS (trre_nft.c:593-657) turned into a priority-ordered
+//    subset construction (leftmost-first, like a Pike VM whose thread list order is the DFS order),
+//    with delayed output per item and longest-common-prefix extraction.  Not every transducer is
+//    subsequential; when the construction does not converge within the limits the program falls
+//    back to TRRE_EXEC_BACKTRACK (the DFS itself, on the GPU).
+#include "automaton.hpp"
+
+#include <algorithm>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <map>
+#include <unordered_map>
+
+#include "../../include/trre_b200.h"
+
+namespace trre {
+namespace {
+
+constexpr int32_t IT_FINAL = -2;      // pseudo item: an accepting path is pending
+constexpr int32_t IT_DIVERGE = -3;    // pseudo item: the reference's DFS never returns from here
+
+struct Item {
+    int32_t q;
+    std::string w;                    // output produced on this path and not yet emitted
+};
+using ItemList = std::vector<Item>;
+
+struct RawEdge {
+    uint8_t  byte;
+    uint32_t next;
+    bool     mark;
+    uint32_t out_id;
+};
+struct RawState {
+    ItemList items;
+    uint32_t flags = 0;
+    uint32_t fin_id = 0;
+    std::vector<RawEdge> edges;
+};
+
+struct NotSubsequential { const char *why; };
+
+class StringPool {
+  public:
+    StringPool() { intern(std::string()); }
+    uint32_t intern(const std::string &s) {
+        auto it = ids_.find(s);
+        if (it != ids_.end()) return it->second;
+        uint32_t id = (uint32_t)strs_.size();
+        strs_.push_back(s);
+        ids_.emplace(s, id);
+        return id;
+    }
+    const std::string &get(uint32_t id) const { return strs_[id]; }
+    size_t count() const { return strs_.size(); }
+
+  private:
+    std::vector<std::string> strs_;
+    std::unordered_map<std::string, uint32_t> ids_;
+};
+
+std::string key_of(const ItemList &l) {
+    std::string k;
+    k.reserve(l.size() * 8);
+    for (const Item &it : l) {
+        uint32_t q = (uint32_t)it.q, n = (uint32_t)it.w.size();
+        k.append(reinterpret_cast<const char *>(&q), 4);
+        k.append(reinterpret_cast<const char *>(&n), 4);
+        k.append(it.w);
+    }
+    return k;
+}
+
+// moves the longest common prefix of all residuals into `prefix` (trre_dft.c:988-1010)
+void strip_lcp(ItemList &l, std::string &prefix) {
+    size_t first = 0;
+    while (first < l.size() && l[first].q == IT_DIVERGE) ++first;   // its output is never printed
+    if (first == l.size()) return;
+    size_t n = l[first].w.size();
+    for (const Item &it : l) {
+        if (it.q == IT_DIVERGE) continue;
+        size_t k = 0, lim = std::min(n, it.w.size());
+        while (k < lim && it.w[k] == l[first].w[k]) ++k;
+        n = k;
+        if (!n) return;
+    }
+    prefix.assign(l[first].w, 0, n);
+    for (Item &it : l)
+        if (it.q != IT_DIVERGE) it.w.erase(0, n);
+}
+
+class Determinizer {
+  public:
+    Determinizer(const Nft &g, int flavor, const CompileLimits &lim, StringPool &pool)
+        : g_(g), flavor_(flavor), lim_(lim), pool_(pool), stamp_(g.st.size(), 0), gray_(g.st.size(), 0) {}
+
+    std::vector<RawState> states;
+
+    void run() {
+        ItemList init;
+        uint32_t flags0 = 0;
+        if (flavor_ == TRRE_FLAVOR_DFT) {
+            // dstart = {(init JOIN, "")}; its `final` stays -1 for ever, so the start
+            // state is never accepting and an empty match cannot happen.
+            init.push_back(Item{g_.start, std::string()});
+        } else {
+            begin_step();
+            close_nft(g_.start);
+            init = std::move(cur_);
+            flags0 = flags_of(init);
+        }
+        add_state(std::move(init), flags0);
+        for (uint32_t s = 0; s < states.size(); ++s) {
+            if (states[s].flags & DSA_S_DECIDED) continue;       // the attempt ends here
+            if (flavor_ == TRRE_FLAVOR_DFT) expand_dft(s); else expand_nft(s);
+        }
+    }
+
+  private:
+    const Nft &g_;
+    int flavor_;
+    const CompileLimits &lim_;
+    StringPool &pool_;
+    std::unordered_map<std::string, uint32_t> index_;
+
+    // scratch of one closure step
+    std::vector<uint32_t> stamp_;
+    std::vector<uint8_t> gray_;
+    uint32_t gen_ = 0;
+    ItemList cur_;
+    std::string wbuf_;
+    bool cut_ = false, born_final_ = false;
+    int depth_ = 0;
+
+    // host memory the construction may take before it is declared non-convergent
+    uint64_t spent_ = 0;
+    uint64_t work_ = 0;
+    void tick() { if (++work_ > lim_.max_work) throw NotSubsequential{"work limit"}; }
+    void charge(uint64_t bytes) {
+        spent_ += bytes;
+        if (spent_ > lim_.max_build_bytes) throw NotSubsequential{"memory limit"};
+    }
+
+    void begin_step() {
+        ++gen_;
+        cur_.clear();
+        wbuf_.clear();
+        cut_ = born_final_ = false;
+    }
+
+    static uint32_t flags_of(const ItemList &l) {
+        uint32_t f = 0;
+        if (!l.empty() && l.back().q == IT_FINAL) f |= DSA_S_HAS_FINAL;
+        if (!l.empty() && l.back().q == IT_DIVERGE) f |= DSA_S_DIVERGE;
+        if (f && l.size() == 1) f |= DSA_S_DECIDED;
+        return f;
+    }
+
+    uint32_t add_state(ItemList &&l, uint32_t flags) {
+        std::string key = key_of(l);
+        auto it = index_.find(key);
+        if (it != index_.end()) return it->second;
+        if (states.size() >= lim_.max_states) throw NotSubsequential{"state limit"};
+        charge(key.size() + 64 + l.size() * sizeof(Item));
+        uint32_t id = (uint32_t)states.size();
+        RawState rs;
+        rs.flags = flags;
+        if (flags & DSA_S_HAS_FINAL) rs.fin_id = pool_.intern(l.back().w);
+        rs.items = std::move(l);
+        states.push_back(std::move(rs));
+        index_.emplace(std::move(key), id);
+        return id;
+    }
+
+    struct DepthGuard {
+        Determinizer &d;
+        explicit DepthGuard(Determinizer &dd) : d(dd) {
+            if (++d.depth_ > d.lim_.max_recursion)
+                throw PatternError{TRRE_E_UNSUPPORTED, "error: expression nests too deeply for the table builder\n"};
+        }
+        ~DepthGuard() { --d.depth_; }
+    };
+
+    // ---- NFT flavour ---------------------------------------------------------------------
+
+    // epsilon closure in DFS priority order (the order infer_backtrack explores, trre_nft.c:610-650)
+    void close_nft(int32_t s) {
+        if (s < 0 || cut_) return;
+        if (gray_[s]) {                                   // epsilon cycle on the current DFS path: the
+            cur_.push_back(Item{IT_DIVERGE, std::string()});   // reference pushes for ever (stack cap)
+            cut_ = true;
+            return;
+        }
+        if (stamp_[s] == gen_) return;                    // reached before with higher priority
+        stamp_[s] = gen_;
+        tick();
+        DepthGuard guard(*this);
+        const NftState &n = g_.st[s];
+        switch (n.op) {
+            case N_CONS:
+                cur_.push_back(Item{s, wbuf_});
+                return;
+            case N_FINAL:
+                cur_.push_back(Item{IT_FINAL, wbuf_});
+                cut_ = born_final_ = true;                // everything after it has lower priority
+                return;
+            default: break;
+        }
+        gray_[s] = 1;
+        switch (n.op) {
+            case N_PROD: {
+                size_t keep = wbuf_.size();
+                if (keep >= lim_.max_residual) throw NotSubsequential{"residual limit"};
+                wbuf_.push_back((char)n.val);
+                close_nft(n.a);
+                wbuf_.resize(keep);
+                break;
+            }
+            case N_JOIN:    close_nft(n.a); break;
+            case N_SPLIT:   close_nft(n.b); close_nft(n.a); break;
+            case N_SPLITNG: close_nft(n.a); close_nft(n.b); break;
+            default: break;
+        }
+        gray_[s] = 0;
+    }
+
+    void expand_nft(uint32_t sid) {
+        const ItemList items = states[sid].items;         // copy: `states` reallocates while we add
+        std::vector<std::vector<uint32_t>> by_byte(256);
+        bool pending = false;
+        for (uint32_t k = 0; k < items.size(); ++k) {
+            if (items[k].q >= 0) by_byte[g_.st[items[k].q].val].push_back(k); else pending = true;
+        }
+        uint32_t idle_next = 0, idle_out = 0;
+        bool idle_done = false;
+        for (int c = 1; c < 256; ++c) {
+            if (c == '\n') continue;                      // neither byte can occur inside a payload
+            const bool live = !by_byte[c].empty();
+            if (!live && !pending) continue;              // dead
+            if (!live && idle_done) {                     // only the pending item survives: same result
+                states[sid].edges.push_back(RawEdge{(uint8_t)c, idle_next, false, idle_out});
+                charge(sizeof(RawEdge));
+                continue;
+            }
+            begin_step();
+            for (uint32_t k : by_byte[c]) {               // in list (= priority) order
+                if (cut_) break;
+                wbuf_ = items[k].w;
+                close_nft(g_.st[items[k].q].a);
+            }
+            if (pending && !cut_) cur_.push_back(items.back());   // FINAL / DIVERGE persist and stay last
+            if (cur_.empty()) continue;
+            bool mark = born_final_;
+            std::string out;
+            strip_lcp(cur_, out);
+            for (const Item &it : cur_)
+                if (it.w.size() > lim_.max_residual) throw NotSubsequential{"residual limit"};
+            uint32_t flags = flags_of(cur_);
+            ItemList next = std::move(cur_);
+            cur_ = ItemList();
+            uint32_t nid = add_state(std::move(next), flags);
+            uint32_t oid = pool_.intern(out);
+            states[sid].edges.push_back(RawEdge{(uint8_t)c, nid, mark, oid});
+            charge(sizeof(RawEdge));
+            if (!live) { idle_done = true; idle_next = nid; idle_out = oid; }
+        }
+    }
+
+    // ---- DFT flavour -----------------------------------------------------------------------
+
+    struct Arrival { int32_t q; std::string w; };
+    std::vector<Arrival> arrivals_;                       // first arrival per CONS / FINAL state, in order
+
+    // nft_step_() for all bytes at once: `visited` is only ever set on the state that matches the
+    // step's byte, and a CONS state has exactly one byte, so "first arrival per state" is the same
+    // for every byte.  `o` is passed BY REFERENCE down the preferred branch and copied afterwards -
+    // the reference's aliasing (trre_dft.c:879-891), which changes the emitted bytes when a PROD
+    // sits on a dead preferred path.
+    void close_dft(int32_t s, std::string &o) {
+        if (s < 0) return;
+        tick();
+        DepthGuard guard(*this);
+        const NftState &n = g_.st[s];
+        switch (n.op) {
+            case N_SPLIT:   { close_dft(n.b, o); std::string o2 = o; close_dft(n.a, o2); break; }
+            case N_SPLITNG: { close_dft(n.a, o); std::string o2 = o; close_dft(n.b, o2); break; }
+            case N_JOIN:    close_dft(n.a, o); break;
+            case N_PROD:
+                if (o.size() >= lim_.max_residual) throw NotSubsequential{"residual limit"};
+                o.push_back((char)n.val);
+                close_dft(n.a, o);
+                break;
+            case N_CONS:
+            case N_FINAL:
+                if (stamp_[s] != gen_) { stamp_[s] = gen_; arrivals_.push_back(Arrival{s, o}); }
+                break;
+        }
+    }
+
+    void expand_dft(uint32_t sid) {
+        ++gen_;
+        arrivals_.clear();
+        {
+            const ItemList items = states[sid].items;
+            for (const Item &it : items) {
+                std::string o = it.w;
+                close_dft(g_.st[it.q].a, o);
+            }
+        }
+        // finality of THIS state = probe with c == 0: first arrival that is FINAL or CONS(0)
+        // (trre_dft.c:1164-1174).  The start state is never probed.
+        if (sid != 0) {
+            for (const Arrival &a : arrivals_) {
+                const NftState &n = g_.st[a.q];
+                if (n.op == N_FINAL || (n.op == N_CONS && n.val == 0)) {
+                    states[sid].flags = DSA_S_HAS_FINAL | DSA_S_DECIDED;
+                    states[sid].fin_id = pool_.intern(a.w);
+                    break;
+                }
+            }
+            if (states[sid].flags & DSA_S_DECIDED) return;   // infer_dft returns at the first final state
+        }
+        std::vector<std::vector<uint32_t>> by_byte(256);
+        for (uint32_t k = 0; k < arrivals_.size(); ++k) {
+            const NftState &n = g_.st[arrivals_[k].q];
+            if (n.op == N_CONS) by_byte[n.val].push_back(k);
+        }
+        std::vector<Arrival> arr = std::move(arrivals_);
+        arrivals_ = std::vector<Arrival>();
+        for (int c = 1; c < 256; ++c) {
+            if (c == '\n' || by_byte[c].empty()) continue;
+            ItemList next;
+            for (uint32_t k : by_byte[c]) next.push_back(Item{arr[k].q, arr[k].w});
+            std::string out;
+            strip_lcp(next, out);
+            uint32_t nid = add_state(std::move(next), 0);
+            states[sid].edges.push_back(RawEdge{(uint8_t)c, nid, false, pool_.intern(out)});
+            charge(sizeof(RawEdge));
+        }
+    }
+};
+
+// ------------------------------------------------------------------------------------------------
+
+struct Program {
+    int flavor = 0;
+    uint32_t exec_kind = TRRE_EXEC_TABLE;
+    uint32_t flags = 0;
+    uint32_t max_depth = 0;
+    uint32_t n_classes = 1;
+    uint8_t classmap[256];
+    uint8_t lut[256];
+    uint8_t startrow[256];
+    std::vector<uint64_t> trans;
+    std::vector<uint64_t> sinfo;
+    std::vector<uint8_t> pool;
+};
+
+class PoolWriter {
+  public:
+    explicit PoolWriter(const StringPool &sp) : sp_(sp), refs_(sp.count(), 0xFFFFFFFFu) {}
+    // -> hi word: off(24) | len(8)
+    uint32_t ref(uint32_t id) {
+        if (refs_[id] != 0xFFFFFFFFu) return refs_[id];
+        const std::string &s = sp_.get(id);
+        uint32_t r;
+        if (s.empty()) {
+            r = 0;
+        } else if (s.size() < 255) {
+            uint32_t off = place(s.data(), s.size());
+            r = off | ((uint32_t)s.size() << 24);
+        } else {
+            while (bytes.size() & 3) bytes.push_back(0);
+            uint32_t len = (uint32_t)s.size();
+            uint32_t off = (uint32_t)bytes.size();
+            bytes.insert(bytes.end(), reinterpret_cast<uint8_t *>(&len), reinterpret_cast<uint8_t *>(&len) + 4);
+            bytes.insert(bytes.end(), s.begin(), s.end());
+            r = off | (255u << 24);
+        }
+        if (bytes.size() >= (1u << 24)) throw NotSubsequential{"output pool limit"};
+        refs_[id] = r;
+        return r;
+    }
+    std::vector<uint8_t> bytes;
+
+  private:
+    const StringPool &sp_;
+    std::vector<uint32_t> refs_;
+    uint32_t place(const char *p, size_t n) {
+        uint32_t off = (uint32_t)bytes.size();
+        bytes.insert(bytes.end(), p, p + n);
+        return off;
+    }
+};
+
+void analyse_and_pack(const std::vector<RawState> &st, const StringPool &sp, int flavor,
+                      const CompileLimits &lim, Program &P) {
+    const uint32_t S = (uint32_t)st.size();
+    // ---- byte classes: bytes whose whole column (over all states) is identical ---------------
+    std::vector<std::vector<uint64_t>> col(256);
+    for (uint32_t s = 0; s < S; ++s)
+        for (const RawEdge &e : st[s].edges) {
+            col[e.byte].push_back(((uint64_t)s << 32) | e.next | (e.mark ? (uint32_t)DSA_E_MARK : 0u));
+            col[e.byte].push_back(e.out_id);
+        }
+    std::map<std::vector<uint64_t>, uint32_t> cls_of;
+    cls_of.emplace(std::vector<uint64_t>(), 0);            // class 0 = dead everywhere (incl. 0 and '\n')
+    for (int c = 0; c < 256; ++c) {
+        auto it = cls_of.find(col[c]);
+        if (it == cls_of.end()) it = cls_of.emplace(col[c], (uint32_t)cls_of.size()).first;
+        P.classmap[c] = (uint8_t)it->second;
+    }
+    if (cls_of.size() > 256) throw NotSubsequential{"class limit"};
+    P.n_classes = (uint32_t)cls_of.size();
+    if ((uint64_t)S * P.n_classes * 8 > lim.max_table_bytes) throw NotSubsequential{"table size limit"};
+
+    // ---- pack --------------------------------------------------------------------------------
+    PoolWriter pw(sp);
+    P.trans.assign((size_t)S * P.n_classes, pack64(DSA_DEAD, 0));
+    P.sinfo.resize(S);
+    for (uint32_t s = 0; s < S; ++s) {
+        P.sinfo[s] = pack64(st[s].flags, (st[s].flags & DSA_S_HAS_FINAL) ? pw.ref(st[s].fin_id) : 0);
+        for (const RawEdge &e : st[s].edges) {
+            // DFT flavour: the match ends where the walk reaches its first final state
+            const bool decided = (st[e.next].flags & DSA_S_DECIDED) != 0;
+            const bool mark = e.mark || (flavor == TRRE_FLAVOR_DFT && decided);
+            uint32_t lo = e.next | (mark ? (uint32_t)DSA_E_MARK : 0u) | (decided ? (uint32_t)DSA_E_DECIDED : 0u);
+            P.trans[(size_t)s * P.n_classes + P.classmap[e.byte]] = pack64(lo, pw.ref(e.out_id));
+        }
+    }
+    P.pool = std::move(pw.bytes);
+    while (P.pool.size() & 15) P.pool.push_back(0);
+    for (int c = 0; c < 256; ++c) P.startrow[c] = 0;
+    for (const RawEdge &e : st[0].edges) P.startrow[e.byte] = 1;
+
+    // ---- flags ---------------------------------------------------------------------------------
+    if (st[0].flags & DSA_S_HAS_FINAL) P.flags |= PF_CAN_MATCH_EMPTY;
+    for (uint32_t s = 0; s < S; ++s)
+        if (st[s].flags & DSA_S_DIVERGE) P.flags |= PF_HAS_DIVERGE;
+
+    // longest attempt / acyclicity: iterative DFS with colours over non-decided states
+    {
+        std::vector<uint8_t> colour(S, 0);
+        std::vector<uint32_t> depth(S, 0);
+        bool cyclic = false;
+        std::vector<std::pair<uint32_t, size_t>> stack;
+        stack.emplace_back(0u, 0u);
+        colour[0] = 1;
+        while (!stack.empty() && !cyclic) {
+            auto &top = stack.back();
+            uint32_t s = top.first;
+            if (top.second < st[s].edges.size()) {
+                uint32_t t = st[s].edges[top.second++].next;
+                if (colour[t] == 1) cyclic = true;
+                else if (colour[t] == 0) { colour[t] = 1; stack.emplace_back(t, 0u); }
+            } else {
+                uint32_t d = 0;
+                for (const RawEdge &e : st[s].edges) d = std::max(d, depth[e.next] + 1);
+                depth[s] = d;
+                colour[s] = 2;
+                stack.pop_back();
+            }
+        }
+        if (cyclic) P.max_depth = 0xFFFFFFFFu;
+        else { P.max_depth = depth[0]; P.flags |= PF_ACYCLIC; }
+    }
+
+    // length preservation: along every path |emitted| - consumed (bal) and consumed - match_end (lag)
+    // must be path independent, and every accepting outcome must emit exactly match_end bytes
+    {
+        const int64_t UNSET = INT64_MIN;
+        std::vector<int64_t> bal(S, UNSET), lag(S, UNSET);
+        bool lp = true;
+        std::vector<uint32_t> work;
+        bal[0] = 0;
+        lag[0] = 0;
+        work.push_back(0);
+        while (!work.empty() && lp) {
+            uint32_t s = work.back();
+            work.pop_back();
+            if (st[s].flags & DSA_S_HAS_FINAL) {
+                int64_t emitted_minus_i = bal[s] + (int64_t)sp.get(st[s].fin_id).size();
+                if (emitted_minus_i != -lag[s]) { lp = false; break; }
+            }
+            for (const RawEdge &e : st[s].edges) {
+                int64_t b = bal[s] + (int64_t)sp.get(e.out_id).size() - 1;
+                int64_t l = e.mark ? 0 : lag[s] + 1;
+                if (flavor == TRRE_FLAVOR_DFT) l = 0;          // the match ends where the walk ends
+                if (bal[e.next] == UNSET) { bal[e.next] = b; lag[e.next] = l; work.push_back(e.next); }
+                else if (bal[e.next] != b || ((st[e.next].flags & DSA_S_HAS_FINAL) && lag[e.next] != l)) { lp = false; break; }
+            }
+        }
+        if (lp) P.flags |= PF_LENGTH_PRESERVING;
+    }
+
+    // byte map: every attempt is decided by its first byte and emits exactly one byte
+    {
+        bool bm = !(st[0].flags & (DSA_S_HAS_FINAL | DSA_S_DIVERGE));
+        for (int c = 0; c < 256; ++c) P.lut[c] = (uint8_t)c;
+        for (const RawEdge &e : st[0].edges) {
+            if (!bm) break;
+            const RawState &t = st[e.next];
+            bool ok = (t.flags & DSA_S_DECIDED) && (t.flags & DSA_S_HAS_FINAL) &&
+                      (flavor == TRRE_FLAVOR_DFT || e.mark);
+            if (!ok) { bm = false; break; }
+            std::string o = sp.get(e.out_id) + sp.get(t.fin_id);
+            if (o.size() != 1) { bm = false; break; }
+            P.lut[e.byte] = (uint8_t)o[0];
+        }
+        if (bm && (P.flags & PF_LENGTH_PRESERVING)) P.exec_kind = TRRE_EXEC_BYTEMAP;
+    }
+}
+
+std::vector<uint8_t> assemble(const Program &P, const Nft &g) {
+    BlobHeader h;
+    std::memset(&h, 0, sizeof h);
+    auto align16 = [](size_t x) { return (x + 15) & ~(size_t)15; };
+    size_t off = align16(sizeof(BlobHeader));
+    h.off_classmap = (uint32_t)off; off += 256;
+    h.off_lut = (uint32_t)off; off += 256;
+    h.off_startrow = (uint32_t)off; off += 256;
+    off = align16(off);
+    h.off_trans = (uint32_t)off; off += P.trans.size() * 8; off = align16(off);
+    h.off_sinfo = (uint32_t)off; off += P.sinfo.size() * 8; off = align16(off);
+    h.off_pool = (uint32_t)off; off += P.pool.size(); off = align16(off);
+    h.off_nft = (uint32_t)off; off += g.st.size() * sizeof(NftFlat); off = align16(off);
+    if (off >= (1ull << 31)) throw PatternError{TRRE_E_UNSUPPORTED, "error: compiled tables exceed 2 GiB\n"};
+    h.magic = 0x32425254u;  // "TRB2"
+    h.abi = TRRE_B200_ABI_VERSION;
+    h.total_bytes = (uint32_t)off;
+    h.flavor = (uint32_t)P.flavor;
+    h.exec_kind = P.exec_kind;
+    h.flags = P.flags;
+    h.nft_states = (uint32_t)g.st.size();
+    h.nft_start = g.start;
+    h.dsa_states = (uint32_t)P.sinfo.size();
+    h.n_classes = P.n_classes;
+    h.max_depth = P.max_depth;
+    h.start_info = P.sinfo.empty() ? 0 : (uint32_t)(P.sinfo[0] & 0xFFFFFFFFu);
+    h.pool_bytes = (uint32_t)P.pool.size();
+    std::vector<uint8_t> blob(off, 0);
+    std::memcpy(blob.data(), &h, sizeof h);
+    std::memcpy(blob.data() + h.off_classmap, P.classmap, 256);
+    std::memcpy(blob.data() + h.off_lut, P.lut, 256);
+    std::memcpy(blob.data() + h.off_startrow, P.startrow, 256);
+    if (!P.trans.empty()) std::memcpy(blob.data() + h.off_trans, P.trans.data(), P.trans.size() * 8);
+    if (!P.sinfo.empty()) std::memcpy(blob.data() + h.off_sinfo, P.sinfo.data(), P.sinfo.size() * 8);
+    if (!P.pool.empty()) std::memcpy(blob.data() + h.off_pool, P.pool.data(), P.pool.size());
+    NftFlat *nf = reinterpret_cast<NftFlat *>(blob.data() + h.off_nft);
+    for (size_t k = 0; k < g.st.size(); ++k) {
+        nf[k].op = g.st[k].op; nf[k].val = g.st[k].val; nf[k].pad0 = nf[k].pad1 = 0;
+        nf[k].a = g.st[k].a; nf[k].b = g.st[k].b;
+    }
+    return blob;
+}
+
+}  // namespace
+
+std::vector<uint8_t> compile_to_blob(const char *expr, int flavor, const CompileLimits &lim) {
+    if (flavor != TRRE_FLAVOR_NFT && flavor != TRRE_FLAVOR_DFT)
+        throw PatternError{TRRE_E_ARG, "error: unknown flavor\n"};
+    SynTree tree = parse_expression(expr);
+    Nft g = build_nft(tree, flavor == TRRE_FLAVOR_DFT);
+
+    Program P;
+    P.flavor = flavor;
+    // can a produced NUL ever be printed?  CONS(0) and CONS('\n') never fire (the payload is a C string
+    // inside one getline record), so what lies behind them - e.g. the PROD(0) of `.` - is unreachable
+    bool nul_out = false;
+    {
+        std::vector<uint8_t> seen(g.st.size(), 0);
+        std::vector<int32_t> todo;
+        if (g.start >= 0) { todo.push_back(g.start); seen[g.start] = 1; }
+        while (!todo.empty()) {
+            int32_t s = todo.back();
+            todo.pop_back();
+            const NftState &n = g.st[s];
+            if (n.op == N_PROD && n.val == 0) nul_out = true;
+            if (n.op == N_CONS && (n.val == 0 || n.val == '\n')) continue;
+            for (int32_t t : {n.a, n.b})
+                if (t >= 0 && !seen[t]) { seen[t] = 1; todo.push_back(t); }
+        }
+    }
+    if (nul_out) P.flags |= PF_NUL_IN_OUTPUT;
+
+    bool tables = true;
+    // fputs() stops at a produced NUL (trre_nft.c:644-645): only the DFS executor models that
+    if (flavor == TRRE_FLAVOR_NFT && nul_out) tables = false;
+    if (tables) {
+        try {
+            StringPool sp;
+            Determinizer det(g, flavor, lim, sp);
+            det.run();
+            analyse_and_pack(det.states, sp, flavor, lim, P);
+        } catch (const PatternError &pe) {
+            if (flavor == TRRE_FLAVOR_DFT || pe.code != TRRE_E_UNSUPPORTED) throw;
+            tables = false;
+        } catch (const NotSubsequential &ns) {
+            if (std::getenv("TRRE_DEBUG")) std::fprintf(stderr, "trre_b200: table construction abandoned: %s\n", ns.why);
+            if (flavor == TRRE_FLAVOR_DFT)
+                throw PatternError{TRRE_E_UNSUPPORTED,
+                                   std::string("error: transducer is not determinizable within limits (") + ns.why +
+                                       "); trre_dft builds states for ever on such input\n"};
+            tables = false;
+        }
+    }
+    if (!tables) {
+        uint32_t keep = P.flags & PF_NUL_IN_OUTPUT;
+        P = Program();
+        P.flavor = flavor;
+        P.flags = keep;
+        P.exec_kind = TRRE_EXEC_BACKTRACK;
+        P.n_classes = 1;
+        for (int c = 0; c < 256; ++c) { P.classmap[c] = 0; P.lut[c] = (uint8_t)c; P.startrow[c] = 1; }
+        P.max_depth = 0xFFFFFFFFu;
+    }
+    return assemble(P, g);
+}
+
+bool blob_is_valid(const void *blob, size_t nbytes, std::string *why) {
+    auto bad = [&](const char *w) { if (why) *why = w; return false; };
+    if (!blob || nbytes < sizeof(BlobHeader)) return bad("blob too small");
+    BlobHeader h;
+    std::memcpy(&h, blob, sizeof h);
+    if (h.magic != 0x32425254u) return bad("bad magic");
+    if (h.abi != TRRE_B200_ABI_VERSION) return bad("ABI version mismatch");
+    if (h.total_bytes != nbytes) return bad("size mismatch");
+    uint64_t need_trans = (uint64_t)h.off_trans + (uint64_t)h.dsa_states * h.n_classes * 8;
+    uint64_t need_sinfo = (uint64_t)h.off_sinfo + (uint64_t)h.dsa_states * 8;
+    uint64_t need_nft = (uint64_t)h.off_nft + (uint64_t)h.nft_states * sizeof(NftFlat);
+    if (need_trans > nbytes || need_sinfo > nbytes || need_nft > nbytes ||
+        (uint64_t)h.off_pool + h.pool_bytes > nbytes || (uint64_t)h.off_startrow + 256 > nbytes)
+        return bad("section out of range");
+    return true;
+}
+
+}  // namespace trre

@@ -1,0 +1,99 @@
+// automaton.hpp - host side: flat NFT -> deterministic scan automaton (DSA) -> device blob.
+//
+// The DSA is the one table format both flavours are executed from on the GPU:
+//
+//   state s, byte class k -> entry { next | DEAD, mark, out-string }       (trans[s*ncls + k])
+//   state s               -> info  { HAS_FINAL, DECIDED, HAS_DIVERGE, fin-string }
+//
+// One scan ATTEMPT at input position p (what infer_dft / infer_backtrack compute per call):
+//
+//     s = start; i = 0; m = HAS_FINAL(start) ? 0 : none; acc = ""
+//     if DECIDED(start): emit fin(start); return 0
+//     loop: c = in[p+i]; stop at end of payload
+//           e = trans[s][class(c)]; stop if DEAD
+//           acc += out(e); s = next(e); i += 1; if mark(e): m = i
+//           if DECIDED(s): emit acc + fin(s); return m
+//     if HAS_FINAL(s): emit acc + fin(s); return m          // winner known once lookahead ended
+//     return FAIL
+//
+// DFT flavour (trre_dft semantics, leftmost-SHORTEST): a state is DECIDED as soon as it is final,
+// exactly infer_dft's "stop at the first final state" (trre_dft.c:1120-1125).
+// NFT flavour (trre semantics, leftmost-FIRST-by-priority): states are priority-ordered item lists;
+// a FINAL item cuts everything of lower priority, survives steps, and wins once every item of higher
+// priority has died; `mark` records where it was born (= bytes consumed by the match).
+#pragma once
+#include <cstdint>
+#include <string>
+#include <vector>
+
+#include "pattern.hpp"
+
+namespace trre {
+
+enum : uint32_t {
+    DSA_DEAD        = 0x00FFFFFFu,   // `next` value of a dead entry
+    DSA_E_MARK      = 1u << 24,      // entry: a FINAL item is born on this transition
+    DSA_E_DECIDED   = 1u << 25,      // entry: target state is DECIDED (attempt ends there)
+    DSA_S_HAS_FINAL = 1u,            // state: a FINAL item is pending in the list
+    DSA_S_DECIDED   = 2u,            // state: nothing of higher priority is alive any more
+    DSA_S_DIVERGE   = 4u             // state: an epsilon cycle is pending (reference: stack cap error)
+};
+
+// blob header flags
+enum : uint32_t {
+    PF_LENGTH_PRESERVING = 1u,
+    PF_CAN_MATCH_EMPTY   = 2u,
+    PF_ACYCLIC           = 4u,
+    PF_NUL_IN_OUTPUT     = 8u,       // some PROD byte is 0: NFT flavour truncates at it (fputs)
+    PF_HAS_DIVERGE       = 16u
+};
+
+struct BlobHeader {
+    uint32_t magic;            // 'TRB2'
+    uint32_t abi;
+    uint32_t total_bytes;
+    uint32_t flavor;
+    uint32_t exec_kind;        // TRRE_EXEC_*
+    uint32_t flags;            // PF_*
+    uint32_t nft_states;
+    int32_t  nft_start;
+    uint32_t dsa_states;
+    uint32_t n_classes;
+    uint32_t max_depth;        // 0xffffffff when cyclic
+    uint32_t start_info;       // DSA_S_* of state 0
+    uint32_t off_classmap;     // u8[256]
+    uint32_t off_lut;          // u8[256]   (TRRE_EXEC_BYTEMAP)
+    uint32_t off_startrow;     // u8[256]: 1 if an attempt starting with this byte is not immediately dead
+    uint32_t off_trans;        // u64[dsa_states * n_classes]
+    uint32_t off_sinfo;        // u64[dsa_states]
+    uint32_t off_pool;         // bytes
+    uint32_t pool_bytes;
+    uint32_t off_nft;          // NftFlat[nft_states]
+    uint32_t reserved[4];
+};
+
+struct NftFlat {               // 12 bytes, device layout of trre_nft.c:334-340
+    uint8_t op, val, pad0, pad1;
+    int32_t a, b;
+};
+
+// entry: lo = next | flags, hi = out_off(24) | out_len(8); out_len == 255 -> u32 length at pool[out_off]
+// sinfo: lo = DSA_S_* flags,  hi = fin_off(24) | fin_len(8), same escape
+static inline uint64_t pack64(uint32_t lo, uint32_t hi) { return (uint64_t)lo | ((uint64_t)hi << 32); }
+
+struct CompileLimits {
+    uint32_t max_states     = 1u << 16;
+    uint64_t max_build_bytes = 192ull << 20;   // host memory of the subset construction
+    uint32_t max_residual   = 4096;        // longest delayed output; beyond = not subsequential (twins)
+    uint64_t max_table_bytes = 128ull << 20;
+    uint64_t max_work       = 24ull * 1000 * 1000;   // closure visits of the subset construction
+    int      max_recursion  = 20000;
+};
+
+// Builds the whole program blob for `expr`.  Throws PatternError.
+std::vector<uint8_t> compile_to_blob(const char *expr, int flavor, const CompileLimits &lim = CompileLimits());
+
+// Validates a blob received from elsewhere (e.g. broadcast from rank 0).
+bool blob_is_valid(const void *blob, size_t nbytes, std::string *why);
+
+}  // namespace trre

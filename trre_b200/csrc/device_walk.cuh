@@ -1,0 +1,159 @@
+// device_walk.cuh - per-line executors shared by the line kernels (sm_100a).
+//
+// One "attempt" = what one call of infer_dft (trre_dft.c:1110-1196) or infer_backtrack
+// (trre_nft.c:593-657) does; one "line" = the per-record loop of the reference's scan drivers
+// (trre_nft.c:778-789 / trre_dft.c:1275-1285).
+#pragma once
+#include <cstdint>
+
+#include "automaton.hpp"
+
+namespace trre {
+
+// status word bits written by kernels
+enum : uint32_t {
+    ST_IRREGULAR   = 1u,    // fast path assumptions broken (NUL byte, no trailing '\n'): rerun generally
+    ST_DIVERGE     = 2u,    // an attempt entered an epsilon cycle (reference: stack max capacity)
+    ST_STACK       = 4u,    // DFS stack of the backtracking executor overflowed
+    ST_OBUF        = 8u,    // per-attempt output buffer of the backtracking executor overflowed
+    ST_NOSPACE     = 16u    // d_out too small
+};
+
+struct DevProg {
+    const uint8_t  *classmap;
+    const uint8_t  *lut;
+    const uint64_t *trans;
+    const uint64_t *sinfo;
+    const uint8_t  *pool;
+    const NftFlat  *nft;
+    uint32_t n_classes;
+    uint32_t start_info;
+    uint32_t flags;
+    int32_t  nft_start;
+};
+
+struct Sink {
+    uint8_t *p;         // nullptr: count only
+    size_t   n;
+    __device__ __forceinline__ void put(uint8_t b) { if (p) p[n] = b; ++n; }
+};
+
+__device__ __forceinline__ uint32_t ref_len(const uint8_t *pool, uint32_t hi) {
+    uint32_t len = hi >> 24;
+    if (len == 255u) len = *reinterpret_cast<const uint32_t *>(pool + (hi & 0xFFFFFFu));
+    return len;
+}
+
+__device__ __forceinline__ void put_ref(Sink &o, const uint8_t *pool, uint32_t hi) {
+    uint32_t len = hi >> 24, off = hi & 0xFFFFFFu;
+    if (len == 255u) { len = *reinterpret_cast<const uint32_t *>(pool + off); off += 4; }
+    if (o.p) for (uint32_t k = 0; k < len; ++k) o.p[o.n + k] = pool[off + k];
+    o.n += len;
+}
+
+// ---- table executor -----------------------------------------------------------------------------
+// Attempt at in[p..lim).  Returns bytes consumed (>=0) on a match, -1 on failure; output appended
+// to `o`.  Bytes 0 and '\n' are in the all-dead class, so the walk stops on them by itself.
+__device__ __forceinline__ long attempt_table(const DevProg &P, const uint8_t *__restrict__ in,
+                                              size_t p, size_t lim, Sink &o, uint32_t &status) {
+    uint32_t s = 0, i = 0, acc = 0;
+    long m = (P.start_info & DSA_S_HAS_FINAL) ? 0 : -1;
+    bool decided = (P.start_info & DSA_S_DECIDED) != 0;
+    if (!decided) {
+        while (p + i < lim) {
+            uint8_t c = __ldg(in + p + i);
+            uint64_t e = __ldg(P.trans + (size_t)s * P.n_classes + __ldg(P.classmap + c));
+            uint32_t lo = (uint32_t)e;
+            if ((lo & 0xFFFFFFu) == DSA_DEAD) break;
+            acc += ref_len(P.pool, (uint32_t)(e >> 32));
+            s = lo & 0xFFFFFFu;
+            ++i;
+            if (lo & DSA_E_MARK) m = i;
+            if (lo & DSA_E_DECIDED) { decided = true; break; }
+        }
+    }
+    uint64_t si = __ldg(P.sinfo + s);
+    uint32_t sf = (uint32_t)si;
+    if (sf & DSA_S_DIVERGE) {
+        // the walk only stops here when nothing of higher priority is left (decided, or end of
+        // payload): the reference's DFS is now inside the cycle and dies with "stack max capacity reached"
+        status |= ST_DIVERGE;
+        return -1;
+    }
+    if (!(sf & DSA_S_HAS_FINAL)) return -1;
+    // emit acc (replay the i transitions) + fin
+    if (o.p) {
+        uint32_t t = 0;
+        for (uint32_t k = 0; k < i; ++k) {
+            uint8_t c = __ldg(in + p + k);
+            uint64_t e = __ldg(P.trans + (size_t)t * P.n_classes + __ldg(P.classmap + c));
+            put_ref(o, P.pool, (uint32_t)(e >> 32));
+            t = (uint32_t)e & 0xFFFFFFu;
+        }
+    } else {
+        o.n += acc;
+    }
+    put_ref(o, P.pool, (uint32_t)(si >> 32));
+    return m;
+}
+
+// ---- backtracking executor (NFT flavour fallback) ---------------------------------------------------
+struct BtScratch {
+    int32_t  *stk_s;      // [cap]
+    uint32_t *stk_i;      // [cap]
+    uint32_t *stk_o;      // [cap]
+    uint8_t  *obuf;       // [ocap]
+    uint32_t  cap, ocap;
+};
+
+// priority DFS over the flat NFT from in[p..lim): first FINAL wins (trre_nft.c:598-655)
+__device__ __forceinline__ long attempt_backtrack(const DevProg &P, const BtScratch &B,
+                                                  const uint8_t *__restrict__ in, size_t p, size_t lim,
+                                                  Sink &o, uint32_t &status) {
+    uint32_t i = 0, w = 0, top = 0;
+    int32_t s = P.nft_start;
+    const uint32_t len = (uint32_t)(lim - p);
+    while (top || s >= 0) {
+        if (s < 0) {
+            --top;
+            s = B.stk_s[top]; i = B.stk_i[top]; w = B.stk_o[top];
+            if (s < 0) continue;
+        }
+        NftFlat n = P.nft[s];
+        switch (n.op) {
+            case N_CONS:
+                if (i < len) {
+                    uint8_t c = __ldg(in + p + i);
+                    if (c != 0 && c != '\n' && c == n.val) { ++i; s = n.a; break; }
+                }
+                s = -1;
+                break;
+            case N_PROD:
+                if (w >= B.ocap) { status |= ST_OBUF; return -1; }
+                B.obuf[w++] = n.val;
+                s = n.a;
+                break;
+            case N_SPLIT:
+            case N_SPLITNG:
+                if (top >= B.cap) { status |= ST_STACK; return -1; }
+                B.stk_s[top] = (n.op == N_SPLIT) ? n.a : n.b;
+                B.stk_i[top] = i; B.stk_o[top] = w; ++top;
+                s = (n.op == N_SPLIT) ? n.b : n.a;
+                break;
+            case N_JOIN:
+                s = n.a;
+                break;
+            default: {   // N_FINAL: fputs(output) prints up to the first produced NUL (trre_nft.c:644-645)
+                for (uint32_t k = 0; k < w; ++k) {
+                    uint8_t b = B.obuf[k];
+                    if (!b) break;
+                    o.put(b);
+                }
+                return (long)i;
+            }
+        }
+    }
+    return -1;
+}
+
+}  // namespace trre

@@ -1,0 +1,264 @@
+// kernels.cuh - sm_100a kernels of the scan path.
+//
+//  k_bytemap      TRRE_EXEC_BYTEMAP, regular input: out[i] = LUT[in[i]], 16-byte vector loads/stores,
+//                 LUT replicated per shared-memory bank (conflict-free), NUL / missing-final-newline
+//                 detection folded in (raises ST_IRREGULAR -> the general path reruns the buffer).
+//  k_lines        every other case: one 128-byte input chunk per thread, the thread owns the lines
+//                 that START in its chunk and runs the reference's per-line driver on them
+//                 (table executor or DFS executor), in one of three modes:
+//                   MODE_INPLACE  length-preserving program + regular input: out offset == in offset
+//                   MODE_COUNT    output bytes per chunk  -> cnt[], per-group sums -> gsum[]
+//                   MODE_WRITE    offsets = scan(gsum)[group] + block-scan(cnt) ; write
+//  k_scan_groups  exclusive scan of the per-group sums (single CTA) + grand total.
+#pragma once
+#include <cstdint>
+
+#include "device_walk.cuh"
+
+namespace trre {
+
+constexpr int kChunk = 128;            // input bytes per thread in k_lines
+constexpr int kLineThreads = 256;      // threads per CTA in k_lines = chunks per group
+
+// ------------------------------------------------------------------------------------------------
+// k_bytemap
+// ------------------------------------------------------------------------------------------------
+constexpr int kBmThreads = 512;
+constexpr int kBmUnroll = 4;           // 16-byte vectors in flight per thread
+
+__device__ __forceinline__ uint4 ld_stream(const uint4 *p) {
+    uint4 r;
+    asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0,%1,%2,%3}, [%4];"
+                 : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "l"(p));
+    return r;
+}
+__device__ __forceinline__ void st_stream(uint4 *p, const uint4 &v) {
+    asm volatile("st.global.L1::no_allocate.v4.u32 [%0], {%1,%2,%3,%4};"
+                 :: "l"(p), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
+}
+
+// tab[c*32 + lane] holds LUT[c] in all four byte lanes: lane L only ever touches bank L
+__device__ __forceinline__ uint32_t map_word(uint32_t w, const uint32_t *tab_lane, uint32_t &nul) {
+    uint32_t r0 = tab_lane[(w & 0xFFu) << 5];
+    uint32_t r1 = tab_lane[((w >> 8) & 0xFFu) << 5];
+    uint32_t r2 = tab_lane[((w >> 16) & 0xFFu) << 5];
+    uint32_t r3 = tab_lane[(w >> 24) << 5];
+    nul |= (w - 0x01010101u) & ~w & 0x80808080u;         // any zero byte in w
+    uint32_t lo = __byte_perm(r0, r1, 0x0040);            // bytes: r0.b0, r1.b0
+    uint32_t hi = __byte_perm(r2, r3, 0x0040);
+    return __byte_perm(lo, hi, 0x5410);
+}
+
+__global__ void __launch_bounds__(kBmThreads)
+k_bytemap(const uint8_t *__restrict__ in, uint8_t *__restrict__ out, size_t n,
+          const uint8_t *__restrict__ lut, uint32_t *__restrict__ status) {
+    extern __shared__ uint32_t tab[];                     // 256 * 32 words = 32 KB
+    for (int k = threadIdx.x; k < 256 * 32; k += blockDim.x)
+        tab[k] = 0x01010101u * (uint32_t)lut[k >> 5];
+    __syncthreads();
+    const uint32_t *tab_lane = tab + (threadIdx.x & 31);
+    uint32_t nul = 0;
+
+    // the vector body needs in and out equally misaligned; the host guarantees (in ^ out) % 16 == 0
+    size_t head = ((16 - (reinterpret_cast<uintptr_t>(in) & 15)) & 15);
+    if (head > n) head = n;
+    const size_t nvec = (n - head) / 16;
+    const uint4 *vin = reinterpret_cast<const uint4 *>(in + head);
+    uint4 *vout = reinterpret_cast<uint4 *>(out + head);
+
+    const size_t stride = (size_t)gridDim.x * blockDim.x;
+    size_t v = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    // main loop: kBmUnroll independent 16-byte loads in flight per thread
+    for (; v + (kBmUnroll - 1) * stride < nvec; v += kBmUnroll * stride) {
+        uint4 x[kBmUnroll];
+#pragma unroll
+        for (int u = 0; u < kBmUnroll; ++u) x[u] = ld_stream(vin + v + u * stride);
+#pragma unroll
+        for (int u = 0; u < kBmUnroll; ++u) {
+            uint4 y;
+            y.x = map_word(x[u].x, tab_lane, nul);
+            y.y = map_word(x[u].y, tab_lane, nul);
+            y.z = map_word(x[u].z, tab_lane, nul);
+            y.w = map_word(x[u].w, tab_lane, nul);
+            st_stream(vout + v + u * stride, y);
+        }
+    }
+    for (; v < nvec; v += stride) {
+        uint4 x = ld_stream(vin + v), y;
+        y.x = map_word(x.x, tab_lane, nul);
+        y.y = map_word(x.y, tab_lane, nul);
+        y.z = map_word(x.z, tab_lane, nul);
+        y.w = map_word(x.w, tab_lane, nul);
+        st_stream(vout + v, y);
+    }
+    // ragged head and tail: one thread, byte by byte
+    if (blockIdx.x == 0 && threadIdx.x == 0) {
+        for (size_t k = 0; k < head; ++k) { uint8_t c = in[k]; if (!c) nul = 1; out[k] = lut[c]; }
+        for (size_t k = head + nvec * 16; k < n; ++k) { uint8_t c = in[k]; if (!c) nul = 1; out[k] = lut[c]; }
+        if (n && in[n - 1] != '\n') nul = 1;              // last record would lose its last byte
+    }
+    if (__any_sync(0xFFFFFFFFu, nul != 0)) {
+        if ((threadIdx.x & 31) == 0) atomicOr(status, ST_IRREGULAR);
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// k_lines
+// ------------------------------------------------------------------------------------------------
+enum { MODE_INPLACE = 0, MODE_COUNT = 1, MODE_WRITE = 2 };
+
+struct LineArgs {
+    DevProg P;
+    const uint8_t *in;
+    uint8_t *out;
+    size_t n;
+    size_t out_cap;
+    uint32_t *cnt;               // [n_chunks]  output bytes of the lines starting in chunk
+    unsigned long long *gsum;    // [n_groups]  after k_scan_groups: exclusive offsets
+    unsigned long long *total;   // grand total of output bytes
+    uint32_t *status;
+    size_t n_chunks;
+    size_t n_groups;
+    uint32_t gate;               // != 0: run only if (*status & gate)
+    // DFS executor scratch, indexed by resident thread
+    int32_t *bt_s; uint32_t *bt_i; uint32_t *bt_o; uint8_t *bt_obuf;
+    uint32_t bt_cap, bt_ocap;
+};
+
+// The per-record loop of the reference's scan drivers (trre_nft.c:778-789 / trre_dft.c:1275-1285)
+// for the record whose payload starts at `p`; `lim` = end of all payload bytes of the buffer (n, or
+// n-1 when the buffer does not end in '\n': getline's last record loses its last byte).
+// Returns the position just past the record.
+template <bool BACKTRACK>
+__device__ __forceinline__ size_t run_record(const DevProg &P, const BtScratch &B, const uint8_t *__restrict__ in,
+                                             size_t p, size_t lim, size_t n, Sink &o, uint32_t &status) {
+    for (;;) {
+        bool at_end = true;
+        uint8_t c = 0;
+        if (p < lim) { c = __ldg(in + p); at_end = (c == 0 || c == '\n'); }
+        long k = BACKTRACK ? attempt_backtrack(P, B, in, p, lim, o, status)
+                           : attempt_table(P, in, p, lim, o, status);
+        if (at_end) break;                                // that was the attempt on the empty tail
+        if (k > 0) p += (size_t)k;
+        else { o.put(c); ++p; }                           // no match or empty match: copy one raw byte
+    }
+    o.put('\n');
+    // skip what getline would still have consumed: the rest of the record after a NUL, and the '\n'
+    while (p < n && __ldg(in + p) != '\n') ++p;
+    return p + 1;
+}
+
+template <int MODE, bool BACKTRACK>
+__global__ void __launch_bounds__(kLineThreads)
+k_lines(LineArgs a) {
+    if (a.gate && !(*a.status & a.gate)) return;
+    __shared__ unsigned long long warp_sums[kLineThreads / 32];
+    __shared__ unsigned long long group_base;
+    const uint8_t *__restrict__ in = a.in;
+    const size_t n = a.n;
+    if (n == 0) return;
+    const bool ends_nl = __ldg(in + n - 1) == '\n';
+    const size_t lim = ends_nl ? n : n - 1;
+    if (MODE == MODE_WRITE && *a.total > a.out_cap) {
+        if (threadIdx.x == 0 && blockIdx.x == 0) atomicOr(a.status, ST_NOSPACE);
+        return;
+    }
+    BtScratch B;
+    if (BACKTRACK) {
+        size_t slot = (size_t)blockIdx.x * kLineThreads + threadIdx.x;
+        B.stk_s = a.bt_s + slot * a.bt_cap; B.stk_i = a.bt_i + slot * a.bt_cap; B.stk_o = a.bt_o + slot * a.bt_cap;
+        B.obuf = a.bt_obuf + slot * a.bt_ocap; B.cap = a.bt_cap; B.ocap = a.bt_ocap;
+    }
+    uint32_t status = 0;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+
+    for (size_t g = blockIdx.x; g < a.n_groups; g += gridDim.x) {
+        const size_t chunk = g * kLineThreads + threadIdx.x;
+        const size_t cbeg = chunk * (size_t)kChunk;
+        const size_t cend = (cbeg + kChunk < n) ? cbeg + kChunk : n;
+        unsigned long long my_off = 0;
+        if (MODE == MODE_WRITE) {
+            // exclusive scan of this group's chunk counts -> where this thread's lines go
+            unsigned long long v = (chunk < a.n_chunks) ? a.cnt[chunk] : 0, x = v;
+#pragma unroll
+            for (int d = 1; d < 32; d <<= 1) {
+                unsigned long long y = __shfl_up_sync(0xFFFFFFFFu, x, d);
+                if (lane >= d) x += y;
+            }
+            __syncthreads();                              // previous iteration's readers are done
+            if (lane == 31) warp_sums[warp] = x;
+            if (threadIdx.x == 0) group_base = a.gsum[g];
+            __syncthreads();
+            unsigned long long wbase = 0;
+            for (int w = 0; w < warp; ++w) wbase += warp_sums[w];
+            my_off = group_base + wbase + x - v;
+        }
+        Sink o;
+        o.p = (MODE == MODE_COUNT) ? nullptr : a.out;
+        o.n = (size_t)my_off;
+        size_t produced = 0;
+        if (cbeg < n) {
+            // find the first record starting in [cbeg, cend)
+            size_t p = cbeg;
+            if (p != 0 && __ldg(in + p - 1) != '\n') {
+                while (p < cend && __ldg(in + p) != '\n') ++p;
+                ++p;                                      // first byte after that '\n' (may be >= cend)
+            }
+            while (p < cend) {                            // p < n here: a record starts at p
+                if (MODE == MODE_INPLACE) o.n = p;
+                size_t before = o.n;
+                p = run_record<BACKTRACK>(a.P, B, in, p, lim, n, o, status);
+                produced += o.n - before;
+                if (MODE == MODE_INPLACE && o.n != p) status |= ST_IRREGULAR;   // a NUL cut the line short
+            }
+        }
+        if (MODE == MODE_COUNT) {
+            if (chunk < a.n_chunks) a.cnt[chunk] = (uint32_t)produced;
+            if (produced > 0xFFFFFFFFull) status |= ST_NOSPACE;   // > 4 GiB from one chunk's lines
+            unsigned long long x = produced;
+#pragma unroll
+            for (int d = 16; d; d >>= 1) x += __shfl_xor_sync(0xFFFFFFFFu, x, d);
+            __syncthreads();
+            if (lane == 0) warp_sums[warp] = x;
+            __syncthreads();
+            if (threadIdx.x == 0) {
+                unsigned long long s = 0;
+                for (int w = 0; w < kLineThreads / 32; ++w) s += warp_sums[w];
+                a.gsum[g] = s;
+            }
+        }
+    }
+    if (MODE == MODE_INPLACE && !ends_nl) status |= ST_IRREGULAR;
+    if (status) atomicOr(a.status, status);
+}
+
+// ------------------------------------------------------------------------------------------------
+// k_scan_groups: gsum[] -> exclusive prefix sums in place, *total = sum.  One CTA.
+// ------------------------------------------------------------------------------------------------
+constexpr int kScanThreads = 1024;
+
+__global__ void __launch_bounds__(kScanThreads)
+k_scan_groups(unsigned long long *gsum, size_t n_groups, unsigned long long *total,
+              const uint32_t *status, uint32_t gate) {
+    if (gate && !(*status & gate)) return;
+    __shared__ unsigned long long part[kScanThreads];
+    const size_t per = (n_groups + kScanThreads - 1) / kScanThreads;
+    const size_t b = (size_t)threadIdx.x * per;
+    const size_t e = (b + per < n_groups) ? b + per : n_groups;
+    unsigned long long s = 0;
+    for (size_t k = b; k < e; ++k) s += gsum[k];
+    part[threadIdx.x] = s;
+    __syncthreads();
+    // Hillis-Steele over 1024 partials
+    for (int d = 1; d < kScanThreads; d <<= 1) {
+        unsigned long long y = (threadIdx.x >= d) ? part[threadIdx.x - d] : 0;
+        __syncthreads();
+        part[threadIdx.x] += y;
+        __syncthreads();
+    }
+    unsigned long long run = part[threadIdx.x] - s;       // exclusive
+    for (size_t k = b; k < e; ++k) { unsigned long long v = gsum[k]; gsum[k] = run; run += v; }
+    if (threadIdx.x == kScanThreads - 1) *total = part[kScanThreads - 1];
+}
+
+}  // namespace trre
