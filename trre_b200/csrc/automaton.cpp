@@ -532,7 +532,8 @@ std::vector<uint8_t> assemble(const Program &P, const Nft &g) {
     h.off_trans = (uint32_t)off; off += P.trans.size() * 8; off = align16(off);
     h.off_sinfo = (uint32_t)off; off += P.sinfo.size() * 8; off = align16(off);
     h.off_pool = (uint32_t)off; off += P.pool.size(); off = align16(off);
-    h.off_nft = (uint32_t)off; off += g.st.size() * sizeof(NftFlat); off = align16(off);
+    h.off_nft = (uint32_t)off; off += g.st.size() * sizeof(NftFlat); off = (off + 127) & ~(size_t)127;
+    if (P.exec_kind == TRRE_EXEC_BYTEMAP) { h.off_pairlut = (uint32_t)off; off += 65536 * 2; }
     if (off >= (1ull << 31)) throw PatternError{TRRE_E_UNSUPPORTED, "error: compiled tables exceed 2 GiB\n"};
     h.magic = 0x32425254u;  // "TRB2"
     h.abi = TRRE_B200_ABI_VERSION;
@@ -559,6 +560,12 @@ std::vector<uint8_t> assemble(const Program &P, const Nft &g) {
     for (size_t k = 0; k < g.st.size(); ++k) {
         nf[k].op = g.st[k].op; nf[k].val = g.st[k].val; nf[k].pad0 = nf[k].pad1 = 0;
         nf[k].a = g.st[k].a; nf[k].b = g.st[k].b;
+    }
+    if (h.off_pairlut) {
+        // pair[c0 | c1 << 8] = LUT[c0] | LUT[c1] << 8 : one shared-memory lookup maps two input bytes
+        uint16_t *pair = reinterpret_cast<uint16_t *>(blob.data() + h.off_pairlut);
+        for (uint32_t v = 0; v < 65536; ++v)
+            pair[v] = (uint16_t)(P.lut[v & 0xFF] | ((uint32_t)P.lut[v >> 8] << 8));
     }
     return blob;
 }

@@ -69,7 +69,8 @@ struct BlobHeader {
     uint32_t off_pool;         // bytes
     uint32_t pool_bytes;
     uint32_t off_nft;          // NftFlat[nft_states]
-    uint32_t reserved[4];
+    uint32_t off_pairlut;      // u16[65536] (TRRE_EXEC_BYTEMAP): LUT applied to two bytes at once, 0 if absent
+    uint32_t reserved[3];
 };
 
 struct NftFlat {               // 12 bytes, device layout of trre_nft.c:334-340

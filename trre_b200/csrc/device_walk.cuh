@@ -22,6 +22,7 @@ enum : uint32_t {
 struct DevProg {
     const uint8_t  *classmap;
     const uint8_t  *lut;
+    const uint16_t *pairlut;       // TRRE_EXEC_BYTEMAP only
     const uint64_t *trans;
     const uint64_t *sinfo;
     const uint8_t  *pool;

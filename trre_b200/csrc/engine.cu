@@ -29,6 +29,8 @@ void set_err(char *err, size_t cap, const std::string &s) {
     }
 }
 
+constexpr int kSlots = 3;                 // pipelined host path: chunks in flight
+
 struct DeviceState {
     int device = -1;
     uint8_t *d_blob = nullptr;
@@ -37,18 +39,24 @@ struct DeviceState {
     uint32_t *d_cnt = nullptr; size_t cap_chunks = 0;
     unsigned long long *d_gsum = nullptr; size_t cap_groups = 0;
     unsigned long long *d_total = nullptr;
-    uint32_t *d_status = nullptr;
+    uint32_t *d_status = nullptr;          // [1 + kSlots]: [0] device-resident API, [1..] pipeline slots
     // pinned mirrors
     unsigned long long *h_total = nullptr;
-    uint32_t *h_status = nullptr;
+    uint32_t *h_status = nullptr;          // [1 + kSlots]
     // DFS scratch
     int32_t *bt_s = nullptr; uint32_t *bt_i = nullptr; uint32_t *bt_o = nullptr; uint8_t *bt_obuf = nullptr;
     size_t bt_threads = 0; uint32_t bt_cap = 0, bt_ocap = 0;
     int sm_count = 148;
-    // bookkeeping of the last enqueue
+    // what the last enqueue left to do / to report
     int launches = 0;
-    size_t last_n = 0;
-    bool last_fast = false;        // a fast path was tried; total = n unless ST_IRREGULAR
+    bool status_dirty = true;      // d_status[0] / d_total must be cleared before the next enqueue
+    bool pend_fast = false;        // only the fast path ran; total = n unless ST_IRREGULAR (then rerun generally)
+    const uint8_t *pend_in = nullptr; uint8_t *pend_out = nullptr; size_t pend_n = 0, pend_cap = 0;
+    // host-buffer path: cached device buffers
+    uint8_t *buf_in = nullptr, *buf_out = nullptr; size_t cap_in = 0, cap_out = 0;
+    uint8_t *slot_in[kSlots] = {nullptr, nullptr, nullptr}, *slot_out[kSlots] = {nullptr, nullptr, nullptr};
+    cudaStream_t slot_stream[kSlots] = {nullptr, nullptr, nullptr};
+    size_t slot_cap = 0;
 };
 
 }  // namespace
@@ -98,14 +106,15 @@ int get_state(const trre_prog *cp, int device, DeviceState **out) {
     CUDA_TRY(cudaMalloc(&d->d_blob, p->blob.size()));
     CUDA_TRY(cudaMemcpy(d->d_blob, p->blob.data(), p->blob.size(), cudaMemcpyHostToDevice));
     CUDA_TRY(cudaMalloc(&d->d_total, sizeof(unsigned long long)));
-    CUDA_TRY(cudaMalloc(&d->d_status, sizeof(uint32_t)));
+    CUDA_TRY(cudaMalloc(&d->d_status, (1 + kSlots) * sizeof(uint32_t)));
     CUDA_TRY(cudaMallocHost(&d->h_total, sizeof(unsigned long long)));
-    CUDA_TRY(cudaMallocHost(&d->h_status, sizeof(uint32_t)));
+    CUDA_TRY(cudaMallocHost(&d->h_status, (1 + kSlots) * sizeof(uint32_t)));
     cudaDeviceProp prop;
     CUDA_TRY(cudaGetDeviceProperties(&prop, device));
     d->sm_count = prop.multiProcessorCount;
     d->P.classmap = d->d_blob + h.off_classmap;
     d->P.lut = d->d_blob + h.off_lut;
+    d->P.pairlut = h.off_pairlut ? reinterpret_cast<const uint16_t *>(d->d_blob + h.off_pairlut) : nullptr;
     d->P.trans = reinterpret_cast<const uint64_t *>(d->d_blob + h.off_trans);
     d->P.sinfo = reinterpret_cast<const uint64_t *>(d->d_blob + h.off_sinfo);
     d->P.pool = d->d_blob + h.off_pool;
@@ -114,7 +123,7 @@ int get_state(const trre_prog *cp, int device, DeviceState **out) {
     d->P.start_info = h.start_info;
     d->P.flags = h.flags;
     d->P.nft_start = h.nft_start;
-    CUDA_TRY(cudaFuncSetAttribute(k_bytemap, cudaFuncAttributeMaxDynamicSharedMemorySize, 32 * 1024));
+    CUDA_TRY(cudaFuncSetAttribute(k_bytemap, cudaFuncAttributeMaxDynamicSharedMemorySize, kPairLutBytes));
     p->dev[device] = d;
     *out = d;
     return TRRE_OK;
@@ -154,61 +163,87 @@ void launch_lines(bool backtrack, int grid, cudaStream_t st, const LineArgs &a) 
     else k_lines<MODE, false><<<grid, kLineThreads, 0, st>>>(a);
 }
 
-// Enqueue one whole-buffer scan.  Never synchronises.
-int enqueue_scan(const trre_prog *p, DeviceState *d, const uint8_t *d_in, size_t n, uint8_t *d_out,
-                 size_t out_cap, cudaStream_t st, bool count_only_general) {
-    const BlobHeader &h = p->hdr;
-    d->launches = 0;
-    d->last_n = n;
-    d->last_fast = false;
-    CUDA_TRY(cudaMemsetAsync(d->d_status, 0, sizeof(uint32_t), st));
-    CUDA_TRY(cudaMemsetAsync(d->d_total, 0, sizeof(unsigned long long), st));
-    if (n == 0) return TRRE_OK;
-
-    const bool backtrack = h.exec_kind == TRRE_EXEC_BACKTRACK;
-    const size_t n_chunks = (n + kChunk - 1) / kChunk;
-    const size_t n_groups = (n_chunks + kLineThreads - 1) / kLineThreads;
-    // persistent-style grid: the DFS executor's scratch is per resident thread
-    int grid_lines = (int)std::min<size_t>(n_groups, backtrack ? (size_t)d->sm_count * 1 : (size_t)d->sm_count * 64);
-    if (grid_lines < 1) grid_lines = 1;
-    int rc = ensure_workspace(d, n_chunks, n_groups, backtrack, (size_t)grid_lines * kLineThreads);
-    if (rc != TRRE_OK) return rc;
-
+LineArgs make_args(DeviceState *d, const uint8_t *d_in, size_t n, uint8_t *d_out, size_t out_cap, uint32_t *status) {
     LineArgs a{};
     a.P = d->P; a.in = d_in; a.out = d_out; a.n = n; a.out_cap = out_cap;
-    a.cnt = d->d_cnt; a.gsum = d->d_gsum; a.total = d->d_total; a.status = d->d_status;
-    a.n_chunks = n_chunks; a.n_groups = n_groups; a.gate = 0;
+    a.cnt = d->d_cnt; a.gsum = d->d_gsum; a.total = d->d_total; a.status = status;
+    a.n_chunks = (n + kChunk - 1) / kChunk;
+    a.n_groups = (a.n_chunks + kLineThreads - 1) / kLineThreads;
+    a.gate = 0;
     a.bt_s = d->bt_s; a.bt_i = d->bt_i; a.bt_o = d->bt_o; a.bt_obuf = d->bt_obuf;
     a.bt_cap = d->bt_cap; a.bt_ocap = d->bt_ocap;
+    return a;
+}
 
-    uint32_t gate = 0;
-    const bool lp = (h.flags & PF_LENGTH_PRESERVING) && !backtrack;
+bool fast_capable(const BlobHeader &h) {
+    return (h.flags & PF_LENGTH_PRESERVING) && h.exec_kind != TRRE_EXEC_BACKTRACK;
+}
+
+// The length-preserving fast path on a regular buffer: ONE kernel, out offset == in offset.
+// Raises ST_IRREGULAR in *status when the buffer is not regular (NUL byte / no final newline).
+int launch_fast(const trre_prog *p, DeviceState *d, const uint8_t *d_in, size_t n, uint8_t *d_out,
+                uint32_t *status, cudaStream_t st) {
+    const BlobHeader &h = p->hdr;
     const bool aligned = ((reinterpret_cast<uintptr_t>(d_in) ^ reinterpret_cast<uintptr_t>(d_out)) & 15) == 0;
-    if (!count_only_general && lp && out_cap >= n) {
-        // fast paths assume a regular buffer (no NUL, ends in '\n'); they raise ST_IRREGULAR otherwise
-        if (h.exec_kind == TRRE_EXEC_BYTEMAP && aligned) {
-            size_t nvec = n / 16;
-            size_t want = (nvec + (size_t)kBmThreads * kBmUnroll - 1) / ((size_t)kBmThreads * kBmUnroll);
-            int grid = (int)std::min<size_t>(std::max<size_t>(want, 1), (size_t)d->sm_count * 4);
-            k_bytemap<<<grid, kBmThreads, 32 * 1024, st>>>(d_in, d_out, n, d->P.lut, d->d_status);
-        } else {
-            launch_lines<MODE_INPLACE>(false, grid_lines, st, a);
-        }
-        d->launches += 1;
-        d->last_fast = true;
-        gate = ST_IRREGULAR;
-    }
-    // general path: count -> scan -> write (gated behind ST_IRREGULAR after a fast path)
-    a.gate = gate;
-    launch_lines<MODE_COUNT>(backtrack, grid_lines, st, a);
-    k_scan_groups<<<1, kScanThreads, 0, st>>>(d->d_gsum, n_groups, d->d_total, d->d_status, gate);
-    d->launches += 2;
-    if (!count_only_general) {
-        launch_lines<MODE_WRITE>(backtrack, grid_lines, st, a);
-        d->launches += 1;
+    if (h.exec_kind == TRRE_EXEC_BYTEMAP && aligned && d->P.pairlut) {
+        k_bytemap<<<d->sm_count, kBmThreads, kPairLutBytes, st>>>(d_in, d_out, n, d->P.pairlut, d->P.lut, status);
+    } else {
+        LineArgs a = make_args(d, d_in, n, d_out, n, status);
+        int grid = (int)std::min<size_t>(a.n_groups, (size_t)d->sm_count * 64);
+        k_lines<MODE_INPLACE, false><<<grid, kLineThreads, 0, st>>>(a);
     }
     CUDA_TRY(cudaGetLastError());
     return TRRE_OK;
+}
+
+// The general path: count -> scan -> (write).  3 kernels (2 when only sizing).
+int launch_general(const trre_prog *p, DeviceState *d, const uint8_t *d_in, size_t n, uint8_t *d_out,
+                   size_t out_cap, cudaStream_t st, bool size_only, int *launches) {
+    const bool backtrack = p->hdr.exec_kind == TRRE_EXEC_BACKTRACK;
+    const size_t n_chunks = (n + kChunk - 1) / kChunk;
+    const size_t n_groups = (n_chunks + kLineThreads - 1) / kLineThreads;
+    // persistent-style grid: the DFS executor's scratch is per resident thread
+    int grid = (int)std::min<size_t>(n_groups, backtrack ? (size_t)d->sm_count : (size_t)d->sm_count * 64);
+    if (grid < 1) grid = 1;
+    int rc = ensure_workspace(d, n_chunks, n_groups, backtrack, (size_t)grid * kLineThreads);
+    if (rc != TRRE_OK) return rc;
+    LineArgs a = make_args(d, d_in, n, d_out, out_cap, d->d_status);
+    launch_lines<MODE_COUNT>(backtrack, grid, st, a);
+    k_scan_groups<<<1, kScanThreads, 0, st>>>(d->d_gsum, n_groups, d->d_total, d->d_status, 0);
+    *launches += 2;
+    if (!size_only) {
+        launch_lines<MODE_WRITE>(backtrack, grid, st, a);
+        *launches += 1;
+    }
+    CUDA_TRY(cudaGetLastError());
+    return TRRE_OK;
+}
+
+int clear_status(DeviceState *d, cudaStream_t st) {
+    CUDA_TRY(cudaMemsetAsync(d->d_status, 0, sizeof(uint32_t), st));
+    CUDA_TRY(cudaMemsetAsync(d->d_total, 0, sizeof(unsigned long long), st));
+    d->status_dirty = false;
+    return TRRE_OK;
+}
+
+// Enqueue one whole-buffer scan.  Never synchronises.  On a length-preserving program only the fast
+// kernel is enqueued; should it find the buffer irregular, collect() reruns it on the general path.
+int enqueue_scan(const trre_prog *p, DeviceState *d, const uint8_t *d_in, size_t n, uint8_t *d_out,
+                 size_t out_cap, cudaStream_t st, bool size_only) {
+    d->launches = 0;
+    d->pend_fast = false;
+    d->pend_in = d_in; d->pend_out = d_out; d->pend_n = n; d->pend_cap = out_cap;
+    if (d->status_dirty) { int rc = clear_status(d, st); if (rc != TRRE_OK) return rc; }
+    if (n == 0) return TRRE_OK;
+    if (!size_only && fast_capable(p->hdr) && out_cap >= n) {
+        int rc = launch_fast(p, d, d_in, n, d_out, d->d_status, st);
+        if (rc != TRRE_OK) return rc;
+        d->launches = 1;
+        d->pend_fast = true;
+        return TRRE_OK;
+    }
+    d->status_dirty = true;                 // k_scan_groups writes d_total
+    return launch_general(p, d, d_in, n, d_out, out_cap, st, size_only, &d->launches);
 }
 
 int status_to_rc(uint32_t s) {
@@ -218,14 +253,101 @@ int status_to_rc(uint32_t s) {
     return TRRE_OK;
 }
 
-int collect(DeviceState *d, cudaStream_t st, size_t *out_n) {
+// Synchronise, finish what the enqueue left open, report size and status.
+int collect(const trre_prog *p, DeviceState *d, cudaStream_t st, size_t *out_n) {
     CUDA_TRY(cudaMemcpyAsync(d->h_status, d->d_status, sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
-    CUDA_TRY(cudaMemcpyAsync(d->h_total, d->d_total, sizeof(unsigned long long), cudaMemcpyDeviceToHost, st));
+    if (!d->pend_fast) CUDA_TRY(cudaMemcpyAsync(d->h_total, d->d_total, sizeof(unsigned long long), cudaMemcpyDeviceToHost, st));
     CUDA_TRY(cudaStreamSynchronize(st));
     uint32_t s = *d->h_status;
-    size_t total = (d->last_fast && !(s & ST_IRREGULAR)) ? d->last_n : (size_t)*d->h_total;
+    size_t total = d->pend_fast ? d->pend_n : (size_t)*d->h_total;
+    if (d->pend_fast && (s & ST_IRREGULAR)) {
+        // NUL bytes or no trailing newline: same buffers, general path
+        int rc = clear_status(d, st);
+        if (rc != TRRE_OK) return rc;
+        d->pend_fast = false;
+        d->status_dirty = true;
+        rc = launch_general(p, d, d->pend_in, d->pend_n, d->pend_out, d->pend_cap, st, false, &d->launches);
+        if (rc != TRRE_OK) return rc;
+        CUDA_TRY(cudaMemcpyAsync(d->h_status, d->d_status, sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
+        CUDA_TRY(cudaMemcpyAsync(d->h_total, d->d_total, sizeof(unsigned long long), cudaMemcpyDeviceToHost, st));
+        CUDA_TRY(cudaStreamSynchronize(st));
+        s = *d->h_status;
+        total = (size_t)*d->h_total;
+    }
+    if (s) d->status_dirty = true;
     if (out_n) *out_n = total;
-    return status_to_rc(s);
+    return status_to_rc(s & ~ST_IRREGULAR);
+}
+
+int ensure_host_path_buffers(DeviceState *d, size_t need_in, size_t need_out) {
+    if (need_in > d->cap_in) {
+        if (d->buf_in) cudaFree(d->buf_in);
+        d->buf_in = nullptr; d->cap_in = 0;
+        CUDA_TRY(cudaMalloc(&d->buf_in, need_in));
+        d->cap_in = need_in;
+    }
+    if (need_out > d->cap_out) {
+        if (d->buf_out) cudaFree(d->buf_out);
+        d->buf_out = nullptr; d->cap_out = 0;
+        CUDA_TRY(cudaMalloc(&d->buf_out, need_out));
+        d->cap_out = need_out;
+    }
+    return TRRE_OK;
+}
+
+int ensure_slots(DeviceState *d, size_t chunk) {
+    if (d->slot_cap >= chunk) return TRRE_OK;
+    for (int k = 0; k < kSlots; ++k) {
+        if (d->slot_in[k]) cudaFree(d->slot_in[k]);
+        if (d->slot_out[k]) cudaFree(d->slot_out[k]);
+        d->slot_in[k] = d->slot_out[k] = nullptr;
+    }
+    d->slot_cap = 0;
+    for (int k = 0; k < kSlots; ++k) {
+        CUDA_TRY(cudaMalloc(&d->slot_in[k], chunk));
+        CUDA_TRY(cudaMalloc(&d->slot_out[k], chunk));
+        if (!d->slot_stream[k]) CUDA_TRY(cudaStreamCreateWithFlags(&d->slot_stream[k], cudaStreamNonBlocking));
+    }
+    d->slot_cap = chunk;
+    return TRRE_OK;
+}
+
+// Host buffers, length-preserving program: the input is cut at line boundaries into chunks that flow
+// through kSlots (H2D -> fast kernel -> D2H) on separate streams, so the two copy engines and the SMs
+// overlap.  Returns 1 when the buffer turned out irregular (caller falls back), 0 when done.
+int pipelined_lp(const trre_prog *p, DeviceState *d, const uint8_t *in, size_t n, uint8_t *out, int *launches) {
+    size_t chunk = 32u << 20;
+    if (const char *e = std::getenv("TRRE_CHUNK_MB")) { long v = std::atol(e); if (v >= 1 && v <= 1024) chunk = (size_t)v << 20; }
+    int rc = ensure_slots(d, chunk);
+    if (rc != TRRE_OK) return rc;
+    CUDA_TRY(cudaMemsetAsync(d->d_status + 1, 0, kSlots * sizeof(uint32_t), d->slot_stream[0]));
+    CUDA_TRY(cudaStreamSynchronize(d->slot_stream[0]));
+    size_t pos = 0;
+    int k = 0;
+    bool irregular = false;
+    while (pos < n) {
+        size_t end = std::min(pos + chunk, n);
+        if (end < n) {
+            const void *nl = memrchr(in + pos, '\n', end - pos);
+            if (!nl) { irregular = true; break; }            // a line longer than a chunk
+            end = (size_t)(static_cast<const uint8_t *>(nl) - in) + 1;
+        }
+        const int slot = k % kSlots;
+        cudaStream_t st = d->slot_stream[slot];               // stream order = reuse order of the slot
+        CUDA_TRY(cudaMemcpyAsync(d->slot_in[slot], in + pos, end - pos, cudaMemcpyHostToDevice, st));
+        rc = launch_fast(p, d, d->slot_in[slot], end - pos, d->slot_out[slot], d->d_status + 1 + slot, st);
+        if (rc != TRRE_OK) return rc;
+        CUDA_TRY(cudaMemcpyAsync(out + pos, d->slot_out[slot], end - pos, cudaMemcpyDeviceToHost, st));
+        *launches += 1;
+        pos = end;
+        ++k;
+    }
+    for (int s2 = 0; s2 < kSlots; ++s2) CUDA_TRY(cudaStreamSynchronize(d->slot_stream[s2]));
+    if (irregular) return 1;
+    CUDA_TRY(cudaMemcpy(d->h_status + 1, d->d_status + 1, kSlots * sizeof(uint32_t), cudaMemcpyDeviceToHost));
+    for (int s2 = 0; s2 < kSlots; ++s2)
+        if (d->h_status[1 + s2]) return 1;
+    return 0;
 }
 
 }  // namespace
@@ -279,6 +401,13 @@ void trre_prog_free(trre_prog *p) {
         cudaFree(d->d_blob); cudaFree(d->d_cnt); cudaFree(d->d_gsum); cudaFree(d->d_total); cudaFree(d->d_status);
         cudaFreeHost(d->h_total); cudaFreeHost(d->h_status);
         if (d->bt_s) { cudaFree(d->bt_s); cudaFree(d->bt_i); cudaFree(d->bt_o); cudaFree(d->bt_obuf); }
+        if (d->buf_in) cudaFree(d->buf_in);
+        if (d->buf_out) cudaFree(d->buf_out);
+        for (int k = 0; k < kSlots; ++k) {
+            if (d->slot_in[k]) cudaFree(d->slot_in[k]);
+            if (d->slot_out[k]) cudaFree(d->slot_out[k]);
+            if (d->slot_stream[k]) cudaStreamDestroy(d->slot_stream[k]);
+        }
         delete d;
     }
     delete p;
@@ -324,7 +453,7 @@ int trre_scan_device(const trre_prog *p, int device, const uint8_t *d_in, size_t
     rc = enqueue_scan(p, d, d_in, n, d_out, out_cap, st, false);
     if (rc != TRRE_OK) return rc;
     if (!out_n) return TRRE_OK;
-    return collect(d, st, out_n);
+    return collect(p, d, st, out_n);
 }
 
 int trre_scan_status(const trre_prog *p, int device, size_t *out_n, void *stream) {
@@ -333,7 +462,7 @@ int trre_scan_status(const trre_prog *p, int device, size_t *out_n, void *stream
     DeviceState *d = nullptr;
     int rc = get_state(p, device, &d);
     if (rc != TRRE_OK) return rc;
-    return collect(d, static_cast<cudaStream_t>(stream), out_n);
+    return collect(p, d, static_cast<cudaStream_t>(stream), out_n);
 }
 
 int trre_scan_launches(const trre_prog *p, int device) {
@@ -352,39 +481,46 @@ int trre_scan_into(const trre_prog *p, int device, const uint8_t *in, size_t n, 
     DeviceState *d = nullptr;
     int rc = get_state(p, device, &d);
     if (rc != TRRE_OK) return rc;
+    d->launches = 0;
     if (n == 0) return TRRE_OK;
     cudaStream_t st = nullptr;
-    uint8_t *d_in = nullptr, *d_out = nullptr;
-    CUDA_TRY(cudaMalloc(&d_in, n));
-    struct Free { uint8_t *&a, *&b; ~Free() { if (a) cudaFree(a); if (b) cudaFree(b); } } fr{d_in, d_out};
-    CUDA_TRY(cudaMemcpyAsync(d_in, in, n, cudaMemcpyHostToDevice, st));
-    const BlobHeader &h = p->hdr;
+    // length-preserving program and room for n bytes: chunked, copy/compute overlapped
+    if (fast_capable(p->hdr) && out && out_cap >= n) {
+        int launches = 0;
+        rc = pipelined_lp(p, d, in, n, out, &launches);
+        d->launches = launches;
+        if (rc == 0) { if (out_n) *out_n = n; return TRRE_OK; }
+        if (rc != 1) return rc;                                  // 1 = irregular buffer: general path below
+    }
+    rc = ensure_host_path_buffers(d, n, 0);
+    if (rc != TRRE_OK) return rc;
+    CUDA_TRY(cudaMemcpyAsync(d->buf_in, in, n, cudaMemcpyHostToDevice, st));
     size_t total = 0;
-    const bool lp = (h.flags & PF_LENGTH_PRESERVING) && h.exec_kind != TRRE_EXEC_BACKTRACK;
-    bool done = false;
-    if (lp) {
-        CUDA_TRY(cudaMalloc(&d_out, n));
-        rc = enqueue_scan(p, d, d_in, n, d_out, n, st, false);
-        if (rc != TRRE_OK) return rc;
-        rc = collect(d, st, &total);
-        if (rc == TRRE_OK) done = true;
-        else if (rc != TRRE_E_NOSPACE) return rc;
-        else { cudaFree(d_out); d_out = nullptr; }           // irregular input that grew: size it exactly
-    }
-    if (!done) {
-        rc = enqueue_scan(p, d, d_in, n, nullptr, 0, st, true);   // count + scan only
-        if (rc != TRRE_OK) return rc;
-        rc = collect(d, st, &total);
-        if (rc != TRRE_OK && rc != TRRE_E_NOSPACE) return rc;
-        CUDA_TRY(cudaMalloc(&d_out, total ? total : 1));
-        rc = enqueue_scan(p, d, d_in, n, d_out, total, st, false);
-        if (rc != TRRE_OK) return rc;
-        rc = collect(d, st, &total);
-        if (rc != TRRE_OK) return rc;
-    }
+    rc = enqueue_scan(p, d, d->buf_in, n, nullptr, 0, st, true);      // count + scan: exact output size
+    if (rc != TRRE_OK) return rc;
+    int launches = d->launches;
+    rc = collect(p, d, st, &total);
+    if (rc != TRRE_OK && rc != TRRE_E_NOSPACE) return rc;
     if (out_n) *out_n = total;
-    if (total > out_cap) { g_last_error = "output buffer too small"; return TRRE_E_NOSPACE; }
-    CUDA_TRY(cudaMemcpyAsync(out, d_out, total, cudaMemcpyDeviceToHost, st));
+    if (total > out_cap || (total && !out)) { g_last_error = "output buffer too small"; return TRRE_E_NOSPACE; }
+    rc = ensure_host_path_buffers(d, n, total ? total : 1);
+    if (rc != TRRE_OK) return rc;
+    // the counts are still in the workspace: only the write pass is left
+    {
+        const bool backtrack = p->hdr.exec_kind == TRRE_EXEC_BACKTRACK;
+        LineArgs a = make_args(d, d->buf_in, n, d->buf_out, total, d->d_status);
+        int grid = (int)std::min<size_t>(a.n_groups, backtrack ? (size_t)d->sm_count : (size_t)d->sm_count * 64);
+        if (d->status_dirty) { CUDA_TRY(cudaMemsetAsync(d->d_status, 0, sizeof(uint32_t), st)); }
+        launch_lines<MODE_WRITE>(backtrack, grid < 1 ? 1 : grid, st, a);
+        CUDA_TRY(cudaGetLastError());
+        d->pend_fast = false;
+        d->status_dirty = true;
+        size_t t2 = 0;
+        rc = collect(p, d, st, &t2);
+        d->launches = launches + 1;
+        if (rc != TRRE_OK) return rc;
+    }
+    CUDA_TRY(cudaMemcpyAsync(out, d->buf_out, total, cudaMemcpyDeviceToHost, st));
     CUDA_TRY(cudaStreamSynchronize(st));
     return TRRE_OK;
 }

@@ -1,8 +1,8 @@
 // kernels.cuh - sm_100a kernels of the scan path.
 //
 //  k_bytemap      TRRE_EXEC_BYTEMAP, regular input: out[i] = LUT[in[i]], 16-byte vector loads/stores,
-//                 LUT replicated per shared-memory bank (conflict-free), NUL / missing-final-newline
-//                 detection folded in (raises ST_IRREGULAR -> the general path reruns the buffer).
+//                 128 KB two-bytes-at-once table staged into shared memory by TMA, NUL / missing-final-
+//                 newline detection folded in (raises ST_IRREGULAR -> the general path reruns the buffer).
 //  k_lines        every other case: one 128-byte input chunk per thread, the thread owns the lines
 //                 that START in its chunk and runs the reference's per-line driver on them
 //                 (table executor or DFS executor), in one of three modes:
@@ -23,8 +23,13 @@ constexpr int kLineThreads = 256;      // threads per CTA in k_lines = chunks pe
 // ------------------------------------------------------------------------------------------------
 // k_bytemap
 // ------------------------------------------------------------------------------------------------
-constexpr int kBmThreads = 512;
+// Persistent: one 1024-thread CTA per SM.  The 128 KB pair table (LUT applied to two bytes at once,
+// built on the host, part of the program blob) is staged into shared memory with TMA bulk copies
+// (cp.async.bulk + mbarrier) while the first input vectors are already in flight; every thread then
+// streams 16-byte vectors: 2 shared-memory lookups + 1 PRMT per 4 bytes.
+constexpr int kBmThreads = 1024;
 constexpr int kBmUnroll = 4;           // 16-byte vectors in flight per thread
+constexpr int kPairLutBytes = 65536 * 2;
 
 __device__ __forceinline__ uint4 ld_stream(const uint4 *p) {
     uint4 r;
@@ -37,26 +42,59 @@ __device__ __forceinline__ void st_stream(uint4 *p, const uint4 &v) {
                  :: "l"(p), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
 }
 
-// tab[c*32 + lane] holds LUT[c] in all four byte lanes: lane L only ever touches bank L
-__device__ __forceinline__ uint32_t map_word(uint32_t w, const uint32_t *tab_lane, uint32_t &nul) {
-    uint32_t r0 = tab_lane[(w & 0xFFu) << 5];
-    uint32_t r1 = tab_lane[((w >> 8) & 0xFFu) << 5];
-    uint32_t r2 = tab_lane[((w >> 16) & 0xFFu) << 5];
-    uint32_t r3 = tab_lane[(w >> 24) << 5];
-    nul |= (w - 0x01010101u) & ~w & 0x80808080u;         // any zero byte in w
-    uint32_t lo = __byte_perm(r0, r1, 0x0040);            // bytes: r0.b0, r1.b0
-    uint32_t hi = __byte_perm(r2, r3, 0x0040);
+__device__ __forceinline__ uint32_t smem_u32(const void *p) {
+    return (uint32_t)__cvta_generic_to_shared(p);
+}
+__device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" :: "r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" :: "r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
+    uint32_t done;
+    do {
+        asm volatile("{\n\t.reg .pred p;\n\t"
+                     "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+                     "selp.u32 %0, 1, 0, p;\n\t}"
+                     : "=r"(done) : "r"(smem_u32(bar)), "r"(parity) : "memory");
+    } while (!done);
+}
+// TMA bulk copy global -> shared, completion counted in bytes on the mbarrier
+__device__ __forceinline__ void tma_bulk_g2s(void *dst_smem, const void *src_gmem, uint32_t bytes, uint64_t *bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 :: "r"(smem_u32(dst_smem)), "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
+
+// one 32-bit word = four input bytes -> four output bytes; also accumulates the zero-byte detector
+__device__ __forceinline__ uint32_t map_word(uint32_t w, uint32_t tab, uint32_t &nul) {
+    uint32_t lo, hi;
+    uint32_t a0 = tab + ((w << 1) & 0x1FFFEu);
+    uint32_t a1 = tab + ((w >> 15) & 0x1FFFEu);
+    asm("ld.shared.u16 %0, [%1];" : "=r"(lo) : "r"(a0));
+    asm("ld.shared.u16 %0, [%1];" : "=r"(hi) : "r"(a1));
+    nul |= (w - 0x01010101u) & ~w;                        // bit 7 of a byte set <=> that byte is 0 (masked later)
     return __byte_perm(lo, hi, 0x5410);
 }
 
-__global__ void __launch_bounds__(kBmThreads)
+__global__ void __launch_bounds__(kBmThreads, 1)
 k_bytemap(const uint8_t *__restrict__ in, uint8_t *__restrict__ out, size_t n,
-          const uint8_t *__restrict__ lut, uint32_t *__restrict__ status) {
-    extern __shared__ uint32_t tab[];                     // 256 * 32 words = 32 KB
-    for (int k = threadIdx.x; k < 256 * 32; k += blockDim.x)
-        tab[k] = 0x01010101u * (uint32_t)lut[k >> 5];
+          const uint16_t *__restrict__ pairlut, const uint8_t *__restrict__ lut, uint32_t *__restrict__ status) {
+    extern __shared__ __align__(128) uint8_t smem_tab[];  // kPairLutBytes
+    __shared__ __align__(8) uint64_t bar;
+    if (threadIdx.x == 0) {
+        mbar_init(&bar, 1);
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    }
     __syncthreads();
-    const uint32_t *tab_lane = tab + (threadIdx.x & 31);
+    if (threadIdx.x == 0) {
+        mbar_expect_tx(&bar, kPairLutBytes);
+#pragma unroll
+        for (int k = 0; k < 8; ++k)
+            tma_bulk_g2s(smem_tab + k * (kPairLutBytes / 8), reinterpret_cast<const uint8_t *>(pairlut) + k * (kPairLutBytes / 8),
+                         kPairLutBytes / 8, &bar);
+    }
+    const uint32_t tab = smem_u32(smem_tab);
     uint32_t nul = 0;
 
     // the vector body needs in and out equally misaligned; the host guarantees (in ^ out) % 16 == 0
@@ -68,29 +106,33 @@ k_bytemap(const uint8_t *__restrict__ in, uint8_t *__restrict__ out, size_t n,
 
     const size_t stride = (size_t)gridDim.x * blockDim.x;
     size_t v = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    bool table_ready = false;
     // main loop: kBmUnroll independent 16-byte loads in flight per thread
     for (; v + (kBmUnroll - 1) * stride < nvec; v += kBmUnroll * stride) {
         uint4 x[kBmUnroll];
 #pragma unroll
         for (int u = 0; u < kBmUnroll; ++u) x[u] = ld_stream(vin + v + u * stride);
+        if (!table_ready) { mbar_wait(&bar, 0); table_ready = true; }   // first loads overlap the table copy
 #pragma unroll
         for (int u = 0; u < kBmUnroll; ++u) {
             uint4 y;
-            y.x = map_word(x[u].x, tab_lane, nul);
-            y.y = map_word(x[u].y, tab_lane, nul);
-            y.z = map_word(x[u].z, tab_lane, nul);
-            y.w = map_word(x[u].w, tab_lane, nul);
+            y.x = map_word(x[u].x, tab, nul);
+            y.y = map_word(x[u].y, tab, nul);
+            y.z = map_word(x[u].z, tab, nul);
+            y.w = map_word(x[u].w, tab, nul);
             st_stream(vout + v + u * stride, y);
         }
     }
+    if (!table_ready) mbar_wait(&bar, 0);
     for (; v < nvec; v += stride) {
         uint4 x = ld_stream(vin + v), y;
-        y.x = map_word(x.x, tab_lane, nul);
-        y.y = map_word(x.y, tab_lane, nul);
-        y.z = map_word(x.z, tab_lane, nul);
-        y.w = map_word(x.w, tab_lane, nul);
+        y.x = map_word(x.x, tab, nul);
+        y.y = map_word(x.y, tab, nul);
+        y.z = map_word(x.z, tab, nul);
+        y.w = map_word(x.w, tab, nul);
         st_stream(vout + v, y);
     }
+    nul &= 0x80808080u;
     // ragged head and tail: one thread, byte by byte
     if (blockIdx.x == 0 && threadIdx.x == 0) {
         for (size_t k = 0; k < head; ++k) { uint8_t c = in[k]; if (!c) nul = 1; out[k] = lut[c]; }
