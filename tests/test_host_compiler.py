@@ -1,0 +1,156 @@
+"""Host side of the product (parser, flat NFT, both subset constructions, analysis, blob) against the
+oracle and the golden fixtures - WITHOUT a GPU: the compiled tables are executed by the test-only
+interpreter tests/dsa_sim.py, which follows the same per-attempt rule the CUDA kernels implement."""
+import random
+
+import pytest
+
+import trre_b200 as T
+from dsa_sim import Blob, Diverged
+from golden_util import load_golden
+from kat_vectors import BAD_EXPRESSIONS
+from oracle_util import NFT, DFT, SCAN, MATCH, oracle_run, lib as oracle_lib
+from patgen import rand_expr, rand_input
+
+GOLDEN = load_golden()
+
+
+def sim_scan(expr, flavor, data):
+    prog = T.compile(expr, flavor)
+    return prog, Blob(prog.blob()).scan(data)
+
+
+def test_golden_scan_vectors_through_compiled_tables():
+    n = 0
+    for v in GOLDEN:
+        if v["mode"] != SCAN or v["all"]:
+            continue
+        try:
+            prog = T.compile(v["expr"], v["flavor"])
+        except T.TrreError as e:
+            if e.code == 1:
+                assert v["rc"] == 1 and e.text == v["err"], (v["expr"], e.text, v["err"])
+            else:
+                assert e.code == 2, (v["expr"], e.code)     # refused (limits): never a wrong answer
+            continue
+        if v["rc"] != 0:
+            continue
+        try:
+            out = Blob(prog.blob()).scan(v["data"])
+        except Diverged:
+            continue
+        assert out == v["out"], (v["tag"], v["expr"], v["flavor"], v["data"], out, v["out"], prog.info)
+        n += 1
+    assert n > 400
+
+
+def test_golden_match_vectors_through_match_host():
+    n = 0
+    for v in GOLDEN:
+        if v["mode"] != MATCH or v["rc"] != 0:
+            continue
+        prog = T.compile(v["expr"], v["flavor"])
+        assert prog.match(v["data"], all_=bool(v["all"])) == v["out"], (v["expr"], v["data"])
+        n += 1
+    assert n >= 51
+
+
+@pytest.mark.parametrize("expr", BAD_EXPRESSIONS)
+def test_parser_errors_match_the_reference_text(expr):
+    for fl in (NFT, DFT):
+        rc, _, err = oracle_run(expr, b"abc\n", flavor=fl)
+        try:
+            T.compile(expr, fl)
+            got = (0, "")
+        except T.TrreError as e:
+            got = (e.code, e.text)
+        if rc == 2:
+            assert got[0] == 2
+        else:
+            assert got == (rc, err), (expr, got, rc, err)
+
+
+def test_empty_pattern():
+    with pytest.raises(T.TrreError) as ei:
+        T.compile(b"", NFT)
+    assert ei.value.code == 134
+
+
+@pytest.mark.parametrize("seed", range(6))
+def test_random_patterns_tables_vs_oracle(seed):
+    rng = random.Random(500 + seed)
+    kinds = set()
+    for _ in range(70):
+        pat = rand_expr(rng, 2).encode()
+        data = rand_input(rng, final_newline=rng.random() < 0.85)
+        for fl in (NFT, DFT):
+            rc, want, err = oracle_run(pat, data, flavor=fl)
+            try:
+                prog = T.compile(pat, fl)
+            except T.TrreError as e:
+                assert e.code in (rc, 2) or rc == 2, (pat, e.code, rc)
+                continue
+            if rc == 2:
+                continue
+            kinds.add(prog.exec_kind)
+            try:
+                out = Blob(prog.blob()).scan(data)
+            except Diverged:
+                continue
+            assert rc == 0 and out == want, (pat, fl, data, out, want, prog.info)
+    assert T.EXEC_TABLE in kinds
+
+
+def test_program_shapes_of_the_baseline_configs():
+    p = T.compile("[a:A-z:Z]", DFT)
+    assert p.exec_kind == T.EXEC_BYTEMAP and p.info["dsa_states"] == 27 and p.info["nft_states"] == 81
+    lut = p.bytemap()
+    assert lut == bytes((c - 32 if 97 <= c <= 122 else c) for c in range(256))
+    p = T.compile("[a:b-y:zz:a]", DFT)
+    assert p.exec_kind == T.EXEC_BYTEMAP and p.info["dsa_states"] == 27
+    assert p.bytemap()[ord("z")] == ord("a") and p.bytemap()[ord("a")] == ord("b")
+    p = T.compile("cat:dog", DFT)
+    assert p.info["dsa_states"] == 4 and p.info["length_preserving"] == 1 and p.info["max_depth"] == 3
+    p = T.compile("(cat:dog|dog:cat)", DFT)
+    assert p.info["dsa_states"] == 7 and p.info["nft_states"] == 16
+    p = T.compile("(cat:dog|dog:cat)", NFT)
+    assert p.exec_kind == T.EXEC_TABLE and p.info["nft_states"] == 15 and p.info["length_preserving"] == 1
+    p = T.compile("a:", NFT)
+    assert p.info["length_preserving"] == 0
+    p = T.compile(":=", NFT)
+    assert p.info["can_match_empty"] == 1
+    p = T.compile("(a:x)*b|a", NFT)                    # not subsequential: unbounded delayed output
+    assert p.exec_kind == T.EXEC_BACKTRACK
+
+
+def test_dictionary_program_matches_reference_state_counts():
+    # K words: 8K CONS/PROD + 2(K-1) SPLITNG/JOIN + FINAL (+ the init JOIN of the DFT flavour):
+    # 10K-1 / 10K states - SURVEY s8a's "100 000 NFT states" for K = 10 000
+    rng = random.Random(7)
+    words = set()
+    while len(words) < 2000:
+        words.add("".join(rng.choice("abcdefghijklmnopqrstuvwxyz") for _ in range(4)))
+    words = sorted(words)
+    rng.shuffle(words)
+    expr = "|".join("%s:%s" % (w, w.upper()) for w in words)
+    p = T.compile(expr, DFT)
+    assert p.info["nft_states"] == 10 * len(words)
+    assert p.exec_kind == T.EXEC_TABLE and p.info["length_preserving"] == 1 and p.info["max_depth"] == 4
+    text = bytes(T.synth_text(11, 4000, words[:50], 0.3, True))
+    rc, want, _ = oracle_run(expr.encode(), text, flavor=DFT)
+    assert rc == 0
+    assert oracle_lib().trre_oracle_last_dstates() <= p.info["dsa_states"]      # lazy <= eager
+    assert Blob(p.blob()).scan(text) == want
+    pn = T.compile(expr, NFT)
+    assert pn.exec_kind == T.EXEC_TABLE and pn.info["nft_states"] == 10 * len(words) - 1
+    assert Blob(pn.blob()).scan(text) == oracle_run(expr.encode(), text, flavor=NFT)[1]
+
+
+def test_blob_round_trip_is_what_gets_broadcast():
+    p = T.compile("(cat:dog|dog:cat)", NFT)
+    q = T.from_blob(p.blob())
+    assert q.info == p.info and q.blob() == p.blob()
+    with pytest.raises(T.TrreError):
+        T.from_blob(p.blob()[:-8])
+    with pytest.raises(T.TrreError):
+        T.from_blob(b"\0" * 200)
