@@ -39,11 +39,31 @@ WORKLOADS = {
     "cfg3": ("(cat:dog|dog:cat)", 0, 8 * GiB, ["cat", "dog", "catdog", "dogcat", "ca", "do", "cot", "dig"], 0.25, False, 0x72726503, "trre"),
     "cfg4": ("[a:b-y:zz:a]", 1, 8 * GiB, None, 0.0, False, 0x72726504, "trre_dft"),
 }
+
+
+def dictionary_words(k=10000, seed=7):
+    """k distinct 4-letter lowercase words (prefix free), seeded, shuffled."""
+    import random
+    rng = random.Random(seed)
+    words = set()
+    while len(words) < k:
+        words.add("".join(rng.choice("abcdefghijklmnopqrstuvwxyz") for _ in range(4)))
+    words = sorted(words)
+    rng.shuffle(words)
+    return words
+
+
+_DICT = dictionary_words()
+WORKLOADS["cfg5"] = ("|".join("%s:%s" % (w, w.upper()) for w in _DICT), 1, 8 * GiB, _DICT, 0.30, True, 0x72726505, "trre_dft")
+WORKLOADS["del"] = ("a:", 0, 1 * GiB, None, 0.0, False, 0x72726506, "trre")
+
 DESCR = {
     "cfg1": "'cat:dog' over 1 MB ASCII (NFT flavour)",
     "cfg2": "'[a:A-z:Z]' uppercase over 1 GiB synthetic ASCII per GPU, DFT flavour (BASELINE configs[1])",
     "cfg3": "'(cat:dog|dog:cat)' over 8 GiB synthetic text per GPU, NFT flavour (BASELINE configs[2])",
     "cfg4": "Caesar '[a:b-y:zz:a]' over 8 GiB synthetic ASCII per GPU, DFT flavour (BASELINE configs[3], 64 GiB at 8 GPUs)",
+    "cfg5": "10k-alternation word:WORD dictionary (18 402-state DFT) over 8 GiB synthetic lowercase text per GPU, DFT flavour (BASELINE configs[4])",
+    "del": "'a:' (delete every a; NOT length preserving: count + scan + write path) over 1 GiB synthetic ASCII, NFT flavour",
 }
 METRIC = "input GB/s (scan mode)"
 
@@ -185,8 +205,8 @@ def run_reference(args, spec):
         "impl": "reference", "metric": METRIC, "value": gbs, "unit": "GB/s", "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * total / args.steps,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8", "data": "synthetic",
-        "config": {"workload": DESCR[args.workload], "pattern": pattern, "flavor": "dft" if flavor else "nft",
-                   "sample_bytes_per_step": sample_n},
+        "config": {"workload": DESCR[args.workload], "pattern": pattern if len(pattern) < 200 else pattern[:60] + "...(%d bytes)" % len(pattern),
+                   "flavor": "dft" if flavor else "nft", "sample_bytes_per_step": sample_n},
         "cpu_baseline": {"value": gbs, "unit": "GB/s", "cores": 1, "kind": kind,
                          "sample": "%d MiB of the same synthetic corpus per step, file in /dev/shm, stdout to /dev/null; "
                                    "single threaded (the reference has no threads)" % (sample_n // MiB)},
@@ -381,7 +401,7 @@ def main():
         return 0
 
     peak, peak_src = measured_hbm_peak()
-    algo_bytes = 2.0 * n                     # 1 B read + 1 B written per input byte (length preserving)
+    algo_bytes = float(n + out_n)            # 1 B read per input byte + 1 B written per output byte
     achieved = algo_bytes / (ms_per_step * 1e-3) / 1e9
     traffic = None
     prof = os.path.join(ROOT, "profiles", "traffic_%s.json" % args.workload)
@@ -396,8 +416,8 @@ def main():
         "metric": METRIC, "value": value, "unit": "GB/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "u8", "data": "synthetic",
-        "config": {"workload": DESCR[args.workload], "pattern": pattern, "flavor": "dft" if flavor else "nft",
-                   "bytes_per_gpu": n, "exec": kernel, "dsa_states": info["dsa_states"], "nft_states": info["nft_states"],
+        "config": {"workload": DESCR[args.workload], "pattern": pattern if len(pattern) < 200 else pattern[:60] + "...(%d bytes)" % len(pattern),
+                   "flavor": "dft" if flavor else "nft", "bytes_per_gpu": n, "exec": kernel, "dsa_states": info["dsa_states"], "nft_states": info["nft_states"],
                    "l2": "input %d MiB per step exceeds the 126 MB L2; no flush needed" % (n // MiB),
                    "parallelism": "lines sharded over %d GPU(s), program blob broadcast, sizes all-gathered" % world},
         "clocks": clocks.summary(),

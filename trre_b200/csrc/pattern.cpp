@@ -381,6 +381,31 @@ Nft build_nft(SynTree &tree, bool with_init_join) {
     } else {
         g.start = p.head;
     }
+    // Path compression of JOIN chains: a JOIN is a pure epsilon move with one successor, so every edge
+    // may point straight at the first non-JOIN state behind it.  Semantics (both flavours, including the
+    // DFS order and the shared-output quirk of trre_dft) are untouched; a K-way alternation otherwise
+    // costs K JOIN hops per accepted word (left-nested '|' nodes, one JOIN each).
+    {
+        const int32_t n = (int32_t)g.st.size();
+        std::vector<int32_t> target(n, -2);
+        auto resolve = [&](int32_t s) {
+            std::vector<int32_t> path;
+            int32_t t = s;
+            while (t >= 0 && g.st[t].op == N_JOIN && g.st[t].a >= 0 && target[t] == -2 && t != init) {
+                path.push_back(t);
+                t = g.st[t].a;
+                if (path.size() > (size_t)n) break;       // cannot happen: cycles always contain a SPLIT
+            }
+            int32_t dst = (t >= 0 && target[t] >= -1 && g.st[t].op == N_JOIN && t != init) ? target[t] : t;
+            for (int32_t q : path) target[q] = dst;
+            return dst;
+        };
+        for (int32_t s = 0; s < n; ++s) {
+            if (g.st[s].a >= 0) g.st[s].a = resolve(g.st[s].a);
+            if (g.st[s].b >= 0) g.st[s].b = resolve(g.st[s].b);
+        }
+        if (!with_init_join && g.start >= 0) g.start = resolve(g.start);
+    }
     return g;
 }
 
