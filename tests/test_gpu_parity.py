@@ -81,3 +81,73 @@ def test_device_resident_api_and_launch_count():
     assert n == len(text)
     assert bytes(d_out.cpu().numpy().tobytes()) == text.upper()
     assert prog.launches() >= 1
+
+
+# ---- k_match: the position-parallel kernel for length-preserving acyclic programs ------------------
+
+LP_PATTERNS = [
+    ("aa:bb", NFT), ("aa:bb", DFT), ("aba:xyz", NFT), ("aba:xyz", DFT),
+    ("abab:wxyz|ba:XY", NFT), ("abab:wxyz|ba:XY", DFT),
+    ("ab:XY|abc:XYZ|a:Z", NFT), ("ab:XY|abc:XYZ|a:Z", DFT),
+    ("(cat:dog|dog:cat)", NFT), ("b:X", NFT), ("[a:A-b:B]c:C", DFT),
+    ("abcabcabcabcabca:ABCABCABCABCABCA|bc:XY", NFT),          # 16-byte matches, heavy overlap
+]
+
+
+def _ab_text(seed, n, alphabet=b"ab", line_lo=1, line_hi=200):
+    rng = random.Random(seed)
+    out = bytearray()
+    while len(out) < n:
+        ln = rng.randint(line_lo, line_hi)
+        out += bytes(rng.choice(alphabet) for _ in range(ln)) + b"\n"
+    return bytes(out[:n - 1]) + b"\n"
+
+
+@pytest.mark.parametrize("expr,flavor", LP_PATTERNS)
+def test_match_kernel_overlapping_matches(expr, flavor):
+    prog = T.compile(expr, flavor)
+    assert prog.info["length_preserving"] == 1 and prog.info["max_depth"] <= 16
+    for seed, alphabet in ((1, b"ab"), (2, b"abc"), (3, b"abc  ")):
+        data = _ab_text(seed, 1 << 20, alphabet)
+        rc, want, _ = oracle_run(expr.encode(), data, flavor=flavor)
+        assert rc == 0
+        got = prog.scan(data)
+        assert got == want, (expr, flavor, seed)
+
+
+def test_match_kernel_equals_line_kernel(monkeypatch):
+    data = _ab_text(9, 3 << 20, b"abc ", 1, 3000)
+    for expr, flavor in LP_PATTERNS[:8]:
+        prog = T.compile(expr, flavor)
+        a = prog.scan(data)
+        monkeypatch.setenv("TRRE_NO_MATCH_KERNEL", "1")
+        b = prog.scan(data)
+        monkeypatch.delenv("TRRE_NO_MATCH_KERNEL")
+        assert a == b, (expr, flavor)
+
+
+@pytest.mark.parametrize("data", [
+    b"a" * 20000 + b"\n",                                  # one line longer than the warm-up window
+    (b"ab" * 5000 + b"\n") * 40,
+    _ab_text(4, 1 << 18, b"ab")[:-1],                      # no final newline
+    _ab_text(5, 1 << 18, b"ab").replace(b"aab", b"a\0b"),  # NUL bytes
+    b"aa\n" * 100000,
+])
+def test_match_kernel_irregular_buffers_fall_back(data):
+    for expr, flavor in (("aa:bb", NFT), ("aba:xyz", DFT), ("(cat:dog|dog:cat)", NFT)):
+        check(expr, flavor, data)
+
+
+def test_dictionary_on_gpu():
+    rng = random.Random(7)
+    words = set()
+    while len(words) < 2000:
+        words.add("".join(rng.choice("abcdefghijklmnopqrstuvwxyz") for _ in range(4)))
+    words = sorted(words)
+    rng.shuffle(words)
+    expr = "|".join("%s:%s" % (w, w.upper()) for w in words)
+    text = bytes(T.synth_text(0x72726505, 4 << 20, words, 0.3, True))
+    for flavor in (DFT, NFT):
+        prog = T.compile(expr, flavor)
+        rc, want, _ = oracle_run(expr.encode(), text, flavor=flavor)
+        assert rc == 0 and prog.scan(text) == want, flavor

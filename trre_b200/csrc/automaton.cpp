@@ -433,7 +433,9 @@ void analyse_and_pack(const std::vector<RawState> &st, const StringPool &sp, int
             // DFT flavour: the match ends where the walk reaches its first final state
             const bool decided = (st[e.next].flags & DSA_S_DECIDED) != 0;
             const bool mark = e.mark || (flavor == TRRE_FLAVOR_DFT && decided);
-            uint32_t lo = e.next | (mark ? (uint32_t)DSA_E_MARK : 0u) | (decided ? (uint32_t)DSA_E_DECIDED : 0u);
+            uint32_t lo = e.next | (mark ? (uint32_t)DSA_E_MARK : 0u) | (decided ? (uint32_t)DSA_E_DECIDED : 0u) |
+                          ((st[e.next].flags & DSA_S_HAS_FINAL) ? (uint32_t)DSA_E_HASFINAL : 0u) |
+                          ((st[e.next].flags & DSA_S_DIVERGE) ? (uint32_t)DSA_E_DIVERGE : 0u);
             P.trans[(size_t)s * P.n_classes + P.classmap[e.byte]] = pack64(lo, pw.ref(e.out_id));
         }
     }
@@ -444,6 +446,13 @@ void analyse_and_pack(const std::vector<RawState> &st, const StringPool &sp, int
 
     // ---- flags ---------------------------------------------------------------------------------
     if (st[0].flags & DSA_S_HAS_FINAL) P.flags |= PF_CAN_MATCH_EMPTY;
+    {
+        bool late = true;
+        for (uint32_t s = 0; s < S && late; ++s)
+            for (const RawEdge &e : st[s].edges)
+                if (!(st[e.next].flags & DSA_S_DECIDED) && !sp.get(e.out_id).empty()) { late = false; break; }
+        if (late) P.flags |= PF_OUT_LATE;
+    }
     for (uint32_t s = 0; s < S; ++s)
         if (st[s].flags & DSA_S_DIVERGE) P.flags |= PF_HAS_DIVERGE;
 
@@ -484,19 +493,23 @@ void analyse_and_pack(const std::vector<RawState> &st, const StringPool &sp, int
         bal[0] = 0;
         lag[0] = 0;
         work.push_back(0);
+        auto accepts_ok = [&](uint32_t t, int64_t b, int64_t l) {
+            // an attempt that ends in t prints acc + fin(t) and consumes i - lag bytes
+            return b + (int64_t)sp.get(st[t].fin_id).size() == -l;
+        };
+        if ((st[0].flags & DSA_S_HAS_FINAL) && !accepts_ok(0, 0, 0)) lp = false;
         while (!work.empty() && lp) {
             uint32_t s = work.back();
             work.pop_back();
-            if (st[s].flags & DSA_S_HAS_FINAL) {
-                int64_t emitted_minus_i = bal[s] + (int64_t)sp.get(st[s].fin_id).size();
-                if (emitted_minus_i != -lag[s]) { lp = false; break; }
-            }
             for (const RawEdge &e : st[s].edges) {
+                const uint32_t t = e.next;
                 int64_t b = bal[s] + (int64_t)sp.get(e.out_id).size() - 1;
                 int64_t l = e.mark ? 0 : lag[s] + 1;
                 if (flavor == TRRE_FLAVOR_DFT) l = 0;          // the match ends where the walk ends
-                if (bal[e.next] == UNSET) { bal[e.next] = b; lag[e.next] = l; work.push_back(e.next); }
-                else if (bal[e.next] != b || ((st[e.next].flags & DSA_S_HAS_FINAL) && lag[e.next] != l)) { lp = false; break; }
+                if ((st[t].flags & DSA_S_HAS_FINAL) && !accepts_ok(t, b, l)) { lp = false; break; }
+                if (st[t].flags & DSA_S_DECIDED) continue;     // terminal: nothing to propagate, any path may end here
+                if (bal[t] == UNSET) { bal[t] = b; lag[t] = l; work.push_back(t); }
+                else if (bal[t] != b || ((st[t].flags & DSA_S_HAS_FINAL) && lag[t] != l)) { lp = false; break; }
             }
         }
         if (lp) P.flags |= PF_LENGTH_PRESERVING;
@@ -534,6 +547,13 @@ std::vector<uint8_t> assemble(const Program &P, const Nft &g) {
     h.off_pool = (uint32_t)off; off += P.pool.size(); off = align16(off);
     h.off_nft = (uint32_t)off; off += g.st.size() * sizeof(NftFlat); off = (off + 127) & ~(size_t)127;
     if (P.exec_kind == TRRE_EXEC_BYTEMAP) { h.off_pairlut = (uint32_t)off; off += 65536 * 2; }
+    // compact tables of the position-parallel kernel (k_match): length-preserving, acyclic, short attempts
+    const bool matchable = P.exec_kind == TRRE_EXEC_TABLE && (P.flags & PF_LENGTH_PRESERVING) && (P.flags & PF_ACYCLIC) &&
+                           !(P.flags & (PF_CAN_MATCH_EMPTY | PF_HAS_DIVERGE)) && P.max_depth >= 1 && P.max_depth <= 16;
+    if (matchable) {
+        h.off_row0 = (uint32_t)off; off += 256 * 4;
+        h.off_ctrans = (uint32_t)off; off += P.trans.size() * 4; off = align16(off);
+    }
     if (off >= (1ull << 31)) throw PatternError{TRRE_E_UNSUPPORTED, "error: compiled tables exceed 2 GiB\n"};
     h.magic = 0x32425254u;  // "TRB2"
     h.abi = TRRE_B200_ABI_VERSION;
@@ -560,6 +580,12 @@ std::vector<uint8_t> assemble(const Program &P, const Nft &g) {
     for (size_t k = 0; k < g.st.size(); ++k) {
         nf[k].op = g.st[k].op; nf[k].val = g.st[k].val; nf[k].pad0 = nf[k].pad1 = 0;
         nf[k].a = g.st[k].a; nf[k].b = g.st[k].b;
+    }
+    if (h.off_row0) {
+        uint32_t *row0 = reinterpret_cast<uint32_t *>(blob.data() + h.off_row0);
+        uint32_t *ct = reinterpret_cast<uint32_t *>(blob.data() + h.off_ctrans);
+        for (int c = 0; c < 256; ++c) row0[c] = (uint32_t)(P.trans[P.classmap[c]] & 0xFFFFFFFFu);
+        for (size_t k = 0; k < P.trans.size(); ++k) ct[k] = (uint32_t)(P.trans[k] & 0xFFFFFFFFu);
     }
     if (h.off_pairlut) {
         // pair[c0 | c1 << 8] = LUT[c0] | LUT[c1] << 8 : one shared-memory lookup maps two input bytes

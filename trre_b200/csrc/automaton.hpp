@@ -34,6 +34,8 @@ enum : uint32_t {
     DSA_DEAD        = 0x00FFFFFFu,   // `next` value of a dead entry
     DSA_E_MARK      = 1u << 24,      // entry: a FINAL item is born on this transition
     DSA_E_DECIDED   = 1u << 25,      // entry: target state is DECIDED (attempt ends there)
+    DSA_E_HASFINAL  = 1u << 26,      // entry: target state has a pending FINAL item (wins if the walk stops there)
+    DSA_E_DIVERGE   = 1u << 27,      // entry: target state has a pending DIVERGE item
     DSA_S_HAS_FINAL = 1u,            // state: a FINAL item is pending in the list
     DSA_S_DECIDED   = 2u,            // state: nothing of higher priority is alive any more
     DSA_S_DIVERGE   = 4u             // state: an epsilon cycle is pending (reference: stack cap error)
@@ -45,7 +47,9 @@ enum : uint32_t {
     PF_CAN_MATCH_EMPTY   = 2u,
     PF_ACYCLIC           = 4u,
     PF_NUL_IN_OUTPUT     = 8u,       // some PROD byte is 0: NFT flavour truncates at it (fputs)
-    PF_HAS_DIVERGE       = 16u
+    PF_HAS_DIVERGE       = 16u,
+    PF_OUT_LATE          = 32u       // every transition into a non-DECIDED state emits nothing: a match's output
+                                     // is out(last transition) + fin(last state)
 };
 
 struct BlobHeader {
@@ -70,7 +74,9 @@ struct BlobHeader {
     uint32_t pool_bytes;
     uint32_t off_nft;          // NftFlat[nft_states]
     uint32_t off_pairlut;      // u16[65536] (TRRE_EXEC_BYTEMAP): LUT applied to two bytes at once, 0 if absent
-    uint32_t reserved[3];
+    uint32_t off_row0;         // u32[256]: low word of trans[start][class(byte)] by raw byte (k_match), 0 if absent
+    uint32_t off_ctrans;       // u32[dsa_states * n_classes]: low words of trans (k_match), 0 if absent
+    uint32_t reserved[1];
 };
 
 struct NftFlat {               // 12 bytes, device layout of trre_nft.c:334-340

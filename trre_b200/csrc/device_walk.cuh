@@ -23,6 +23,10 @@ struct DevProg {
     const uint8_t  *classmap;
     const uint8_t  *lut;
     const uint16_t *pairlut;       // TRRE_EXEC_BYTEMAP only
+    const uint32_t *row0;          // k_match: first step by raw byte
+    const uint32_t *ctrans;        // k_match: low words of trans
+    uint32_t n_states;
+    uint32_t max_depth;
     const uint64_t *trans;
     const uint64_t *sinfo;
     const uint8_t  *pool;

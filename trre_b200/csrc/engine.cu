@@ -14,6 +14,7 @@
 #include "../../include/trre_b200.h"
 #include "automaton.hpp"
 #include "kernels.cuh"
+#include "match_kernel.cuh"
 #include "pattern.hpp"
 
 using namespace trre;
@@ -57,6 +58,10 @@ struct DeviceState {
     uint8_t *slot_in[kSlots] = {nullptr, nullptr, nullptr}, *slot_out[kSlots] = {nullptr, nullptr, nullptr};
     cudaStream_t slot_stream[kSlots] = {nullptr, nullptr, nullptr};
     size_t slot_cap = 0;
+    // k_match launch plan
+    uint32_t match_repl = 0, match_states = 0;
+    size_t match_smem = 0;
+    int match_blocks = 0;
 };
 
 }  // namespace
@@ -115,6 +120,10 @@ int get_state(const trre_prog *cp, int device, DeviceState **out) {
     d->P.classmap = d->d_blob + h.off_classmap;
     d->P.lut = d->d_blob + h.off_lut;
     d->P.pairlut = h.off_pairlut ? reinterpret_cast<const uint16_t *>(d->d_blob + h.off_pairlut) : nullptr;
+    d->P.row0 = h.off_row0 ? reinterpret_cast<const uint32_t *>(d->d_blob + h.off_row0) : nullptr;
+    d->P.ctrans = h.off_ctrans ? reinterpret_cast<const uint32_t *>(d->d_blob + h.off_ctrans) : nullptr;
+    d->P.n_states = h.dsa_states;
+    d->P.max_depth = h.max_depth;
     d->P.trans = reinterpret_cast<const uint64_t *>(d->d_blob + h.off_trans);
     d->P.sinfo = reinterpret_cast<const uint64_t *>(d->d_blob + h.off_sinfo);
     d->P.pool = d->d_blob + h.off_pool;
@@ -124,6 +133,33 @@ int get_state(const trre_prog *cp, int device, DeviceState **out) {
     d->P.flags = h.flags;
     d->P.nft_start = h.nft_start;
     CUDA_TRY(cudaFuncSetAttribute(k_bytemap, cudaFuncAttributeMaxDynamicSharedMemorySize, kPairLutBytes));
+    if (h.off_row0) {
+        // shared-memory plan of k_match: replicate row0 per bank when everything fits, else cache the
+        // first (shallowest: states are numbered breadth first) rows of the compact table
+        const size_t warp_bytes = (size_t)kMatchWarps * kWarpSmem;
+        const size_t ct_full = (size_t)h.dsa_states * h.n_classes * 4;
+        const size_t budget = 108 * 1024;                       // two CTAs per SM
+        if (32768 + 256 + ((ct_full + 15) & ~(size_t)15) + warp_bytes <= budget) {
+            d->match_repl = 1;
+            d->match_states = h.dsa_states;
+        } else {
+            d->match_repl = 0;
+            size_t room = budget - 1024 - 256 - warp_bytes;
+            size_t rows = room / ((size_t)h.n_classes * 4);
+            d->match_states = (uint32_t)std::min<size_t>(rows, h.dsa_states);
+        }
+        size_t ct_words = ((size_t)d->match_states * h.n_classes + 3) & ~(size_t)3;
+        d->match_smem = (d->match_repl ? 32768 : 1024) + 256 + ct_words * 4 + warp_bytes;
+        int per_sm = 1;
+        if (d->match_states == h.dsa_states) {
+            CUDA_TRY(cudaFuncSetAttribute(k_match<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)d->match_smem));
+            CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_match<true>, kMatchThreads, d->match_smem));
+        } else {
+            CUDA_TRY(cudaFuncSetAttribute(k_match<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)d->match_smem));
+            CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_match<false>, kMatchThreads, d->match_smem));
+        }
+        d->match_blocks = d->sm_count * (per_sm < 1 ? 1 : per_sm);
+    }
     p->dev[device] = d;
     *out = d;
     return TRRE_OK;
@@ -187,6 +223,17 @@ int launch_fast(const trre_prog *p, DeviceState *d, const uint8_t *d_in, size_t 
     const bool aligned = ((reinterpret_cast<uintptr_t>(d_in) ^ reinterpret_cast<uintptr_t>(d_out)) & 15) == 0;
     if (h.exec_kind == TRRE_EXEC_BYTEMAP && aligned && d->P.pairlut) {
         k_bytemap<<<d->sm_count, kBmThreads, kPairLutBytes, st>>>(d_in, d_out, n, d->P.pairlut, d->P.lut, status);
+    } else if (d->P.row0 && aligned && (reinterpret_cast<uintptr_t>(d_in) & 15) == 0 && !std::getenv("TRRE_NO_MATCH_KERNEL")) {
+        MatchArgs m{};
+        m.P = d->P; m.in = d_in; m.out = d_out; m.n = n; m.status = status;
+        m.smem_states = d->match_states; m.row0_replicated = d->match_repl;
+        const size_t n_tiles = (n + kTile - 1) / kTile;
+        // every warp owns a contiguous span of tiles; keep spans >= 16 tiles so the warm-up stays cheap
+        size_t blocks = std::min<size_t>((size_t)d->match_blocks, (n_tiles + 16 * kMatchWarps - 1) / (16 * kMatchWarps));
+        if (blocks < 1) blocks = 1;
+        m.tiles_per_warp = (n_tiles + blocks * kMatchWarps - 1) / (blocks * kMatchWarps);
+        if (d->match_states == d->P.n_states) k_match<true><<<(int)blocks, kMatchThreads, d->match_smem, st>>>(m);
+        else k_match<false><<<(int)blocks, kMatchThreads, d->match_smem, st>>>(m);
     } else {
         LineArgs a = make_args(d, d_in, n, d_out, n, status);
         int grid = (int)std::min<size_t>(a.n_groups, (size_t)d->sm_count * 64);

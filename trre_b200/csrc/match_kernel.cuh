@@ -1,0 +1,303 @@
+// match_kernel.cuh - k_match: position-parallel scan for length-preserving, acyclic programs (sm_100a).
+//
+// Applies to TABLE programs whose every match emits exactly what it consumes, whose automaton has no
+// cycle and whose attempts read at most 16 bytes (cat:dog, (cat:dog|dog:cat), word:WORD dictionaries).
+// On a regular buffer (no NUL, final '\n') output offset == input offset and the scan driver
+// (trre_nft.c:778-789) degenerates to: "an attempt starts at every position not covered by an earlier
+// match of the same line".  '\n' can never be consumed (dead byte class), so lines need no bookkeeping:
+//
+//   warp-synchronous, one 512-byte tile per warp iteration, 16 positions per lane
+//   A  16-byte vector load per lane (next tile prefetched), staged to the warp's shared-memory tile
+//   B  first transition of an attempt at EVERY position: row0[byte]  -> 16-bit candidate mask
+//   C  candidates finish their walk (compact u32 table: hot states in shared memory, rest L2); the
+//      match lengths stay in registers (16-bit mask + 4 bits per position)
+//   D  chain resolution: which candidates are real (not covered by an earlier match) - speculate
+//      "entry overhang 0" per lane, repair through warp shuffles until stable; carry across tiles
+//   E  output tile = raw copy, real matches overwrite their span (may spill into the next tile: carried),
+//      16-byte vector store per lane
+//
+// Each warp owns a contiguous span of tiles; it warms up from the last '\n' before its span so the
+// chain state at the span start is exact.  Anything irregular (NUL byte, missing final newline, a
+// line longer than the warm-up window) raises ST_IRREGULAR and the general path reruns the buffer.
+#pragma once
+#include <cstdint>
+
+#include "device_walk.cuh"
+
+namespace trre {
+
+constexpr int kMatchThreads = 512;
+constexpr int kMatchWarps = kMatchThreads / 32;
+constexpr int kTile = 512;                       // bytes per warp iteration
+constexpr int kWarpSmem = 544 + 544;             // s_in (+halo), s_out (+halo)
+constexpr int kWarmTiles = 8;                    // warm-up looks back at most 4 KB for a '\n'
+
+struct MatchArgs {
+    DevProg P;
+    const uint8_t *in;
+    uint8_t *out;
+    size_t n;
+    uint32_t *status;
+    uint32_t smem_states;        // states [0, smem_states) of ctrans live in shared memory
+    uint32_t row0_replicated;    // 1: row0 is stored 32x (bank = lane), conflict free
+    size_t tiles_per_warp;
+};
+
+__device__ __forceinline__ uint4 ldg_vec(const uint8_t *p) {
+    uint4 r;
+    asm volatile("ld.global.nc.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "l"(p));
+    return r;
+}
+
+// 16 input bytes at `pos`, '\n'-padded beyond n
+__device__ __forceinline__ uint4 load_padded(const uint8_t *__restrict__ in, size_t pos, size_t n) {
+    if (pos + 16 <= n) return ldg_vec(in + pos);
+    uint32_t w[4] = {0x0A0A0A0Au, 0x0A0A0A0Au, 0x0A0A0A0Au, 0x0A0A0A0Au};
+    for (int k = 0; k < 16; ++k)
+        if (pos + k < n) w[k >> 2] = (w[k >> 2] & ~(0xFFu << ((k & 3) * 8))) | ((uint32_t)in[pos + k] << ((k & 3) * 8));
+    return make_uint4(w[0], w[1], w[2], w[3]);
+}
+
+struct MatchTables {
+    const uint32_t *row0_s;      // shared
+    const uint8_t *classmap_s;   // shared
+    const uint32_t *ctrans_s;    // shared, first smem_states rows
+    const uint32_t *ctrans_g;    // global, all rows
+    uint32_t n_classes, smem_states, row0_stride, lane;
+};
+
+__device__ __forceinline__ uint32_t row0_at(const MatchTables &T, uint32_t c) {
+    return T.row0_s[c * T.row0_stride + (T.row0_stride == 1 ? 0 : T.lane)];
+}
+__device__ __forceinline__ uint32_t step_at(const MatchTables &T, uint32_t s, uint32_t c) {
+    uint32_t idx = s * T.n_classes + T.classmap_s[c];
+    return s < T.smem_states ? T.ctrans_s[idx] : __ldg(T.ctrans_g + idx);
+}
+
+// One finished walk: m = bytes consumed by the match (0 = no match).
+template <bool ALL_SMEM>
+__device__ __forceinline__ uint32_t walk_from(const MatchTables &T, const uint8_t *s_in, uint32_t p) {
+    uint32_t lo = row0_at(T, s_in[p]);
+    uint32_t i = 1, m = (lo & DSA_E_MARK) ? 1u : 0u;
+    while (!(lo & DSA_E_DECIDED)) {
+        const uint32_t c = s_in[p + i];                              // p + i <= 511 + 16: inside the halo
+        const uint32_t idx = (lo & 0xFFFFFFu) * T.n_classes + T.classmap_s[c];
+        const uint32_t nx = (ALL_SMEM || (lo & 0xFFFFFFu) < T.smem_states) ? T.ctrans_s[idx] : __ldg(T.ctrans_g + idx);
+        if ((nx & 0xFFFFFFu) == DSA_DEAD) break;                     // '\n' (line end, padding) is dead
+        lo = nx;
+        ++i;
+        if (lo & DSA_E_MARK) m = i;
+        if (i >= 16) break;
+    }
+    return (lo & (DSA_E_DECIDED | DSA_E_HASFINAL)) ? m : 0u;
+}
+
+// Output bytes of the real match at tile position p (length m) -> s_out[p .. p+m)
+template <bool ALL_SMEM>
+__device__ __forceinline__ void emit_match(const MatchArgs &a, const MatchTables &T, const uint8_t *s_in,
+                                           uint8_t *s_out, uint32_t p, uint32_t m, uint32_t &status) {
+    Sink o;
+    o.p = s_out;
+    o.n = p;
+    if (a.P.flags & PF_OUT_LATE) {
+        // replay on the compact table (shared memory); only the last transition and the last state print
+        uint32_t lo = row0_at(T, s_in[p]), i = 1;
+        uint32_t edge = T.classmap_s[s_in[p]];                       // index into trans of the last transition
+        while (!(lo & DSA_E_DECIDED)) {
+            const uint32_t idx = (lo & 0xFFFFFFu) * T.n_classes + T.classmap_s[s_in[p + i]];
+            const uint32_t nx = (ALL_SMEM || (lo & 0xFFFFFFu) < T.smem_states) ? T.ctrans_s[idx] : __ldg(T.ctrans_g + idx);
+            if ((nx & 0xFFFFFFu) == DSA_DEAD) break;
+            lo = nx; edge = idx; ++i;
+            if (i >= 16) break;
+        }
+        if (lo & DSA_E_DECIDED) put_ref(o, a.P.pool, (uint32_t)(__ldg(a.P.trans + edge) >> 32));
+        put_ref(o, a.P.pool, (uint32_t)(__ldg(a.P.sinfo + (lo & 0xFFFFFFu)) >> 32));
+    } else {
+        // general: replay with the full table, print every transition's string, then the final string
+        uint32_t s = 0, i = 0;
+        for (;;) {
+            uint64_t e = __ldg(a.P.trans + (size_t)s * a.P.n_classes + T.classmap_s[s_in[p + i]]);
+            uint32_t lo = (uint32_t)e;
+            if ((lo & 0xFFFFFFu) == DSA_DEAD) break;
+            put_ref(o, a.P.pool, (uint32_t)(e >> 32));
+            s = lo & 0xFFFFFFu;
+            ++i;
+            if ((lo & DSA_E_DECIDED) || i >= 16) break;
+        }
+        put_ref(o, a.P.pool, (uint32_t)(__ldg(a.P.sinfo + s) >> 32));
+    }
+    if (o.n - p != m) status |= ST_IRREGULAR;                        // cannot happen for a length-preserving program
+}
+
+template <bool STORE, bool ALL_SMEM>
+__device__ __forceinline__ void match_tile(const MatchArgs &a, const MatchTables &T, uint8_t *s_in,
+                                           uint8_t *s_out, size_t base, uint4 x, uint4 halo_in, uint32_t lane,
+                                           uint32_t first_valid, uint32_t &carry_e, uint4 &carry_halo,
+                                           uint32_t &nul_acc, uint32_t &status) {
+    // ---- A: stage the tile (input and default output = raw copy) -----------------------------------
+    *reinterpret_cast<uint4 *>(s_in + lane * 16) = x;
+    *reinterpret_cast<uint4 *>(s_out + lane * 16) = x;
+    if (lane == 0) {
+        *reinterpret_cast<uint4 *>(s_in + kTile) = halo_in;
+        *reinterpret_cast<uint4 *>(s_out + kTile) = halo_in;
+    }
+    nul_acc |= ((x.x - 0x01010101u) & ~x.x) | ((x.y - 0x01010101u) & ~x.y) | ((x.z - 0x01010101u) & ~x.z) | ((x.w - 0x01010101u) & ~x.w);
+
+    // ---- B: first transition at every position -> candidate mask -----------------------------------
+    uint32_t cand = 0;
+    {
+        const uint32_t w[4] = {x.x, x.y, x.z, x.w};
+#pragma unroll
+        for (int j = 0; j < 16; ++j) {
+            uint32_t c = (w[j >> 2] >> ((j & 3) * 8)) & 0xFFu;
+            uint32_t lo = row0_at(T, c);
+            cand |= ((lo & 0xFFFFFFu) != DSA_DEAD ? 1u : 0u) << j;
+        }
+    }
+    {
+        const uint32_t my0 = lane * 16;
+        if (first_valid > my0) cand &= (first_valid - my0 >= 16) ? 0u : (0xFFFFu << (first_valid - my0));
+    }
+    __syncwarp();
+
+    // ---- C: candidates finish their walk; matches stay in registers: C = mask, lens = 4 bits each ----
+    uint32_t C = 0;
+    unsigned long long lens = 0;                                     // (m - 1) per position
+    while (cand) {
+        const uint32_t j = __ffs(cand) - 1;
+        cand &= cand - 1;
+        const uint32_t m = walk_from<ALL_SMEM>(T, s_in, lane * 16 + j);
+        if (m) { C |= 1u << j; lens |= (unsigned long long)(m - 1) << (4 * j); }
+    }
+
+    // ---- D: which matches are real (start outside every earlier match) ---------------------------------
+    const uint32_t first = C ? (uint32_t)__ffs(C) - 1 : 16u;
+    uint32_t e_used = (lane == 0) ? carry_e : 0u, real = 0, e_out = 0;
+    auto chain = [&](uint32_t e) {
+        uint32_t pos = e, r = 0;
+        uint32_t Cm = C & (0xFFFFu << pos);                          // e <= 15
+        while (Cm) {
+            uint32_t j = __ffs(Cm) - 1;
+            r |= 1u << j;
+            pos = j + 1 + ((uint32_t)(lens >> (4 * j)) & 15u);
+            Cm = pos < 16 ? (C & (0xFFFFu << pos)) : 0u;
+        }
+        real = r;
+        e_out = pos > 16 ? pos - 16 : 0u;
+    };
+    chain(e_used);
+    for (;;) {
+        uint32_t prev = __shfl_up_sync(0xFFFFFFFFu, e_out, 1);
+        if (lane == 0) prev = carry_e;
+        const bool differs = prev != e_used;
+        const bool need = differs && (prev > first || e_used > first);
+        if (differs) e_used = prev;
+        if (!__any_sync(0xFFFFFFFFu, need)) break;
+        if (need) chain(e_used);
+    }
+
+    // ---- E: real matches overwrite their span of the output tile ---------------------------------------
+    if (lane == 0 && carry_e) {
+        const uint32_t h[4] = {carry_halo.x, carry_halo.y, carry_halo.z, carry_halo.w};
+        for (uint32_t k = 0; k < carry_e; ++k) s_out[k] = (uint8_t)(h[k >> 2] >> ((k & 3) * 8));
+    }
+    while (real) {
+        const uint32_t j = __ffs(real) - 1;
+        real &= real - 1;
+        emit_match<ALL_SMEM>(a, T, s_in, s_out, lane * 16 + j, 1 + ((uint32_t)(lens >> (4 * j)) & 15u), status);
+    }
+    __syncwarp();
+    if (STORE) {
+        const size_t my = base + (size_t)lane * 16;
+        uint4 y = *reinterpret_cast<const uint4 *>(s_out + lane * 16);
+        if (my + 16 <= a.n) {
+            *reinterpret_cast<uint4 *>(a.out + my) = y;
+        } else if (my < a.n) {
+            const uint32_t w[4] = {y.x, y.y, y.z, y.w};
+            for (int k = 0; k < 16 && my + k < a.n; ++k) a.out[my + k] = (uint8_t)(w[k >> 2] >> ((k & 3) * 8));
+        }
+    }
+    carry_e = __shfl_sync(0xFFFFFFFFu, e_out, 31);
+    carry_halo = *reinterpret_cast<const uint4 *>(s_out + kTile);     // every lane reads it; only lane 0 uses it
+    __syncwarp();
+}
+
+template <bool ALL_SMEM>
+__global__ void __launch_bounds__(kMatchThreads)
+k_match(MatchArgs a) {
+    extern __shared__ __align__(16) uint8_t smem[];
+    const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const uint32_t row0_words = a.row0_replicated ? 256u * 32u : 256u;
+    uint32_t *row0_s = reinterpret_cast<uint32_t *>(smem);
+    uint8_t *classmap_s = smem + row0_words * 4;
+    uint32_t *ctrans_s = reinterpret_cast<uint32_t *>(classmap_s + 256);
+    const uint32_t ct_words = a.smem_states * a.P.n_classes;
+    uint8_t *warp_base = reinterpret_cast<uint8_t *>(ctrans_s + ((ct_words + 3) & ~3u)) + warp * kWarpSmem;
+
+    for (uint32_t k = threadIdx.x; k < row0_words; k += blockDim.x)
+        row0_s[k] = __ldg(a.P.row0 + (a.row0_replicated ? (k >> 5) : k));
+    for (uint32_t k = threadIdx.x; k < 256; k += blockDim.x) classmap_s[k] = __ldg(a.P.classmap + k);
+    for (uint32_t k = threadIdx.x; k < ct_words; k += blockDim.x) ctrans_s[k] = __ldg(a.P.ctrans + k);
+    __syncthreads();
+
+    MatchTables T;
+    T.row0_s = row0_s; T.classmap_s = classmap_s; T.ctrans_s = ctrans_s; T.ctrans_g = a.P.ctrans;
+    T.n_classes = a.P.n_classes; T.smem_states = a.smem_states; T.row0_stride = a.row0_replicated ? 32u : 1u; T.lane = lane;
+
+    uint8_t *s_in = warp_base, *s_out = warp_base + 544;
+    const size_t n = a.n;
+    const size_t n_tiles = (n + kTile - 1) / kTile;
+    const size_t gwarp = (size_t)blockIdx.x * kMatchWarps + warp;
+    const size_t t0 = gwarp * a.tiles_per_warp;
+    size_t t1 = t0 + a.tiles_per_warp;
+    if (t1 > n_tiles) t1 = n_tiles;
+    uint32_t status = 0, nul_acc = 0;
+    if (t0 < t1) {
+        uint32_t carry_e = 0;
+        uint4 carry_halo = make_uint4(0, 0, 0, 0);
+        // ---- warm-up: the chain state at t0 is only known from the last '\n' before it -------------
+        size_t tw = t0;
+        uint32_t first_valid = 0;
+        if (t0 > 0) {
+            bool found = false;
+            for (int k = 1; k <= kWarmTiles && !found; ++k) {
+                if ((size_t)k > t0) { tw = 0; first_valid = 0; found = true; break; }   // reached the buffer start
+                const size_t tb = (t0 - k) * (size_t)kTile;
+                uint4 v = ldg_vec(a.in + tb + lane * 16);                              // full tile: tb + 512 <= t0*512 <= n
+                const uint32_t w[4] = {v.x, v.y, v.z, v.w};
+                int last = -1;
+#pragma unroll
+                for (int j = 0; j < 16; ++j)
+                    if (((w[j >> 2] >> ((j & 3) * 8)) & 0xFFu) == '\n') last = j;
+                uint32_t has = __ballot_sync(0xFFFFFFFFu, last >= 0);
+                if (has) {
+                    int src = 31 - __clz(has);
+                    int lj = __shfl_sync(0xFFFFFFFFu, last, src);
+                    uint32_t pos_in_tile = (uint32_t)src * 16 + (uint32_t)lj + 1;        // first byte after the '\n'
+                    if (pos_in_tile >= (uint32_t)kTile) { tw = t0 - k + 1; first_valid = 0; }
+                    else { tw = t0 - k; first_valid = pos_in_tile; }
+                    found = true;
+                }
+            }
+            if (!found) { status |= ST_IRREGULAR; tw = t0; }     // line longer than the window: general path
+        }
+        // ---- tiles -----------------------------------------------------------------------------------
+        size_t base = tw * (size_t)kTile;
+        uint4 x = load_padded(a.in, base + lane * 16, n);
+        for (size_t t = tw; t < t1; ++t) {
+            base = t * (size_t)kTile;
+            uint4 halo_in = load_padded(a.in, base + kTile, n);
+            uint4 x_next = make_uint4(0x0A0A0A0Au, 0x0A0A0A0Au, 0x0A0A0A0Au, 0x0A0A0A0Au);
+            if (t + 1 < t1) x_next = load_padded(a.in, base + kTile + lane * 16, n);   // prefetch
+            if (t < t0) match_tile<false, ALL_SMEM>(a, T, s_in, s_out, base, x, halo_in, lane, first_valid, carry_e, carry_halo, nul_acc, status);
+            else        match_tile<true, ALL_SMEM>(a, T, s_in, s_out, base, x, halo_in, lane, first_valid, carry_e, carry_halo, nul_acc, status);
+            first_valid = 0;
+            x = x_next;
+        }
+    }
+    if (nul_acc & 0x80808080u) status |= ST_IRREGULAR;
+    if (blockIdx.x == 0 && threadIdx.x == 0 && n && a.in[n - 1] != '\n') status |= ST_IRREGULAR;
+    if (status) atomicOr(a.status, status);
+}
+
+}  // namespace trre
