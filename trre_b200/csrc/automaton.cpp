@@ -363,6 +363,7 @@ struct Program {
     std::vector<uint64_t> trans;
     std::vector<uint64_t> sinfo;
     std::vector<uint8_t> pool;
+    std::vector<uint32_t> eout;      // see BlobHeader::off_eout
 };
 
 class PoolWriter {
@@ -437,6 +438,34 @@ void analyse_and_pack(const std::vector<RawState> &st, const StringPool &sp, int
                           ((st[e.next].flags & DSA_S_HAS_FINAL) ? (uint32_t)DSA_E_HASFINAL : 0u) |
                           ((st[e.next].flags & DSA_S_DIVERGE) ? (uint32_t)DSA_E_DIVERGE : 0u);
             P.trans[(size_t)s * P.n_classes + P.classmap[e.byte]] = pack64(lo, pw.ref(e.out_id));
+        }
+    }
+    // combined "what a match prints" strings for the position-parallel kernel: one copy per match
+    {
+        bool late = true;
+        for (uint32_t s = 0; s < S && late; ++s)
+            for (const RawEdge &e : st[s].edges)
+                if (!(st[e.next].flags & DSA_S_DECIDED) && !sp.get(e.out_id).empty()) { late = false; break; }
+        if (late) {
+            std::unordered_map<std::string, uint32_t> placed;
+            auto place = [&](const std::string &str) -> uint32_t {
+                if (str.empty()) return 0;
+                auto it = placed.find(str);
+                if (it != placed.end()) return it->second;
+                uint32_t off = (uint32_t)pw.bytes.size();
+                pw.bytes.insert(pw.bytes.end(), str.begin(), str.end());
+                placed.emplace(str, off);
+                return off;
+            };
+            P.eout.assign((size_t)S * P.n_classes + S, 0);
+            for (uint32_t s = 0; s < S; ++s) {
+                if ((st[s].flags & DSA_S_HAS_FINAL) && !(st[s].flags & DSA_S_DECIDED))
+                    P.eout[(size_t)S * P.n_classes + s] = place(sp.get(st[s].fin_id));
+                for (const RawEdge &e : st[s].edges)
+                    if (st[e.next].flags & DSA_S_DECIDED)
+                        P.eout[(size_t)s * P.n_classes + P.classmap[e.byte]] = place(sp.get(e.out_id) + sp.get(st[e.next].fin_id));
+            }
+            if (pw.bytes.size() >= (1u << 24)) P.eout.clear();
         }
     }
     P.pool = std::move(pw.bytes);
@@ -553,6 +582,7 @@ std::vector<uint8_t> assemble(const Program &P, const Nft &g) {
     if (matchable) {
         h.off_row0 = (uint32_t)off; off += 256 * 4;
         h.off_ctrans = (uint32_t)off; off += P.trans.size() * 4; off = align16(off);
+        if (!P.eout.empty()) { h.off_eout = (uint32_t)off; off += P.eout.size() * 4; off = align16(off); }
     }
     if (off >= (1ull << 31)) throw PatternError{TRRE_E_UNSUPPORTED, "error: compiled tables exceed 2 GiB\n"};
     h.magic = 0x32425254u;  // "TRB2"
@@ -587,6 +617,7 @@ std::vector<uint8_t> assemble(const Program &P, const Nft &g) {
         for (int c = 0; c < 256; ++c) row0[c] = (uint32_t)(P.trans[P.classmap[c]] & 0xFFFFFFFFu);
         for (size_t k = 0; k < P.trans.size(); ++k) ct[k] = (uint32_t)(P.trans[k] & 0xFFFFFFFFu);
     }
+    if (h.off_eout) std::memcpy(blob.data() + h.off_eout, P.eout.data(), P.eout.size() * 4);
     if (h.off_pairlut) {
         // pair[c0 | c1 << 8] = LUT[c0] | LUT[c1] << 8 : one shared-memory lookup maps two input bytes
         uint16_t *pair = reinterpret_cast<uint16_t *>(blob.data() + h.off_pairlut);

@@ -76,7 +76,8 @@ struct BlobHeader {
     uint32_t off_pairlut;      // u16[65536] (TRRE_EXEC_BYTEMAP): LUT applied to two bytes at once, 0 if absent
     uint32_t off_row0;         // u32[256]: low word of trans[start][class(byte)] by raw byte (k_match), 0 if absent
     uint32_t off_ctrans;       // u32[dsa_states * n_classes]: low words of trans (k_match), 0 if absent
-    uint32_t reserved[1];
+    uint32_t off_eout;         // u32[dsa_states * n_classes]: (PF_OUT_LATE) pool offset of out(edge)+fin(target) for edges
+                               // into DECIDED states; u32[dsa_states] fin offsets follow (pending FINAL). 0 if absent
 };
 
 struct NftFlat {               // 12 bytes, device layout of trre_nft.c:334-340

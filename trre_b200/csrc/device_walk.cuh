@@ -25,6 +25,8 @@ struct DevProg {
     const uint16_t *pairlut;       // TRRE_EXEC_BYTEMAP only
     const uint32_t *row0;          // k_match: first step by raw byte
     const uint32_t *ctrans;        // k_match: low words of trans
+    const uint32_t *eout;          // k_match: pool offsets of what a match prints (edge table, then per-state)
+    uint32_t pool_bytes;
     uint32_t n_states;
     uint32_t max_depth;
     const uint64_t *trans;

@@ -59,7 +59,7 @@ struct DeviceState {
     cudaStream_t slot_stream[kSlots] = {nullptr, nullptr, nullptr};
     size_t slot_cap = 0;
     // k_match launch plan
-    uint32_t match_repl = 0, match_states = 0;
+    uint32_t match_repl = 0, match_states = 0, match_pool = 0;
     size_t match_smem = 0;
     int match_blocks = 0;
 };
@@ -122,6 +122,8 @@ int get_state(const trre_prog *cp, int device, DeviceState **out) {
     d->P.pairlut = h.off_pairlut ? reinterpret_cast<const uint16_t *>(d->d_blob + h.off_pairlut) : nullptr;
     d->P.row0 = h.off_row0 ? reinterpret_cast<const uint32_t *>(d->d_blob + h.off_row0) : nullptr;
     d->P.ctrans = h.off_ctrans ? reinterpret_cast<const uint32_t *>(d->d_blob + h.off_ctrans) : nullptr;
+    d->P.eout = h.off_eout ? reinterpret_cast<const uint32_t *>(d->d_blob + h.off_eout) : nullptr;
+    d->P.pool_bytes = h.pool_bytes;
     d->P.n_states = h.dsa_states;
     d->P.max_depth = h.max_depth;
     d->P.trans = reinterpret_cast<const uint64_t *>(d->d_blob + h.off_trans);
@@ -137,19 +139,20 @@ int get_state(const trre_prog *cp, int device, DeviceState **out) {
         // shared-memory plan of k_match: replicate row0 per bank when everything fits, else cache the
         // first (shallowest: states are numbered breadth first) rows of the compact table
         const size_t warp_bytes = (size_t)kMatchWarps * kWarpSmem;
-        const size_t ct_full = (size_t)h.dsa_states * h.n_classes * 4;
+        const size_t ct_full = (((size_t)h.dsa_states * h.n_classes + 3) & ~(size_t)3) * 4;
         const size_t budget = 108 * 1024;                       // two CTAs per SM
-        if (32768 + 256 + ((ct_full + 15) & ~(size_t)15) + warp_bytes <= budget) {
+        d->match_pool = h.pool_bytes <= 4096 ? 1 : 0;
+        const size_t fixed = 1024 + 256 + (d->match_pool ? ((h.pool_bytes + 15) & ~15u) : 0) + warp_bytes;
+        if (32768 + fixed + ct_full <= budget) {
             d->match_repl = 1;
             d->match_states = h.dsa_states;
         } else {
             d->match_repl = 0;
-            size_t room = budget - 1024 - 256 - warp_bytes;
-            size_t rows = room / ((size_t)h.n_classes * 4);
+            size_t rows = (budget - fixed) / ((size_t)h.n_classes * 4);
             d->match_states = (uint32_t)std::min<size_t>(rows, h.dsa_states);
         }
         size_t ct_words = ((size_t)d->match_states * h.n_classes + 3) & ~(size_t)3;
-        d->match_smem = (d->match_repl ? 32768 : 1024) + 256 + ct_words * 4 + warp_bytes;
+        d->match_smem = (d->match_repl ? 32768 : 0) + fixed + ct_words * 4;
         int per_sm = 1;
         if (d->match_states == h.dsa_states) {
             CUDA_TRY(cudaFuncSetAttribute(k_match<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)d->match_smem));
@@ -226,7 +229,7 @@ int launch_fast(const trre_prog *p, DeviceState *d, const uint8_t *d_in, size_t 
     } else if (d->P.row0 && aligned && (reinterpret_cast<uintptr_t>(d_in) & 15) == 0 && !std::getenv("TRRE_NO_MATCH_KERNEL")) {
         MatchArgs m{};
         m.P = d->P; m.in = d_in; m.out = d_out; m.n = n; m.status = status;
-        m.smem_states = d->match_states; m.row0_replicated = d->match_repl;
+        m.smem_states = d->match_states; m.row0_replicated = d->match_repl; m.pool_in_smem = d->match_pool;
         const size_t n_tiles = (n + kTile - 1) / kTile;
         // every warp owns a contiguous span of tiles; keep spans >= 16 tiles so the warm-up stays cheap
         size_t blocks = std::min<size_t>((size_t)d->match_blocks, (n_tiles + 16 * kMatchWarps - 1) / (16 * kMatchWarps));

@@ -29,7 +29,7 @@ namespace trre {
 constexpr int kMatchThreads = 512;
 constexpr int kMatchWarps = kMatchThreads / 32;
 constexpr int kTile = 512;                       // bytes per warp iteration
-constexpr int kWarpSmem = 544 + 544;             // s_in (+halo), s_out (+halo)
+constexpr int kWarpSmem = 544 + 544 + 1024;      // s_in (+halo), s_out (+halo), list of real matches (u16 x 512)
 constexpr int kWarmTiles = 8;                    // warm-up looks back at most 4 KB for a '\n'
 
 struct MatchArgs {
@@ -39,7 +39,8 @@ struct MatchArgs {
     size_t n;
     uint32_t *status;
     uint32_t smem_states;        // states [0, smem_states) of ctrans live in shared memory
-    uint32_t row0_replicated;    // 1: row0 is stored 32x (bank = lane), conflict free
+    uint32_t row0_replicated;    // 1: a 32x replicated live/dead table (bank = lane) serves step B
+    uint32_t pool_in_smem;       // 1: the string pool is copied to shared memory
     size_t tiles_per_warp;
 };
 
@@ -59,25 +60,19 @@ __device__ __forceinline__ uint4 load_padded(const uint8_t *__restrict__ in, siz
 }
 
 struct MatchTables {
-    const uint32_t *row0_s;      // shared
+    const uint32_t *live_s;      // shared: 1/0 per byte, replicated 32x (bank = lane); nullptr when not replicated
+    const uint32_t *row0_s;      // shared: first transition by raw byte
     const uint8_t *classmap_s;   // shared
     const uint32_t *ctrans_s;    // shared, first smem_states rows
     const uint32_t *ctrans_g;    // global, all rows
-    uint32_t n_classes, smem_states, row0_stride, lane;
+    const uint8_t *pool;         // shared copy when small, else global
+    uint32_t n_classes, smem_states, lane;
 };
-
-__device__ __forceinline__ uint32_t row0_at(const MatchTables &T, uint32_t c) {
-    return T.row0_s[c * T.row0_stride + (T.row0_stride == 1 ? 0 : T.lane)];
-}
-__device__ __forceinline__ uint32_t step_at(const MatchTables &T, uint32_t s, uint32_t c) {
-    uint32_t idx = s * T.n_classes + T.classmap_s[c];
-    return s < T.smem_states ? T.ctrans_s[idx] : __ldg(T.ctrans_g + idx);
-}
 
 // One finished walk: m = bytes consumed by the match (0 = no match).
 template <bool ALL_SMEM>
 __device__ __forceinline__ uint32_t walk_from(const MatchTables &T, const uint8_t *s_in, uint32_t p) {
-    uint32_t lo = row0_at(T, s_in[p]);
+    uint32_t lo = T.row0_s[s_in[p]];
     uint32_t i = 1, m = (lo & DSA_E_MARK) ? 1u : 0u;
     while (!(lo & DSA_E_DECIDED)) {
         const uint32_t c = s_in[p + i];                              // p + i <= 511 + 16: inside the halo
@@ -96,13 +91,10 @@ __device__ __forceinline__ uint32_t walk_from(const MatchTables &T, const uint8_
 template <bool ALL_SMEM>
 __device__ __forceinline__ void emit_match(const MatchArgs &a, const MatchTables &T, const uint8_t *s_in,
                                            uint8_t *s_out, uint32_t p, uint32_t m, uint32_t &status) {
-    Sink o;
-    o.p = s_out;
-    o.n = p;
-    if (a.P.flags & PF_OUT_LATE) {
-        // replay on the compact table (shared memory); only the last transition and the last state print
-        uint32_t lo = row0_at(T, s_in[p]), i = 1;
-        uint32_t edge = T.classmap_s[s_in[p]];                       // index into trans of the last transition
+    if (a.P.eout) {
+        // PF_OUT_LATE: replay on the compact table; the last transition (or the pending state) names ONE string
+        uint32_t lo = T.row0_s[s_in[p]], i = 1;
+        uint32_t edge = T.classmap_s[s_in[p]];
         while (!(lo & DSA_E_DECIDED)) {
             const uint32_t idx = (lo & 0xFFFFFFu) * T.n_classes + T.classmap_s[s_in[p + i]];
             const uint32_t nx = (ALL_SMEM || (lo & 0xFFFFFFu) < T.smem_states) ? T.ctrans_s[idx] : __ldg(T.ctrans_g + idx);
@@ -110,29 +102,33 @@ __device__ __forceinline__ void emit_match(const MatchArgs &a, const MatchTables
             lo = nx; edge = idx; ++i;
             if (i >= 16) break;
         }
-        if (lo & DSA_E_DECIDED) put_ref(o, a.P.pool, (uint32_t)(__ldg(a.P.trans + edge) >> 32));
-        put_ref(o, a.P.pool, (uint32_t)(__ldg(a.P.sinfo + (lo & 0xFFFFFFu)) >> 32));
-    } else {
-        // general: replay with the full table, print every transition's string, then the final string
-        uint32_t s = 0, i = 0;
-        for (;;) {
-            uint64_t e = __ldg(a.P.trans + (size_t)s * a.P.n_classes + T.classmap_s[s_in[p + i]]);
-            uint32_t lo = (uint32_t)e;
-            if ((lo & 0xFFFFFFu) == DSA_DEAD) break;
-            put_ref(o, a.P.pool, (uint32_t)(e >> 32));
-            s = lo & 0xFFFFFFu;
-            ++i;
-            if ((lo & DSA_E_DECIDED) || i >= 16) break;
-        }
-        put_ref(o, a.P.pool, (uint32_t)(__ldg(a.P.sinfo + s) >> 32));
+        const uint32_t slot = (lo & DSA_E_DECIDED) ? edge : a.P.n_states * T.n_classes + (lo & 0xFFFFFFu);
+        const uint8_t *src = T.pool + __ldg(a.P.eout + slot);
+        for (uint32_t k = 0; k < m; ++k) s_out[p + k] = src[k];
+        return;
     }
+    // general: replay with the full table, print every transition's string, then the final string
+    Sink o;
+    o.p = s_out;
+    o.n = p;
+    uint32_t s = 0, i = 0;
+    for (;;) {
+        uint64_t e = __ldg(a.P.trans + (size_t)s * a.P.n_classes + T.classmap_s[s_in[p + i]]);
+        uint32_t lo = (uint32_t)e;
+        if ((lo & 0xFFFFFFu) == DSA_DEAD) break;
+        put_ref(o, a.P.pool, (uint32_t)(e >> 32));
+        s = lo & 0xFFFFFFu;
+        ++i;
+        if ((lo & DSA_E_DECIDED) || i >= 16) break;
+    }
+    put_ref(o, a.P.pool, (uint32_t)(__ldg(a.P.sinfo + s) >> 32));
     if (o.n - p != m) status |= ST_IRREGULAR;                        // cannot happen for a length-preserving program
 }
 
 template <bool STORE, bool ALL_SMEM>
 __device__ __forceinline__ void match_tile(const MatchArgs &a, const MatchTables &T, uint8_t *s_in,
-                                           uint8_t *s_out, size_t base, uint4 x, uint4 halo_in, uint32_t lane,
-                                           uint32_t first_valid, uint32_t &carry_e, uint4 &carry_halo,
+                                           uint8_t *s_out, uint16_t *s_list, size_t base, uint4 x, uint4 halo_in,
+                                           uint32_t lane, uint32_t first_valid, uint32_t &carry_e, uint4 &carry_halo,
                                            uint32_t &nul_acc, uint32_t &status) {
     // ---- A: stage the tile (input and default output = raw copy) -----------------------------------
     *reinterpret_cast<uint4 *>(s_in + lane * 16) = x;
@@ -143,15 +139,23 @@ __device__ __forceinline__ void match_tile(const MatchArgs &a, const MatchTables
     }
     nul_acc |= ((x.x - 0x01010101u) & ~x.x) | ((x.y - 0x01010101u) & ~x.y) | ((x.z - 0x01010101u) & ~x.z) | ((x.w - 0x01010101u) & ~x.w);
 
-    // ---- B: first transition at every position -> candidate mask -----------------------------------
+    // ---- B: can an attempt starting with this byte survive its first transition? -> candidate mask ---
     uint32_t cand = 0;
     {
         const uint32_t w[4] = {x.x, x.y, x.z, x.w};
+        if (T.live_s) {
+            const uint32_t *live_lane = T.live_s + lane;
 #pragma unroll
-        for (int j = 0; j < 16; ++j) {
-            uint32_t c = (w[j >> 2] >> ((j & 3) * 8)) & 0xFFu;
-            uint32_t lo = row0_at(T, c);
-            cand |= ((lo & 0xFFFFFFu) != DSA_DEAD ? 1u : 0u) << j;
+            for (int j = 0; j < 16; ++j) {
+                uint32_t c = (w[j >> 2] >> ((j & 3) * 8)) & 0xFFu;
+                cand |= live_lane[c << 5] << j;                       // conflict free: bank == lane
+            }
+        } else {
+#pragma unroll
+            for (int j = 0; j < 16; ++j) {
+                uint32_t c = (w[j >> 2] >> ((j & 3) * 8)) & 0xFFu;
+                cand |= ((T.row0_s[c] & 0xFFFFFFu) != DSA_DEAD ? 1u : 0u) << j;
+            }
         }
     }
     {
@@ -196,15 +200,30 @@ __device__ __forceinline__ void match_tile(const MatchArgs &a, const MatchTables
         if (need) chain(e_used);
     }
 
-    // ---- E: real matches overwrite their span of the output tile ---------------------------------------
+    // ---- E: real matches overwrite their span of the output tile; the work is dealt round the warp ------
     if (lane == 0 && carry_e) {
         const uint32_t h[4] = {carry_halo.x, carry_halo.y, carry_halo.z, carry_halo.w};
         for (uint32_t k = 0; k < carry_e; ++k) s_out[k] = (uint8_t)(h[k >> 2] >> ((k & 3) * 8));
     }
-    while (real) {
-        const uint32_t j = __ffs(real) - 1;
-        real &= real - 1;
-        emit_match<ALL_SMEM>(a, T, s_in, s_out, lane * 16 + j, 1 + ((uint32_t)(lens >> (4 * j)) & 15u), status);
+    {
+        uint32_t cnt = __popc(real), incl = cnt;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            uint32_t y = __shfl_up_sync(0xFFFFFFFFu, incl, d);
+            if (lane >= (uint32_t)d) incl += y;
+        }
+        const uint32_t total = __shfl_sync(0xFFFFFFFFu, incl, 31);
+        uint32_t slot = incl - cnt;
+        while (real) {
+            const uint32_t j = __ffs(real) - 1;
+            real &= real - 1;
+            s_list[slot++] = (uint16_t)((lane * 16 + j) | (((uint32_t)(lens >> (4 * j)) & 15u) << 12));
+        }
+        __syncwarp();
+        for (uint32_t q = lane; q < total; q += 32) {
+            const uint32_t ent = s_list[q];
+            emit_match<ALL_SMEM>(a, T, s_in, s_out, ent & 0xFFFu, (ent >> 12) + 1, status);
+        }
     }
     __syncwarp();
     if (STORE) {
@@ -227,24 +246,35 @@ __global__ void __launch_bounds__(kMatchThreads)
 k_match(MatchArgs a) {
     extern __shared__ __align__(16) uint8_t smem[];
     const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const uint32_t row0_words = a.row0_replicated ? 256u * 32u : 256u;
-    uint32_t *row0_s = reinterpret_cast<uint32_t *>(smem);
-    uint8_t *classmap_s = smem + row0_words * 4;
-    uint32_t *ctrans_s = reinterpret_cast<uint32_t *>(classmap_s + 256);
+    // layout: [live 32 KB]? [row0 1 KB] [classmap 256] [pool copy]? [ctrans rows] [per warp: s_in, s_out, list]
+    uint8_t *cur = smem;
+    uint32_t *live_s = nullptr;
+    if (a.row0_replicated) { live_s = reinterpret_cast<uint32_t *>(cur); cur += 256 * 32 * 4; }
+    uint32_t *row0_s = reinterpret_cast<uint32_t *>(cur); cur += 1024;
+    uint8_t *classmap_s = cur; cur += 256;
+    uint8_t *pool_s = nullptr;
+    if (a.pool_in_smem) { pool_s = cur; cur += (a.P.pool_bytes + 15) & ~15u; }
+    uint32_t *ctrans_s = reinterpret_cast<uint32_t *>(cur);
     const uint32_t ct_words = a.smem_states * a.P.n_classes;
-    uint8_t *warp_base = reinterpret_cast<uint8_t *>(ctrans_s + ((ct_words + 3) & ~3u)) + warp * kWarpSmem;
+    cur += ((ct_words + 3) & ~3u) * 4;
+    uint8_t *warp_base = cur + warp * kWarpSmem;
 
-    for (uint32_t k = threadIdx.x; k < row0_words; k += blockDim.x)
-        row0_s[k] = __ldg(a.P.row0 + (a.row0_replicated ? (k >> 5) : k));
-    for (uint32_t k = threadIdx.x; k < 256; k += blockDim.x) classmap_s[k] = __ldg(a.P.classmap + k);
+    if (live_s)
+        for (uint32_t k = threadIdx.x; k < 256u * 32u; k += blockDim.x)
+            live_s[k] = (__ldg(a.P.row0 + (k >> 5)) & 0xFFFFFFu) != DSA_DEAD ? 1u : 0u;
+    for (uint32_t k = threadIdx.x; k < 256; k += blockDim.x) { row0_s[k] = __ldg(a.P.row0 + k); classmap_s[k] = __ldg(a.P.classmap + k); }
+    if (pool_s)
+        for (uint32_t k = threadIdx.x; k < a.P.pool_bytes; k += blockDim.x) pool_s[k] = __ldg(a.P.pool + k);
     for (uint32_t k = threadIdx.x; k < ct_words; k += blockDim.x) ctrans_s[k] = __ldg(a.P.ctrans + k);
     __syncthreads();
 
     MatchTables T;
-    T.row0_s = row0_s; T.classmap_s = classmap_s; T.ctrans_s = ctrans_s; T.ctrans_g = a.P.ctrans;
-    T.n_classes = a.P.n_classes; T.smem_states = a.smem_states; T.row0_stride = a.row0_replicated ? 32u : 1u; T.lane = lane;
+    T.live_s = live_s; T.row0_s = row0_s; T.classmap_s = classmap_s; T.ctrans_s = ctrans_s; T.ctrans_g = a.P.ctrans;
+    T.pool = pool_s ? pool_s : a.P.pool;
+    T.n_classes = a.P.n_classes; T.smem_states = a.smem_states; T.lane = lane;
 
     uint8_t *s_in = warp_base, *s_out = warp_base + 544;
+    uint16_t *s_list = reinterpret_cast<uint16_t *>(warp_base + 1088);
     const size_t n = a.n;
     const size_t n_tiles = (n + kTile - 1) / kTile;
     const size_t gwarp = (size_t)blockIdx.x * kMatchWarps + warp;
@@ -289,8 +319,8 @@ k_match(MatchArgs a) {
             uint4 halo_in = load_padded(a.in, base + kTile, n);
             uint4 x_next = make_uint4(0x0A0A0A0Au, 0x0A0A0A0Au, 0x0A0A0A0Au, 0x0A0A0A0Au);
             if (t + 1 < t1) x_next = load_padded(a.in, base + kTile + lane * 16, n);   // prefetch
-            if (t < t0) match_tile<false, ALL_SMEM>(a, T, s_in, s_out, base, x, halo_in, lane, first_valid, carry_e, carry_halo, nul_acc, status);
-            else        match_tile<true, ALL_SMEM>(a, T, s_in, s_out, base, x, halo_in, lane, first_valid, carry_e, carry_halo, nul_acc, status);
+            if (t < t0) match_tile<false, ALL_SMEM>(a, T, s_in, s_out, s_list, base, x, halo_in, lane, first_valid, carry_e, carry_halo, nul_acc, status);
+            else        match_tile<true, ALL_SMEM>(a, T, s_in, s_out, s_list, base, x, halo_in, lane, first_valid, carry_e, carry_halo, nul_acc, status);
             first_valid = 0;
             x = x_next;
         }
