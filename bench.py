@@ -355,6 +355,25 @@ def main():
     ms_per_step = ms_max / args.steps
     value = world * n / (ms_per_step * 1e-3) / 1e9
 
+    # ---- calibration outside the clock: a plain device copy of the SAME size (the roofline denominator in
+    # MEASURED_PEAKS.json was taken on 2 GiB buffers; fixed launch cost weighs more on 1 GiB)
+    copy_gbs = None
+    try:
+        for _ in range(3):
+            d_out[:n].copy_(d_in)
+        torch.cuda.synchronize()
+        c0, c1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        c0.record(stream)
+        for _ in range(10):
+            d_out[:n].copy_(d_in)
+        c1.record(stream)
+        torch.cuda.synchronize()
+        copy_gbs = 2.0 * n * 10 / (c0.elapsed_time(c1) * 1e-3) / 1e9
+        step()                      # restore d_out
+        prog.scan_status(device=local_rank, stream=sp)
+    except Exception:
+        pass
+
     # ---- verification outside the clock (size independent): compare with the byte map applied by torch ---
     verified = None
     if info["exec_kind"] == T.EXEC_BYTEMAP:
@@ -426,7 +445,8 @@ def main():
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                      "traffic": traffic, "kernel": kernel, "peak_source": peak_src,
                      "algorithmic_bytes_per_launch": algo_bytes,
-                     "input_read_frac_of_peak": value / world / peak},
+                     "input_read_frac_of_peak": value / world / peak,
+                     "torch_copy_same_size_gbs": copy_gbs},
         "verified": verified,
         "output_bytes_per_rank": sizes_all,
     }

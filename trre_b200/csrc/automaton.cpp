@@ -621,8 +621,11 @@ std::vector<uint8_t> assemble(const Program &P, const Nft &g) {
     if (h.off_pairlut) {
         // pair[c0 | c1 << 8] = LUT[c0] | LUT[c1] << 8 : one shared-memory lookup maps two input bytes
         uint16_t *pair = reinterpret_cast<uint16_t *>(blob.data() + h.off_pairlut);
+        // stored swizzled: the shared-memory bank of an entry would otherwise depend on bits 1-5 of the FIRST
+        // byte only (about 13 distinct banks on lowercase text); XOR-ing the low 5 bits of the second byte
+        // into the bank bits spreads a warp's 32 lookups over all banks (k_bytemap::map_word mirrors this)
         for (uint32_t v = 0; v < 65536; ++v)
-            pair[v] = (uint16_t)(P.lut[v & 0xFF] | ((uint32_t)P.lut[v >> 8] << 8));
+            pair[v ^ (((v >> 8) & 0x1Fu) << 1)] = (uint16_t)(P.lut[v & 0xFF] | ((uint32_t)P.lut[v >> 8] << 8));
     }
     return blob;
 }
