@@ -60,6 +60,7 @@ struct DeviceState {
     size_t slot_cap = 0;
     // k_match launch plan
     uint32_t match_repl = 0, match_states = 0, match_pool = 0;
+    int match_tab = 0;
     size_t match_smem = 0;
     int match_blocks = 0;
 };
@@ -143,24 +144,27 @@ int get_state(const trre_prog *cp, int device, DeviceState **out) {
         const size_t budget = 108 * 1024;                       // two CTAs per SM
         d->match_pool = h.pool_bytes <= 4096 ? 1 : 0;
         const size_t fixed = 1024 + 256 + (d->match_pool ? ((h.pool_bytes + 15) & ~15u) : 0) + warp_bytes;
-        if (32768 + fixed + ct_full <= budget) {
-            d->match_repl = 1;
-            d->match_states = h.dsa_states;
+        d->match_tab = TAB_PART;
+        size_t ct_bytes;
+        if (32768 + fixed + (size_t)h.dsa_states * 1024 <= budget) {          // small automaton: raw-byte rows
+            d->match_repl = 1; d->match_states = h.dsa_states; d->match_tab = TAB_WIDE;
+            ct_bytes = (size_t)h.dsa_states * 1024;
+        } else if (32768 + fixed + ct_full <= budget) {
+            d->match_repl = 1; d->match_states = h.dsa_states; d->match_tab = TAB_ALL;
+            ct_bytes = ct_full;
         } else {
             d->match_repl = 0;
             size_t rows = (budget - fixed) / ((size_t)h.n_classes * 4);
             d->match_states = (uint32_t)std::min<size_t>(rows, h.dsa_states);
+            if (d->match_states == h.dsa_states) d->match_tab = TAB_ALL;
+            ct_bytes = (((size_t)d->match_states * h.n_classes + 3) & ~(size_t)3) * 4;
         }
-        size_t ct_words = ((size_t)d->match_states * h.n_classes + 3) & ~(size_t)3;
-        d->match_smem = (d->match_repl ? 32768 : 0) + fixed + ct_words * 4;
+        d->match_smem = (d->match_repl ? 32768 : 0) + fixed + ct_bytes;
         int per_sm = 1;
-        if (d->match_states == h.dsa_states) {
-            CUDA_TRY(cudaFuncSetAttribute(k_match<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)d->match_smem));
-            CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_match<true>, kMatchThreads, d->match_smem));
-        } else {
-            CUDA_TRY(cudaFuncSetAttribute(k_match<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)d->match_smem));
-            CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_match<false>, kMatchThreads, d->match_smem));
-        }
+        const void *fn = d->match_tab == TAB_WIDE ? (const void *)k_match<TAB_WIDE>
+                       : d->match_tab == TAB_ALL  ? (const void *)k_match<TAB_ALL> : (const void *)k_match<TAB_PART>;
+        CUDA_TRY(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)d->match_smem));
+        CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fn, kMatchThreads, d->match_smem));
         d->match_blocks = d->sm_count * (per_sm < 1 ? 1 : per_sm);
     }
     p->dev[device] = d;
@@ -235,8 +239,9 @@ int launch_fast(const trre_prog *p, DeviceState *d, const uint8_t *d_in, size_t 
         size_t blocks = std::min<size_t>((size_t)d->match_blocks, (n_tiles + 16 * kMatchWarps - 1) / (16 * kMatchWarps));
         if (blocks < 1) blocks = 1;
         m.tiles_per_warp = (n_tiles + blocks * kMatchWarps - 1) / (blocks * kMatchWarps);
-        if (d->match_states == d->P.n_states) k_match<true><<<(int)blocks, kMatchThreads, d->match_smem, st>>>(m);
-        else k_match<false><<<(int)blocks, kMatchThreads, d->match_smem, st>>>(m);
+        if (d->match_tab == TAB_WIDE) k_match<TAB_WIDE><<<(int)blocks, kMatchThreads, d->match_smem, st>>>(m);
+        else if (d->match_tab == TAB_ALL) k_match<TAB_ALL><<<(int)blocks, kMatchThreads, d->match_smem, st>>>(m);
+        else k_match<TAB_PART><<<(int)blocks, kMatchThreads, d->match_smem, st>>>(m);
     } else {
         LineArgs a = make_args(d, d_in, n, d_out, n, status);
         int grid = (int)std::min<size_t>(a.n_groups, (size_t)d->sm_count * 64);

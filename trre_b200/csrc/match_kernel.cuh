@@ -29,7 +29,7 @@ namespace trre {
 constexpr int kMatchThreads = 512;
 constexpr int kMatchWarps = kMatchThreads / 32;
 constexpr int kTile = 512;                       // bytes per warp iteration
-constexpr int kWarpSmem = 544 + 544 + 1024;      // s_in (+halo), s_out (+halo), list of real matches (u16 x 512)
+constexpr int kWarpSmem = 544 + 544 + 1024 + 16; // s_in (+halo), s_out (+halo), list of real matches (u16 x 512), its counter
 constexpr int kWarmTiles = 8;                    // warm-up looks back at most 4 KB for a '\n'
 
 struct MatchArgs {
@@ -69,15 +69,25 @@ struct MatchTables {
     uint32_t n_classes, smem_states, lane;
 };
 
+// table layouts: TAB_PART  compact rows, the first smem_states of them in shared memory, the rest in L2
+//                TAB_ALL   compact rows, all in shared memory
+//                TAB_WIDE  one 256-entry row per state in shared memory, indexed by the raw byte (small automata)
+enum { TAB_PART = 0, TAB_ALL = 1, TAB_WIDE = 2 };
+
+template <int TAB>
+__device__ __forceinline__ uint32_t next_entry(const MatchTables &T, uint32_t s, uint32_t c) {
+    if (TAB == TAB_WIDE) return T.ctrans_s[(s << 8) | c];
+    const uint32_t idx = s * T.n_classes + T.classmap_s[c];
+    return (TAB == TAB_ALL || s < T.smem_states) ? T.ctrans_s[idx] : __ldg(T.ctrans_g + idx);
+}
+
 // One finished walk: m = bytes consumed by the match (0 = no match).
-template <bool ALL_SMEM>
+template <int TAB>
 __device__ __forceinline__ uint32_t walk_from(const MatchTables &T, const uint8_t *s_in, uint32_t p) {
     uint32_t lo = T.row0_s[s_in[p]];
     uint32_t i = 1, m = (lo & DSA_E_MARK) ? 1u : 0u;
     while (!(lo & DSA_E_DECIDED)) {
-        const uint32_t c = s_in[p + i];                              // p + i <= 511 + 16: inside the halo
-        const uint32_t idx = (lo & 0xFFFFFFu) * T.n_classes + T.classmap_s[c];
-        const uint32_t nx = (ALL_SMEM || (lo & 0xFFFFFFu) < T.smem_states) ? T.ctrans_s[idx] : __ldg(T.ctrans_g + idx);
+        const uint32_t nx = next_entry<TAB>(T, lo & 0xFFFFFFu, s_in[p + i]);   // p + i <= 511 + 16: inside the halo
         if ((nx & 0xFFFFFFu) == DSA_DEAD) break;                     // '\n' (line end, padding) is dead
         lo = nx;
         ++i;
@@ -88,21 +98,23 @@ __device__ __forceinline__ uint32_t walk_from(const MatchTables &T, const uint8_
 }
 
 // Output bytes of the real match at tile position p (length m) -> s_out[p .. p+m)
-template <bool ALL_SMEM>
+template <int TAB>
 __device__ __forceinline__ void emit_match(const MatchArgs &a, const MatchTables &T, const uint8_t *s_in,
                                            uint8_t *s_out, uint32_t p, uint32_t m, uint32_t &status) {
     if (a.P.eout) {
         // PF_OUT_LATE: replay on the compact table; the last transition (or the pending state) names ONE string
         uint32_t lo = T.row0_s[s_in[p]], i = 1;
-        uint32_t edge = T.classmap_s[s_in[p]];
+        uint32_t from = 0, by = s_in[p];                             // the last transition taken: (state, byte)
         while (!(lo & DSA_E_DECIDED)) {
-            const uint32_t idx = (lo & 0xFFFFFFu) * T.n_classes + T.classmap_s[s_in[p + i]];
-            const uint32_t nx = (ALL_SMEM || (lo & 0xFFFFFFu) < T.smem_states) ? T.ctrans_s[idx] : __ldg(T.ctrans_g + idx);
+            const uint32_t c = s_in[p + i];
+            const uint32_t nx = next_entry<TAB>(T, lo & 0xFFFFFFu, c);
             if ((nx & 0xFFFFFFu) == DSA_DEAD) break;
-            lo = nx; edge = idx; ++i;
+            from = lo & 0xFFFFFFu; by = c;
+            lo = nx; ++i;
             if (i >= 16) break;
         }
-        const uint32_t slot = (lo & DSA_E_DECIDED) ? edge : a.P.n_states * T.n_classes + (lo & 0xFFFFFFu);
+        const uint32_t slot = (lo & DSA_E_DECIDED) ? from * T.n_classes + T.classmap_s[by]
+                                                   : a.P.n_states * T.n_classes + (lo & 0xFFFFFFu);
         const uint8_t *src = T.pool + __ldg(a.P.eout + slot);
         for (uint32_t k = 0; k < m; ++k) s_out[p + k] = src[k];
         return;
@@ -125,9 +137,9 @@ __device__ __forceinline__ void emit_match(const MatchArgs &a, const MatchTables
     if (o.n - p != m) status |= ST_IRREGULAR;                        // cannot happen for a length-preserving program
 }
 
-template <bool STORE, bool ALL_SMEM>
+template <bool STORE, int TAB>
 __device__ __forceinline__ void match_tile(const MatchArgs &a, const MatchTables &T, uint8_t *s_in,
-                                           uint8_t *s_out, uint16_t *s_list, size_t base, uint4 x, uint4 halo_in,
+                                           uint8_t *s_out, uint16_t *s_list, uint32_t *s_count, size_t base, uint4 x, uint4 halo_in,
                                            uint32_t lane, uint32_t first_valid, uint32_t &carry_e, uint4 &carry_halo,
                                            uint32_t &nul_acc, uint32_t &status) {
     // ---- A: stage the tile (input and default output = raw copy) -----------------------------------
@@ -136,6 +148,7 @@ __device__ __forceinline__ void match_tile(const MatchArgs &a, const MatchTables
     if (lane == 0) {
         *reinterpret_cast<uint4 *>(s_in + kTile) = halo_in;
         *reinterpret_cast<uint4 *>(s_out + kTile) = halo_in;
+        *s_count = 0;
     }
     nul_acc |= ((x.x - 0x01010101u) & ~x.x) | ((x.y - 0x01010101u) & ~x.y) | ((x.z - 0x01010101u) & ~x.z) | ((x.w - 0x01010101u) & ~x.w);
 
@@ -170,7 +183,7 @@ __device__ __forceinline__ void match_tile(const MatchArgs &a, const MatchTables
     while (cand) {
         const uint32_t j = __ffs(cand) - 1;
         cand &= cand - 1;
-        const uint32_t m = walk_from<ALL_SMEM>(T, s_in, lane * 16 + j);
+        const uint32_t m = walk_from<TAB>(T, s_in, lane * 16 + j);
         if (m) { C |= 1u << j; lens |= (unsigned long long)(m - 1) << (4 * j); }
     }
 
@@ -206,23 +219,18 @@ __device__ __forceinline__ void match_tile(const MatchArgs &a, const MatchTables
         for (uint32_t k = 0; k < carry_e; ++k) s_out[k] = (uint8_t)(h[k >> 2] >> ((k & 3) * 8));
     }
     {
-        uint32_t cnt = __popc(real), incl = cnt;
-#pragma unroll
-        for (int d = 1; d < 32; d <<= 1) {
-            uint32_t y = __shfl_up_sync(0xFFFFFFFFu, incl, d);
-            if (lane >= (uint32_t)d) incl += y;
-        }
-        const uint32_t total = __shfl_sync(0xFFFFFFFFu, incl, 31);
-        uint32_t slot = incl - cnt;
+        // order within the list does not matter: one shared-memory atomic hands out the slots
+        uint32_t slot = real ? atomicAdd(s_count, (uint32_t)__popc(real)) : 0u;
         while (real) {
             const uint32_t j = __ffs(real) - 1;
             real &= real - 1;
             s_list[slot++] = (uint16_t)((lane * 16 + j) | (((uint32_t)(lens >> (4 * j)) & 15u) << 12));
         }
         __syncwarp();
+        const uint32_t total = *s_count;
         for (uint32_t q = lane; q < total; q += 32) {
             const uint32_t ent = s_list[q];
-            emit_match<ALL_SMEM>(a, T, s_in, s_out, ent & 0xFFFu, (ent >> 12) + 1, status);
+            emit_match<TAB>(a, T, s_in, s_out, ent & 0xFFFu, (ent >> 12) + 1, status);
         }
     }
     __syncwarp();
@@ -241,7 +249,7 @@ __device__ __forceinline__ void match_tile(const MatchArgs &a, const MatchTables
     __syncwarp();
 }
 
-template <bool ALL_SMEM>
+template <int TAB>
 __global__ void __launch_bounds__(kMatchThreads)
 k_match(MatchArgs a) {
     extern __shared__ __align__(16) uint8_t smem[];
@@ -255,7 +263,7 @@ k_match(MatchArgs a) {
     uint8_t *pool_s = nullptr;
     if (a.pool_in_smem) { pool_s = cur; cur += (a.P.pool_bytes + 15) & ~15u; }
     uint32_t *ctrans_s = reinterpret_cast<uint32_t *>(cur);
-    const uint32_t ct_words = a.smem_states * a.P.n_classes;
+    const uint32_t ct_words = TAB == TAB_WIDE ? a.P.n_states * 256u : a.smem_states * a.P.n_classes;
     cur += ((ct_words + 3) & ~3u) * 4;
     uint8_t *warp_base = cur + warp * kWarpSmem;
 
@@ -265,7 +273,12 @@ k_match(MatchArgs a) {
     for (uint32_t k = threadIdx.x; k < 256; k += blockDim.x) { row0_s[k] = __ldg(a.P.row0 + k); classmap_s[k] = __ldg(a.P.classmap + k); }
     if (pool_s)
         for (uint32_t k = threadIdx.x; k < a.P.pool_bytes; k += blockDim.x) pool_s[k] = __ldg(a.P.pool + k);
-    for (uint32_t k = threadIdx.x; k < ct_words; k += blockDim.x) ctrans_s[k] = __ldg(a.P.ctrans + k);
+    if (TAB == TAB_WIDE) {
+        for (uint32_t k = threadIdx.x; k < ct_words; k += blockDim.x)
+            ctrans_s[k] = __ldg(a.P.ctrans + (k >> 8) * a.P.n_classes + __ldg(a.P.classmap + (k & 255u)));
+    } else {
+        for (uint32_t k = threadIdx.x; k < ct_words; k += blockDim.x) ctrans_s[k] = __ldg(a.P.ctrans + k);
+    }
     __syncthreads();
 
     MatchTables T;
@@ -275,6 +288,7 @@ k_match(MatchArgs a) {
 
     uint8_t *s_in = warp_base, *s_out = warp_base + 544;
     uint16_t *s_list = reinterpret_cast<uint16_t *>(warp_base + 1088);
+    uint32_t *s_count = reinterpret_cast<uint32_t *>(warp_base + 1088 + 1024);
     const size_t n = a.n;
     const size_t n_tiles = (n + kTile - 1) / kTile;
     const size_t gwarp = (size_t)blockIdx.x * kMatchWarps + warp;
@@ -319,8 +333,8 @@ k_match(MatchArgs a) {
             uint4 halo_in = load_padded(a.in, base + kTile, n);
             uint4 x_next = make_uint4(0x0A0A0A0Au, 0x0A0A0A0Au, 0x0A0A0A0Au, 0x0A0A0A0Au);
             if (t + 1 < t1) x_next = load_padded(a.in, base + kTile + lane * 16, n);   // prefetch
-            if (t < t0) match_tile<false, ALL_SMEM>(a, T, s_in, s_out, s_list, base, x, halo_in, lane, first_valid, carry_e, carry_halo, nul_acc, status);
-            else        match_tile<true, ALL_SMEM>(a, T, s_in, s_out, s_list, base, x, halo_in, lane, first_valid, carry_e, carry_halo, nul_acc, status);
+            if (t < t0) match_tile<false, TAB>(a, T, s_in, s_out, s_list, s_count, base, x, halo_in, lane, first_valid, carry_e, carry_halo, nul_acc, status);
+            else        match_tile<true, TAB>(a, T, s_in, s_out, s_list, s_count, base, x, halo_in, lane, first_valid, carry_e, carry_halo, nul_acc, status);
             first_valid = 0;
             x = x_next;
         }
