@@ -430,7 +430,16 @@ def main():
                 traffic = json.load(f).get("dram_bytes_per_launch")
         except Exception:
             pass
-    kernel = {T.EXEC_BYTEMAP: "k_bytemap", T.EXEC_TABLE: "k_lines<table>", T.EXEC_BACKTRACK: "k_lines<dfs>"}[info["exec_kind"]]
+    if info["exec_kind"] == T.EXEC_BYTEMAP:
+        kernel = "k_bytemap"
+    elif info["exec_kind"] == T.EXEC_BACKTRACK:
+        kernel = "k_lines<dfs> (count, scan, write)"
+    elif info["length_preserving"] and info["max_depth"] <= 16 and not info["can_match_empty"]:
+        kernel = "k_match"
+    elif info["length_preserving"]:
+        kernel = "k_lines<inplace>"
+    else:
+        kernel = "k_lines_s<count> + k_scan_groups + k_lines_s<write>"
     line = {
         "metric": METRIC, "value": value, "unit": "GB/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,

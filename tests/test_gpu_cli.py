@@ -1,0 +1,51 @@
+"""-m gpu: the drop-in command lines (bin/trre, bin/trre_dft) against the real reference binaries
+(oracle/_ref, shipped prebuilt to the GPU box) or, when those are absent, the oracle: same argv, same
+stdin, byte-identical stdout, same exit code."""
+import os
+import subprocess
+
+import pytest
+
+import trre_b200 as T
+from oracle_util import NFT, DFT, have_ref, oracle_run, REF_NFT, REF_DFT
+
+pytestmark = pytest.mark.gpu
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+BIN = {NFT: os.path.join(ROOT, "bin", "trre"), DFT: os.path.join(ROOT, "bin", "trre_dft")}
+REF = {NFT: REF_NFT, DFT: REF_DFT}
+
+TEXT = bytes(T.synth_text(0x72726501, 200000, ["cat", "dog", "concatenate", "dogma"], 0.25))
+CASES = [("cat:dog", TEXT), ("[a:A-z:Z]", TEXT), ("(cat:dog|dog:cat)", TEXT), ("[a:b-y:zz:a]", TEXT),
+         ("a:", TEXT), (":=", b"or\n"), ("a+:x", b"aaab\ncaaat\n"), ("cat:dog", b"cat"), ("b:X", b"ab\0cb\nb\n"),
+         ("xo:", b"xor\n"), ("(cat)*:dog", b"catcatcat\n"), ("cat:dog", b""), ("[a:A-z:Z]", TEXT[:-1])]
+
+
+def expected(expr, data, flavor):
+    if have_ref():
+        r = subprocess.run([REF[flavor], expr], input=data, capture_output=True)
+        return r.returncode, r.stdout
+    rc, out, _ = oracle_run(expr.encode(), data, flavor=flavor)
+    return rc, out
+
+
+@pytest.mark.parametrize("flavor", [NFT, DFT])
+def test_cli_stdin_matches_reference(flavor):
+    for expr, data in CASES:
+        rc, want = expected(expr, data, flavor)
+        r = subprocess.run([BIN[flavor], expr], input=data, capture_output=True)
+        assert r.returncode == rc and r.stdout == want, (expr, flavor, r.stderr[:200])
+
+
+def test_cli_file_argument(tmp_path):
+    f = tmp_path / "in.txt"
+    f.write_bytes(TEXT)
+    rc, want = expected("cat:dog", TEXT, NFT)
+    r = subprocess.run([BIN[NFT], "cat:dog", str(f)], capture_output=True)
+    assert r.returncode == rc and r.stdout == want
+
+
+def test_cli_match_flags_stay_on_the_host():
+    r = subprocess.run([BIN[NFT], "-ma", "(.:x)*.*"], input=b"aaa\n", capture_output=True)
+    assert r.stdout == b"xxx\nxxa\nxaa\naaa\n"
+    r = subprocess.run([BIN[NFT], "-a", "a:x|a:y"], input=b"ab\n", capture_output=True)
+    assert r.stdout == b"xyab\n"                                  # -a in scan mode

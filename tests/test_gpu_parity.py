@@ -151,3 +151,29 @@ def test_dictionary_on_gpu():
         prog = T.compile(expr, flavor)
         rc, want, _ = oracle_run(expr.encode(), text, flavor=flavor)
         assert rc == 0 and prog.scan(text) == want, flavor
+
+
+# ---- the general path: shared-memory staged kernels against the plain ones and the oracle -----------
+
+@pytest.mark.parametrize("expr,flavor", [("a:", NFT), (":=", NFT), ("a:xy", DFT), ("a+:x", NFT), ("(cat)*:dog", NFT),
+                                         ("[a-c]+:<&>", NFT), ("b:", DFT), ("(.:x)*?.*", NFT), ("ab:X|abc:Y|a:Z", DFT)])
+def test_general_path_large_inputs(expr, flavor, monkeypatch):
+    for seed, alphabet, hi in ((11, b"abc ", 300), (12, b"ab", 40), (13, b"abcat dog", 5000)):
+        data = _ab_text(seed, 3 << 20, alphabet, 0, hi)
+        rc, want, _ = oracle_run(expr.encode(), data, flavor=flavor)
+        assert rc == 0
+        prog = T.compile(expr, flavor)
+        got = prog.scan(data)
+        assert got == want, (expr, flavor, seed)
+        monkeypatch.setenv("TRRE_NO_STAGED_LINES", "1")
+        plain = prog.scan(data)
+        monkeypatch.delenv("TRRE_NO_STAGED_LINES")
+        assert plain == want, (expr, flavor, seed, "plain kernels")
+
+
+def test_general_path_expansion_beyond_staging():
+    # every byte becomes 8: the group's output (256 KB) does not fit the 40 KB staging window
+    data = _ab_text(21, 1 << 20, b"ab", 1, 100)
+    for expr, flavor in (("a:AAAAAAAA|b:BBBBBBBB", NFT), (":0123456789", NFT)):
+        rc, want, _ = oracle_run(expr.encode(), data, flavor=flavor)
+        assert rc == 0 and T.compile(expr, flavor).scan(data) == want

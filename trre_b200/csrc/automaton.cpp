@@ -579,10 +579,10 @@ std::vector<uint8_t> assemble(const Program &P, const Nft &g) {
     // compact tables of the position-parallel kernel (k_match): length-preserving, acyclic, short attempts
     const bool matchable = P.exec_kind == TRRE_EXEC_TABLE && (P.flags & PF_LENGTH_PRESERVING) && (P.flags & PF_ACYCLIC) &&
                            !(P.flags & (PF_CAN_MATCH_EMPTY | PF_HAS_DIVERGE)) && P.max_depth >= 1 && P.max_depth <= 16;
-    if (matchable) {
+    if (!P.trans.empty()) {                                   // compact tables: every table program
         h.off_row0 = (uint32_t)off; off += 256 * 4;
         h.off_ctrans = (uint32_t)off; off += P.trans.size() * 4; off = align16(off);
-        if (!P.eout.empty()) { h.off_eout = (uint32_t)off; off += P.eout.size() * 4; off = align16(off); }
+        if (matchable && !P.eout.empty()) { h.off_eout = (uint32_t)off; off += P.eout.size() * 4; off = align16(off); }
     }
     if (off >= (1ull << 31)) throw PatternError{TRRE_E_UNSUPPORTED, "error: compiled tables exceed 2 GiB\n"};
     h.magic = 0x32425254u;  // "TRB2"
@@ -590,7 +590,7 @@ std::vector<uint8_t> assemble(const Program &P, const Nft &g) {
     h.total_bytes = (uint32_t)off;
     h.flavor = (uint32_t)P.flavor;
     h.exec_kind = P.exec_kind;
-    h.flags = P.flags;
+    h.flags = P.flags | (matchable ? (uint32_t)PF_MATCHABLE : 0u);
     h.nft_states = (uint32_t)g.st.size();
     h.nft_start = g.start;
     h.dsa_states = (uint32_t)P.sinfo.size();

@@ -48,6 +48,7 @@ enum : uint32_t {
     PF_ACYCLIC           = 4u,
     PF_NUL_IN_OUTPUT     = 8u,       // some PROD byte is 0: NFT flavour truncates at it (fputs)
     PF_HAS_DIVERGE       = 16u,
+    PF_MATCHABLE         = 64u,      // k_match applies: length preserving, acyclic, attempts <= 16 bytes, no empty match
     PF_OUT_LATE          = 32u       // every transition into a non-DECIDED state emits nothing: a match's output
                                      // is out(last transition) + fin(last state)
 };

@@ -15,6 +15,7 @@
 #include "automaton.hpp"
 #include "kernels.cuh"
 #include "match_kernel.cuh"
+#include "lines_staged.cuh"
 #include "pattern.hpp"
 
 using namespace trre;
@@ -61,6 +62,7 @@ struct DeviceState {
     // k_match launch plan
     uint32_t match_repl = 0, match_states = 0, match_pool = 0;
     int match_tab = 0;
+    bool staged_attr = false;
     size_t match_smem = 0;
     int match_blocks = 0;
 };
@@ -136,7 +138,7 @@ int get_state(const trre_prog *cp, int device, DeviceState **out) {
     d->P.flags = h.flags;
     d->P.nft_start = h.nft_start;
     CUDA_TRY(cudaFuncSetAttribute(k_bytemap, cudaFuncAttributeMaxDynamicSharedMemorySize, kPairLutBytes));
-    if (h.off_row0) {
+    if (h.flags & PF_MATCHABLE) {
         // shared-memory plan of k_match: replicate row0 per bank when everything fits, else cache the
         // first (shallowest: states are numbered breadth first) rows of the compact table
         const size_t warp_bytes = (size_t)kMatchWarps * kWarpSmem;
@@ -230,7 +232,7 @@ int launch_fast(const trre_prog *p, DeviceState *d, const uint8_t *d_in, size_t 
     const bool aligned = ((reinterpret_cast<uintptr_t>(d_in) ^ reinterpret_cast<uintptr_t>(d_out)) & 15) == 0;
     if (h.exec_kind == TRRE_EXEC_BYTEMAP && aligned && d->P.pairlut) {
         k_bytemap<<<d->sm_count, kBmThreads, kPairLutBytes, st>>>(d_in, d_out, n, d->P.pairlut, d->P.lut, status);
-    } else if (d->P.row0 && aligned && (reinterpret_cast<uintptr_t>(d_in) & 15) == 0 && !std::getenv("TRRE_NO_MATCH_KERNEL")) {
+    } else if ((d->P.flags & PF_MATCHABLE) && d->P.row0 && aligned && (reinterpret_cast<uintptr_t>(d_in) & 15) == 0 && !std::getenv("TRRE_NO_MATCH_KERNEL")) {
         MatchArgs m{};
         m.P = d->P; m.in = d_in; m.out = d_out; m.n = n; m.status = status;
         m.smem_states = d->match_states; m.row0_replicated = d->match_repl; m.pool_in_smem = d->match_pool;
@@ -252,8 +254,10 @@ int launch_fast(const trre_prog *p, DeviceState *d, const uint8_t *d_in, size_t 
 }
 
 // The general path: count -> scan -> (write).  3 kernels (2 when only sizing).
+enum { PH_SIZE = 0, PH_ALL = 1, PH_WRITE = 2 };    // count+scan | count+scan+write | write (counts already there)
+
 int launch_general(const trre_prog *p, DeviceState *d, const uint8_t *d_in, size_t n, uint8_t *d_out,
-                   size_t out_cap, cudaStream_t st, bool size_only, int *launches) {
+                   size_t out_cap, cudaStream_t st, int phase, int *launches) {
     const bool backtrack = p->hdr.exec_kind == TRRE_EXEC_BACKTRACK;
     const size_t n_chunks = (n + kChunk - 1) / kChunk;
     const size_t n_groups = (n_chunks + kLineThreads - 1) / kLineThreads;
@@ -263,11 +267,37 @@ int launch_general(const trre_prog *p, DeviceState *d, const uint8_t *d_in, size
     int rc = ensure_workspace(d, n_chunks, n_groups, backtrack, (size_t)grid * kLineThreads);
     if (rc != TRRE_OK) return rc;
     LineArgs a = make_args(d, d_in, n, d_out, out_cap, d->d_status);
-    launch_lines<MODE_COUNT>(backtrack, grid, st, a);
-    k_scan_groups<<<1, kScanThreads, 0, st>>>(d->d_gsum, n_groups, d->d_total, d->d_status, 0);
-    *launches += 2;
-    if (!size_only) {
-        launch_lines<MODE_WRITE>(backtrack, grid, st, a);
+    const bool staged = !backtrack && d->P.ctrans && !std::getenv("TRRE_NO_STAGED_LINES");
+    StagedArgs sa{};
+    size_t smem_count = 0, smem_write = 0;
+    int grid_s = grid;
+    if (staged) {
+        // shared memory: classmap + cached rows of the compact table + the group's input (+ its output)
+        const size_t row_bytes = (size_t)d->P.n_classes * 4;
+        size_t rows = std::min<size_t>(d->P.n_states, (24 * 1024) / row_bytes);
+        sa.L = a;
+        sa.smem_states = (uint32_t)rows;
+        const size_t ct = ((rows * d->P.n_classes + 3) & ~(size_t)3) * 4;
+        smem_count = 256 + 1024 + ct + kGroupBytes + 16;
+        smem_write = smem_count + kStageOut + 16;
+        if (!d->staged_attr) {
+            CUDA_TRY(cudaFuncSetAttribute(k_lines_s<MODE_COUNT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_count));
+            CUDA_TRY(cudaFuncSetAttribute(k_lines_s<MODE_WRITE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_write));
+            d->staged_attr = true;
+        }
+        grid_s = (int)std::min<size_t>(n_groups, (size_t)d->sm_count * 3);
+        if (grid_s < 1) grid_s = 1;
+        if (phase != PH_WRITE) k_lines_s<MODE_COUNT><<<grid_s, kLineThreads, smem_count, st>>>(sa);
+    } else if (phase != PH_WRITE) {
+        launch_lines<MODE_COUNT>(backtrack, grid, st, a);
+    }
+    if (phase != PH_WRITE) {
+        k_scan_groups<<<1, kScanThreads, 0, st>>>(d->d_gsum, n_groups, d->d_total, d->d_status, 0);
+        *launches += 2;
+    }
+    if (phase != PH_SIZE) {
+        if (staged) k_lines_s<MODE_WRITE><<<std::min(grid_s, d->sm_count * 2), kLineThreads, smem_write, st>>>(sa);
+        else launch_lines<MODE_WRITE>(backtrack, grid, st, a);
         *launches += 1;
     }
     CUDA_TRY(cudaGetLastError());
@@ -298,7 +328,7 @@ int enqueue_scan(const trre_prog *p, DeviceState *d, const uint8_t *d_in, size_t
         return TRRE_OK;
     }
     d->status_dirty = true;                 // k_scan_groups writes d_total
-    return launch_general(p, d, d_in, n, d_out, out_cap, st, size_only, &d->launches);
+    return launch_general(p, d, d_in, n, d_out, out_cap, st, size_only ? PH_SIZE : PH_ALL, &d->launches);
 }
 
 int status_to_rc(uint32_t s) {
@@ -321,7 +351,7 @@ int collect(const trre_prog *p, DeviceState *d, cudaStream_t st, size_t *out_n) 
         if (rc != TRRE_OK) return rc;
         d->pend_fast = false;
         d->status_dirty = true;
-        rc = launch_general(p, d, d->pend_in, d->pend_n, d->pend_out, d->pend_cap, st, false, &d->launches);
+        rc = launch_general(p, d, d->pend_in, d->pend_n, d->pend_out, d->pend_cap, st, PH_ALL, &d->launches);
         if (rc != TRRE_OK) return rc;
         CUDA_TRY(cudaMemcpyAsync(d->h_status, d->d_status, sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
         CUDA_TRY(cudaMemcpyAsync(d->h_total, d->d_total, sizeof(unsigned long long), cudaMemcpyDeviceToHost, st));
@@ -562,17 +592,15 @@ int trre_scan_into(const trre_prog *p, int device, const uint8_t *in, size_t n, 
     if (rc != TRRE_OK) return rc;
     // the counts are still in the workspace: only the write pass is left
     {
-        const bool backtrack = p->hdr.exec_kind == TRRE_EXEC_BACKTRACK;
-        LineArgs a = make_args(d, d->buf_in, n, d->buf_out, total, d->d_status);
-        int grid = (int)std::min<size_t>(a.n_groups, backtrack ? (size_t)d->sm_count : (size_t)d->sm_count * 64);
         if (d->status_dirty) { CUDA_TRY(cudaMemsetAsync(d->d_status, 0, sizeof(uint32_t), st)); }
-        launch_lines<MODE_WRITE>(backtrack, grid < 1 ? 1 : grid, st, a);
-        CUDA_TRY(cudaGetLastError());
+        int wl = 0;
+        rc = launch_general(p, d, d->buf_in, n, d->buf_out, total, st, PH_WRITE, &wl);
+        if (rc != TRRE_OK) return rc;
         d->pend_fast = false;
         d->status_dirty = true;
         size_t t2 = 0;
         rc = collect(p, d, st, &t2);
-        d->launches = launches + 1;
+        d->launches = launches + wl;
         if (rc != TRRE_OK) return rc;
     }
     CUDA_TRY(cudaMemcpyAsync(out, d->buf_out, total, cudaMemcpyDeviceToHost, st));
