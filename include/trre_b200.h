@@ -103,8 +103,11 @@ int  trre_scan_into(const trre_prog *p, int device,
 
 /* Device-resident scan: d_in/d_out are device pointers on `device`; work is enqueued on `stream`
  * (a cudaStream_t).  If out_n != NULL the call synchronises the stream and returns the output size
- * and status; if out_n == NULL it only enqueues (status can be collected later with
- * trre_scan_status).  Tables are uploaded to the device on first use and stay resident. */
+ * and status; if out_n == NULL it only enqueues: the result is complete, and its size/status known,
+ * once trre_scan_status returns, so d_in/d_out must stay valid until then (a fast kernel that meets an
+ * irregular buffer - NUL byte, no final newline - is rerun on the general path from there).
+ * Tables are uploaded to the device on first use and stay resident.  One call at a time per
+ * (program, device): the per-device workspace is not shared between host threads. */
 int  trre_scan_device(const trre_prog *p, int device,
                       const uint8_t *d_in, size_t n, uint8_t *d_out, size_t out_cap,
                       size_t *out_n, void *stream);

@@ -177,3 +177,49 @@ def test_general_path_expansion_beyond_staging():
     for expr, flavor in (("a:AAAAAAAA|b:BBBBBBBB", NFT), (":0123456789", NFT)):
         rc, want, _ = oracle_run(expr.encode(), data, flavor=flavor)
         assert rc == 0 and T.compile(expr, flavor).scan(data) == want
+
+
+# ---- BASELINE sizes: size-independent properties (lines are independent => tiles replicate) ------------
+
+def test_full_size_cfg2_one_gib_device_resident():
+    torch = pytest.importorskip("torch")
+    tile = T.synth_text(0x72726502, 256 << 20)
+    prog = T.compile("[a:A-z:Z]", DFT)
+    d_tile = torch.frombuffer(tile, dtype=torch.uint8).cuda()
+    d_in = d_tile.repeat(4)                                       # 1 GiB
+    d_out = torch.empty_like(d_in)
+    n = prog.scan_device(d_in.data_ptr(), d_in.numel(), d_out.data_ptr(), d_out.numel(),
+                         stream=torch.cuda.current_stream().cuda_stream)
+    assert n == d_in.numel() and prog.launches() == 1
+    lut = torch.frombuffer(bytearray(prog.bytemap()), dtype=torch.uint8).cuda()
+    for k in range(4):
+        sl = slice(k * len(tile), (k + 1) * len(tile))
+        assert torch.equal(d_out[sl], lut[d_in[sl].long()])
+    # the first 8 MiB against the oracle itself
+    head = bytes(tile[:8 << 20])
+    cut = head.rfind(b"\n") + 1
+    rc, want, _ = oracle_run(b"[a:A-z:Z]", head[:cut], flavor=DFT)
+    assert rc == 0 and bytes(d_out[:cut].cpu().numpy().tobytes()) == want
+
+
+def test_full_size_cfg3_replicated_tiles():
+    torch = pytest.importorskip("torch")
+    words = ["cat", "dog", "catdog", "dogcat", "ca", "do", "cot", "dig"]
+    tile = T.synth_text(0x72726503, 128 << 20, words, 0.25)
+    prog = T.compile("(cat:dog|dog:cat)", NFT)
+    d_tile = torch.frombuffer(tile, dtype=torch.uint8).cuda()
+    d_in = d_tile.repeat(8)                                       # 1 GiB
+    d_out = torch.empty_like(d_in)
+    n = prog.scan_device(d_in.data_ptr(), d_in.numel(), d_out.data_ptr(), d_out.numel(),
+                         stream=torch.cuda.current_stream().cuda_stream)
+    assert n == d_in.numel()
+    for k in range(1, 8):
+        assert torch.equal(d_out[:len(tile)], d_out[k * len(tile):(k + 1) * len(tile)])
+    head = bytes(tile[:8 << 20])
+    cut = head.rfind(b"\n") + 1
+    rc, want, _ = oracle_run(b"(cat:dog|dog:cat)", head[:cut], flavor=NFT)
+    assert rc == 0 and bytes(d_out[:cut].cpu().numpy().tobytes()) == want
+    # length preserving + involution: cat<->dog applied twice is the identity on this corpus
+    d_back = torch.empty_like(d_in)
+    prog.scan_device(d_out.data_ptr(), n, d_back.data_ptr(), n, stream=torch.cuda.current_stream().cuda_stream)
+    assert torch.equal(d_back, d_in)

@@ -214,7 +214,6 @@ LineArgs make_args(DeviceState *d, const uint8_t *d_in, size_t n, uint8_t *d_out
     a.cnt = d->d_cnt; a.gsum = d->d_gsum; a.total = d->d_total; a.status = status;
     a.n_chunks = (n + kChunk - 1) / kChunk;
     a.n_groups = (a.n_chunks + kLineThreads - 1) / kLineThreads;
-    a.gate = 0;
     a.bt_s = d->bt_s; a.bt_i = d->bt_i; a.bt_o = d->bt_o; a.bt_obuf = d->bt_obuf;
     a.bt_cap = d->bt_cap; a.bt_ocap = d->bt_ocap;
     return a;
@@ -292,7 +291,7 @@ int launch_general(const trre_prog *p, DeviceState *d, const uint8_t *d_in, size
         launch_lines<MODE_COUNT>(backtrack, grid, st, a);
     }
     if (phase != PH_WRITE) {
-        k_scan_groups<<<1, kScanThreads, 0, st>>>(d->d_gsum, n_groups, d->d_total, d->d_status, 0);
+        k_scan_groups<<<1, kScanThreads, 0, st>>>(d->d_gsum, n_groups, d->d_total);
         *launches += 2;
     }
     if (phase != PH_SIZE) {

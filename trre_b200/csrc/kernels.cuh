@@ -178,7 +178,6 @@ struct LineArgs {
     uint32_t *status;
     size_t n_chunks;
     size_t n_groups;
-    uint32_t gate;               // != 0: run only if (*status & gate)
     // DFS executor scratch, indexed by resident thread
     int32_t *bt_s; uint32_t *bt_i; uint32_t *bt_o; uint8_t *bt_obuf;
     uint32_t bt_cap, bt_ocap;
@@ -210,7 +209,6 @@ __device__ __forceinline__ size_t run_record(const DevProg &P, const BtScratch &
 template <int MODE, bool BACKTRACK>
 __global__ void __launch_bounds__(kLineThreads)
 k_lines(LineArgs a) {
-    if (a.gate && !(*a.status & a.gate)) return;
     __shared__ unsigned long long warp_sums[kLineThreads / 32];
     __shared__ unsigned long long group_base;
     const uint8_t *__restrict__ in = a.in;
@@ -297,9 +295,7 @@ k_lines(LineArgs a) {
 constexpr int kScanThreads = 1024;
 
 __global__ void __launch_bounds__(kScanThreads)
-k_scan_groups(unsigned long long *gsum, size_t n_groups, unsigned long long *total,
-              const uint32_t *status, uint32_t gate) {
-    if (gate && !(*status & gate)) return;
+k_scan_groups(unsigned long long *gsum, size_t n_groups, unsigned long long *total) {
     __shared__ unsigned long long part[kScanThreads];
     const size_t per = (n_groups + kScanThreads - 1) / kScanThreads;
     const size_t b = (size_t)threadIdx.x * per;
