@@ -223,3 +223,41 @@ def test_full_size_cfg3_replicated_tiles():
     d_back = torch.empty_like(d_in)
     prog.scan_device(d_out.data_ptr(), n, d_back.data_ptr(), n, stream=torch.cuda.current_stream().cuda_stream)
     assert torch.equal(d_back, d_in)
+
+
+# ---- variable-length byte maps (k_bmv_count / k_bmv_write) ---------------------------------------------
+
+BMV_PATTERNS = [("a:", NFT), ("a:", DFT), ("a:xy", NFT), ("a:xy", DFT), ("[a-c]:", NFT), ("a:|b:XYZ|c:C", NFT),
+                ("a:" + "Q" * 200, NFT), (" :__", DFT), ("[a:A-c:C]|d:", NFT)]
+
+
+@pytest.mark.parametrize("expr,flavor", BMV_PATTERNS)
+def test_bytemap_var_against_oracle_and_general_path(expr, flavor, monkeypatch):
+    for seed, alphabet, hi, size in ((31, b"abcd ", 120, 2 << 20), (32, b"ab", 3000, 1 << 20), (33, b"a", 50, 1 << 18)):
+        data = _ab_text(seed, size, alphabet, 0, hi)
+        rc, want, _ = oracle_run(expr.encode(), data, flavor=flavor)
+        assert rc == 0
+        prog = T.compile(expr, flavor)
+        assert prog.scan(data) == want, (expr, flavor, seed, "k_bmv")
+        monkeypatch.setenv("TRRE_NO_BMV", "1")
+        assert prog.scan(data) == want, (expr, flavor, seed, "general")
+        monkeypatch.delenv("TRRE_NO_BMV")
+    for data in (b"", b"a", b"a\n", b"aaa", b"b\0a\na\n", b"\n\n", b"ab" * 7 + b"\n"):
+        check(expr, flavor, data)
+
+
+def test_bytemap_var_device_api_unaligned_output_and_capacity():
+    torch = pytest.importorskip("torch")
+    data = _ab_text(41, 5 << 20, b"abc ", 1, 90)
+    prog = T.compile("a:", NFT)
+    rc, want, _ = oracle_run(b"a:", data, flavor=NFT)
+    d_in = torch.frombuffer(bytearray(data), dtype=torch.uint8).cuda()
+    buf = torch.zeros(len(data) + 64, dtype=torch.uint8, device="cuda")
+    for shift in (0, 1, 7, 15):
+        d_out = buf[shift:]
+        n = prog.scan_device(d_in.data_ptr(), d_in.numel(), d_out.data_ptr(), d_out.numel(),
+                             stream=torch.cuda.current_stream().cuda_stream)
+        assert n == len(want) and bytes(d_out[:n].cpu().numpy().tobytes()) == want, shift
+    with pytest.raises(T.TrreError) as ei:
+        prog.scan_device(d_in.data_ptr(), d_in.numel(), buf.data_ptr(), 1000, stream=torch.cuda.current_stream().cuda_stream)
+    assert ei.value.code == 4 and ei.value.needed == len(want)

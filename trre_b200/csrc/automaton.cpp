@@ -364,6 +364,8 @@ struct Program {
     std::vector<uint64_t> sinfo;
     std::vector<uint8_t> pool;
     std::vector<uint32_t> eout;      // see BlobHeader::off_eout
+    bool vmap = false;               // PF_BYTEMAP_VAR
+    std::string vstr[256];           // what an attempt starting with this byte prints (raw copy: the byte itself)
 };
 
 class PoolWriter {
@@ -560,6 +562,24 @@ void analyse_and_pack(const std::vector<RawState> &st, const StringPool &sp, int
         }
         if (bm && (P.flags & PF_LENGTH_PRESERVING)) P.exec_kind = TRRE_EXEC_BYTEMAP;
     }
+    // variable-length byte map: every attempt is still decided by its first byte, but prints 0..255 bytes
+    // (deletions `a:`, expansions `a:xy`, tr-like maps mixed with them)
+    if (P.exec_kind != TRRE_EXEC_BYTEMAP) {
+        bool vm = !(st[0].flags & (DSA_S_HAS_FINAL | DSA_S_DIVERGE));
+        for (int c = 0; c < 256; ++c) P.vstr[c].assign(1, (char)c);
+        size_t pool = 0;
+        for (const RawEdge &e : st[0].edges) {
+            if (!vm) break;
+            const RawState &t = st[e.next];
+            bool ok = (t.flags & DSA_S_DECIDED) && (t.flags & DSA_S_HAS_FINAL) && !(t.flags & DSA_S_DIVERGE) &&
+                      (flavor == TRRE_FLAVOR_DFT || e.mark);
+            if (!ok) { vm = false; break; }
+            P.vstr[e.byte] = sp.get(e.out_id) + sp.get(t.fin_id);
+            if (P.vstr[e.byte].size() > 255) { vm = false; break; }
+            if (P.vstr[e.byte].size() > 1) pool += P.vstr[e.byte].size();
+        }
+        if (vm && pool < 60000 && !st[0].edges.empty()) P.vmap = true;
+    }
 }
 
 std::vector<uint8_t> assemble(const Program &P, const Nft &g) {
@@ -579,6 +599,21 @@ std::vector<uint8_t> assemble(const Program &P, const Nft &g) {
     // compact tables of the position-parallel kernel (k_match): length-preserving, acyclic, short attempts
     const bool matchable = P.exec_kind == TRRE_EXEC_TABLE && (P.flags & PF_LENGTH_PRESERVING) && (P.flags & PF_ACYCLIC) &&
                            !(P.flags & (PF_CAN_MATCH_EMPTY | PF_HAS_DIVERGE)) && P.max_depth >= 1 && P.max_depth <= 16;
+    std::vector<uint8_t> vpool;
+    std::vector<uint32_t> vent(256, 0);
+    if (P.vmap) {
+        for (int c = 0; c < 256; ++c) {
+            const std::string &str = P.vstr[c];
+            uint32_t ent = (uint32_t)str.size() | ((str.empty() ? 0u : (uint32_t)(uint8_t)str[0]) << 8);
+            if (str.size() > 1) { ent |= (uint32_t)vpool.size() << 16; vpool.insert(vpool.end(), str.begin(), str.end()); }
+            vent[c] = ent;
+        }
+        while (vpool.size() & 15) vpool.push_back(0);
+        h.off_vent = (uint32_t)off; off += 1024;
+        off = (off + 127) & ~(size_t)127;
+        h.off_vpairlen = (uint32_t)off; off += 65536 * 2;
+        h.off_vpool = (uint32_t)off; h.vpool_bytes = (uint32_t)vpool.size(); off += vpool.size(); off = align16(off);
+    }
     if (!P.trans.empty()) {                                   // compact tables: every table program
         h.off_row0 = (uint32_t)off; off += 256 * 4;
         h.off_ctrans = (uint32_t)off; off += P.trans.size() * 4; off = align16(off);
@@ -590,7 +625,7 @@ std::vector<uint8_t> assemble(const Program &P, const Nft &g) {
     h.total_bytes = (uint32_t)off;
     h.flavor = (uint32_t)P.flavor;
     h.exec_kind = P.exec_kind;
-    h.flags = P.flags | (matchable ? (uint32_t)PF_MATCHABLE : 0u);
+    h.flags = P.flags | (matchable ? (uint32_t)PF_MATCHABLE : 0u) | (P.vmap ? (uint32_t)PF_BYTEMAP_VAR : 0u);
     h.nft_states = (uint32_t)g.st.size();
     h.nft_start = g.start;
     h.dsa_states = (uint32_t)P.sinfo.size();
@@ -618,6 +653,13 @@ std::vector<uint8_t> assemble(const Program &P, const Nft &g) {
         for (size_t k = 0; k < P.trans.size(); ++k) ct[k] = (uint32_t)(P.trans[k] & 0xFFFFFFFFu);
     }
     if (h.off_eout) std::memcpy(blob.data() + h.off_eout, P.eout.data(), P.eout.size() * 4);
+    if (h.off_vent) {
+        std::memcpy(blob.data() + h.off_vent, vent.data(), 1024);
+        if (!vpool.empty()) std::memcpy(blob.data() + h.off_vpool, vpool.data(), vpool.size());
+        uint16_t *pl = reinterpret_cast<uint16_t *>(blob.data() + h.off_vpairlen);
+        for (uint32_t v = 0; v < 65536; ++v)
+            pl[v ^ (((v >> 8) & 0x1Fu) << 1)] = (uint16_t)((vent[v & 0xFF] & 0xFFu) + (vent[v >> 8] & 0xFFu));
+    }
     if (h.off_pairlut) {
         // pair[c0 | c1 << 8] = LUT[c0] | LUT[c1] << 8 : one shared-memory lookup maps two input bytes
         uint16_t *pair = reinterpret_cast<uint16_t *>(blob.data() + h.off_pairlut);

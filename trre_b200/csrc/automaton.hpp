@@ -48,7 +48,8 @@ enum : uint32_t {
     PF_ACYCLIC           = 4u,
     PF_NUL_IN_OUTPUT     = 8u,       // some PROD byte is 0: NFT flavour truncates at it (fputs)
     PF_HAS_DIVERGE       = 16u,
-    PF_MATCHABLE         = 64u,      // k_match applies: length preserving, acyclic, attempts <= 16 bytes, no empty match
+    PF_MATCHABLE         = 64u,
+    PF_BYTEMAP_VAR       = 128u,     // every attempt is decided by one byte; that byte prints 0..255 bytes (k_bmv_*)      // k_match applies: length preserving, acyclic, attempts <= 16 bytes, no empty match
     PF_OUT_LATE          = 32u       // every transition into a non-DECIDED state emits nothing: a match's output
                                      // is out(last transition) + fin(last state)
 };
@@ -77,6 +78,10 @@ struct BlobHeader {
     uint32_t off_pairlut;      // u16[65536] (TRRE_EXEC_BYTEMAP): LUT applied to two bytes at once, 0 if absent
     uint32_t off_row0;         // u32[256]: low word of trans[start][class(byte)] by raw byte (k_match), 0 if absent
     uint32_t off_ctrans;       // u32[dsa_states * n_classes]: low words of trans (k_match), 0 if absent
+    uint32_t off_vent;         // (PF_BYTEMAP_VAR) u32[256]: len | first byte << 8 | offset into vpool << 16, by raw byte
+    uint32_t off_vpairlen;     // (PF_BYTEMAP_VAR) u16[65536]: len[c0] + len[c1], bank-swizzled like the pair LUT
+    uint32_t off_vpool;        // (PF_BYTEMAP_VAR) strings longer than one byte
+    uint32_t vpool_bytes;
     uint32_t off_eout;         // u32[dsa_states * n_classes]: (PF_OUT_LATE) pool offset of out(edge)+fin(target) for edges
                                // into DECIDED states; u32[dsa_states] fin offsets follow (pending FINAL). 0 if absent
 };

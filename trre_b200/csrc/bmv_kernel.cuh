@@ -1,0 +1,224 @@
+// bmv_kernel.cuh - variable-length byte maps (PF_BYTEMAP_VAR) on regular buffers: deletions (`a:`), expansions
+// (`a:xy`), tr-like maps mixed with them.  Every attempt of the reference's scan loop is decided by its first
+// byte, so the driver (trre_nft.c:778-789) degenerates to "every byte prints its own string" - position
+// parallel, no state between bytes; only the output offsets need a prefix sum:
+//
+//   k_bmv_count  per span (contiguous 512-byte tiles owned by one warp): sum of output lengths, two bytes
+//                per shared-memory lookup (128 KB pair-length table staged by TMA like k_bytemap's)
+//   k_scan_groups  exclusive scan over the spans (kernels.cuh)
+//   k_bmv_write  per tile: 16 conflict-free entry lookups per lane (length | first byte | pool offset),
+//                lane-local prefix + warp scan, bytes placed into the warp's shared-memory window, which
+//                leaves in aligned 16-byte vectors; the < 16 leftover bytes carry into the next tile
+//
+// NUL bytes / a missing final newline raise ST_IRREGULAR (the general path reruns the buffer).
+#pragma once
+#include <cstdint>
+
+#include "kernels.cuh"
+
+namespace trre {
+
+constexpr int kBmvCountThreads = 1024;
+constexpr int kBmvWriteThreads = 512;
+constexpr int kBmvTile = 512;
+constexpr int kBmvWindow = 2048;                     // output bytes a warp assembles per tile without falling back
+constexpr int kBmvWarpSmem = 16 + kBmvWindow + 32;
+
+struct BmvArgs {
+    const uint8_t *in;
+    uint8_t *out;
+    size_t n;
+    size_t out_cap;
+    const uint32_t *vent;            // [256]
+    const uint16_t *vpairlen;        // [65536] swizzled
+    const uint8_t *vpool;
+    uint32_t vpool_bytes;
+    unsigned long long *gsum;        // [n_spans]: lengths, then exclusive offsets
+    const unsigned long long *total;
+    uint32_t *status;
+    size_t n_spans;
+    size_t tiles_per_span;
+};
+
+__device__ __forceinline__ uint32_t pairlen_word(uint32_t w, uint32_t tab) {
+    uint32_t lo, hi;
+    uint32_t a0 = tab + (((w << 1) & 0x1FFFEu) ^ ((w >> 6) & 0x7Cu));
+    uint32_t a1 = tab + (((w >> 15) & 0x1FFFEu) ^ ((w >> 22) & 0x7Cu));
+    asm("ld.shared.u16 %0, [%1];" : "=r"(lo) : "r"(a0));
+    asm("ld.shared.u16 %0, [%1];" : "=r"(hi) : "r"(a1));
+    return lo + hi;
+}
+
+__global__ void __launch_bounds__(kBmvCountThreads, 1)
+k_bmv_count(BmvArgs a) {
+    extern __shared__ __align__(128) uint8_t smem_tab[];   // kPairLutBytes
+    __shared__ __align__(8) uint64_t bar;
+    if (threadIdx.x == 0) {
+        mbar_init(&bar, 1);
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        mbar_expect_tx(&bar, kPairLutBytes);
+#pragma unroll
+        for (int k = 0; k < 8; ++k)
+            tma_bulk_g2s(smem_tab + k * (kPairLutBytes / 8), reinterpret_cast<const uint8_t *>(a.vpairlen) + k * (kPairLutBytes / 8),
+                         kPairLutBytes / 8, &bar);
+    }
+    const uint32_t tab = smem_u32(smem_tab);
+    const uint32_t lane = threadIdx.x & 31;
+    const size_t n = a.n;
+    const size_t n_tiles = (n + kBmvTile - 1) / kBmvTile;
+    const size_t warps_total = (size_t)gridDim.x * (blockDim.x / 32);
+    uint32_t nul = 0;
+    mbar_wait(&bar, 0);
+    for (size_t span = (size_t)blockIdx.x * (blockDim.x / 32) + (threadIdx.x >> 5); span < a.n_spans; span += warps_total) {
+        const size_t t0 = span * a.tiles_per_span;
+        size_t t1 = t0 + a.tiles_per_span;
+        if (t1 > n_tiles) t1 = n_tiles;
+        unsigned long long sum = 0;
+        for (size_t t = t0; t < t1; ++t) {
+            const size_t pos = t * (size_t)kBmvTile + lane * 16;
+            if (pos + 16 <= n) {
+                const uint4 x = ld_stream(reinterpret_cast<const uint4 *>(a.in + pos));
+                sum += pairlen_word(x.x, tab) + pairlen_word(x.y, tab) + pairlen_word(x.z, tab) + pairlen_word(x.w, tab);
+                nul |= ((x.x - 0x01010101u) & ~x.x) | ((x.y - 0x01010101u) & ~x.y) | ((x.z - 0x01010101u) & ~x.z) | ((x.w - 0x01010101u) & ~x.w);
+            } else {
+                for (size_t k = pos; k < n; ++k) {
+                    const uint8_t c = a.in[k];
+                    if (!c) nul = 0x80u;
+                    sum += __ldg(a.vent + c) & 0xFFu;
+                }
+            }
+        }
+#pragma unroll
+        for (int d = 16; d; d >>= 1) sum += __shfl_xor_sync(0xFFFFFFFFu, sum, d);
+        if (lane == 0) a.gsum[span] = sum;
+    }
+    nul &= 0x80808080u;
+    if (blockIdx.x == 0 && threadIdx.x == 0 && n && a.in[n - 1] != '\n') nul = 1;
+    if (__any_sync(0xFFFFFFFFu, nul != 0)) {
+        if (lane == 0) atomicOr(a.status, ST_IRREGULAR);
+    }
+}
+
+__global__ void __launch_bounds__(kBmvWriteThreads)
+k_bmv_write(BmvArgs a) {
+    extern __shared__ __align__(16) uint8_t smem[];
+    const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    uint32_t *vent_s = reinterpret_cast<uint32_t *>(smem);                       // [256][32], bank == lane
+    uint8_t *vpool_s = smem + 256 * 32 * 4;
+    uint8_t *s_out = vpool_s + ((a.vpool_bytes + 15) & ~15u) + warp * kBmvWarpSmem;
+    if (*a.status & ST_IRREGULAR) return;                                          // k_bmv_count saw a NUL / no final newline
+    if (*a.total > a.out_cap) {
+        if (threadIdx.x == 0 && blockIdx.x == 0) atomicOr(a.status, ST_NOSPACE);
+        return;
+    }
+    for (uint32_t k = threadIdx.x; k < 256u * 32u; k += blockDim.x) vent_s[k] = __ldg(a.vent + (k >> 5));
+    for (uint32_t k = threadIdx.x; k < a.vpool_bytes; k += blockDim.x) vpool_s[k] = __ldg(a.vpool + k);
+    __syncthreads();
+    const uint32_t *vent_lane = vent_s + lane;
+    const size_t n = a.n;
+    const size_t n_tiles = (n + kBmvTile - 1) / kBmvTile;
+    const size_t warps_total = (size_t)gridDim.x * (blockDim.x / 32);
+
+    for (size_t span = (size_t)blockIdx.x * (blockDim.x / 32) + warp; span < a.n_spans; span += warps_total) {
+        const size_t t0 = span * a.tiles_per_span;
+        size_t t1 = t0 + a.tiles_per_span;
+        if (t1 > n_tiles) t1 = n_tiles;
+        if (t0 >= t1) continue;
+        const unsigned long long span_off = a.gsum[span];
+        // s_out[0] always corresponds to the 16-byte aligned output address out + gpos; the first `foreign`
+        // bytes of the window belong to the previous span and are never stored
+        uint32_t foreign = (uint32_t)((reinterpret_cast<uintptr_t>(a.out) + span_off) & 15);
+        unsigned long long gpos = span_off - foreign;
+        uint32_t fill = foreign;                                                   // bytes present in the window
+        for (size_t t = t0; t < t1; ++t) {
+            const size_t pos = t * (size_t)kBmvTile + lane * 16;
+            uint4 x = make_uint4(0, 0, 0, 0);
+            uint32_t valid = 0;
+            if (pos + 16 <= n) { x = ld_stream(reinterpret_cast<const uint4 *>(a.in + pos)); valid = 16; }
+            else if (pos < n) {
+                uint32_t w[4] = {0, 0, 0, 0};
+                valid = (uint32_t)(n - pos);
+                for (uint32_t k = 0; k < valid; ++k) w[k >> 2] |= (uint32_t)a.in[pos + k] << ((k & 3) * 8);
+                x = make_uint4(w[0], w[1], w[2], w[3]);
+            }
+            const uint32_t w[4] = {x.x, x.y, x.z, x.w};
+            uint32_t ent[16], mine = 0;
+#pragma unroll
+            for (int j = 0; j < 16; ++j) {
+                const uint32_t c = (w[j >> 2] >> ((j & 3) * 8)) & 0xFFu;
+                ent[j] = (uint32_t)j < valid ? vent_lane[c << 5] : 0u;
+                mine += ent[j] & 0xFFu;
+            }
+            uint32_t incl = mine;
+#pragma unroll
+            for (int d = 1; d < 32; d <<= 1) {
+                const uint32_t y = __shfl_up_sync(0xFFFFFFFFu, incl, d);
+                if (lane >= (uint32_t)d) incl += y;
+            }
+            const uint32_t tile_total = __shfl_sync(0xFFFFFFFFu, incl, 31);
+            uint32_t at = fill + incl - mine;
+            if (fill + tile_total <= (uint32_t)kBmvWindow + 16) {
+#pragma unroll
+                for (int j = 0; j < 16; ++j) {
+                    const uint32_t len = ent[j] & 0xFFu;
+                    if (len == 1) s_out[at] = (uint8_t)(ent[j] >> 8);
+                    else if (len > 1) {
+                        const uint8_t *src = vpool_s + (ent[j] >> 16);
+                        for (uint32_t k = 0; k < len; ++k) s_out[at + k] = src[k];
+                    }
+                    at += len;
+                }
+                fill += tile_total;
+                __syncwarp();
+                // full vectors leave; vector 0 byte-wise while it still contains foreign bytes
+                const uint32_t nvec = fill / 16;
+                for (uint32_t v = lane; v < nvec; v += 32) {
+                    const uint4 y = *reinterpret_cast<const uint4 *>(s_out + v * 16);
+                    if (v == 0 && foreign) {
+                        const uint32_t yy[4] = {y.x, y.y, y.z, y.w};
+                        for (uint32_t k = foreign; k < 16; ++k) a.out[gpos + k] = (uint8_t)(yy[k >> 2] >> ((k & 3) * 8));
+                    } else {
+                        st_stream(reinterpret_cast<uint4 *>(a.out + gpos) + v, y);
+                    }
+                }
+                const uint32_t rest = fill - nvec * 16;
+                uint8_t keep = 0;
+                if (lane < rest) keep = s_out[nvec * 16 + lane];
+                __syncwarp();
+                if (nvec) {
+                    if (lane < rest) s_out[lane] = keep;
+                    gpos += (unsigned long long)nvec * 16;
+                    fill = rest;
+                    foreign = 0;
+                }
+                __syncwarp();
+            } else {
+                // a tile that prints more than the window holds: flush what is pending, then store directly
+                for (uint32_t k = foreign + lane; k < fill; k += 32) a.out[gpos + k] = s_out[k];
+                unsigned long long g = gpos + at;
+#pragma unroll
+                for (int j = 0; j < 16; ++j) {
+                    const uint32_t len = ent[j] & 0xFFu;
+                    if (len == 1) a.out[g] = (uint8_t)(ent[j] >> 8);
+                    else if (len > 1) {
+                        const uint8_t *src = vpool_s + (ent[j] >> 16);
+                        for (uint32_t k = 0; k < len; ++k) a.out[g + k] = src[k];
+                    }
+                    g += len;
+                }
+                const unsigned long long end = gpos + fill + tile_total;
+                foreign = (uint32_t)((reinterpret_cast<uintptr_t>(a.out) + end) & 15);
+                gpos = end - foreign;
+                fill = foreign;
+                __syncwarp();
+            }
+        }
+        for (uint32_t k = foreign + lane; k < fill; k += 32) a.out[gpos + k] = s_out[k];   // the span's last < 16 bytes
+        __syncwarp();
+    }
+}
+
+}  // namespace trre

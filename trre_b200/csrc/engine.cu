@@ -16,6 +16,7 @@
 #include "kernels.cuh"
 #include "match_kernel.cuh"
 #include "lines_staged.cuh"
+#include "bmv_kernel.cuh"
 #include "pattern.hpp"
 
 using namespace trre;
@@ -49,10 +50,15 @@ struct DeviceState {
     int32_t *bt_s = nullptr; uint32_t *bt_i = nullptr; uint32_t *bt_o = nullptr; uint8_t *bt_obuf = nullptr;
     size_t bt_threads = 0; uint32_t bt_cap = 0, bt_ocap = 0;
     int sm_count = 148;
+    const uint32_t *vent = nullptr; const uint16_t *vpairlen = nullptr; const uint8_t *vpool = nullptr; uint32_t vpool_bytes = 0;
     // what the last enqueue left to do / to report
     int launches = 0;
     bool status_dirty = true;      // d_status[0] / d_total must be cleared before the next enqueue
-    bool pend_fast = false;        // only the fast path ran; total = n unless ST_IRREGULAR (then rerun generally)
+    bool pend_fast = false;        // only a fast path ran; on ST_IRREGULAR collect() reruns the buffer generally
+    bool pend_total_is_n = false;  // fast path was length preserving: total = n, else total comes from d_total
+    int pend_phase = 1;            // PH_* the fast path stood for
+    int counts_kind = 0;           // whose counts sit in the workspace: 1 general (cnt/gsum per group), 2 k_bmv (gsum per span)
+    size_t bmv_smem = 0; bool bmv_attr = false;
     const uint8_t *pend_in = nullptr; uint8_t *pend_out = nullptr; size_t pend_n = 0, pend_cap = 0;
     // host-buffer path: cached device buffers
     uint8_t *buf_in = nullptr, *buf_out = nullptr; size_t cap_in = 0, cap_out = 0;
@@ -125,6 +131,10 @@ int get_state(const trre_prog *cp, int device, DeviceState **out) {
     d->P.pairlut = h.off_pairlut ? reinterpret_cast<const uint16_t *>(d->d_blob + h.off_pairlut) : nullptr;
     d->P.row0 = h.off_row0 ? reinterpret_cast<const uint32_t *>(d->d_blob + h.off_row0) : nullptr;
     d->P.ctrans = h.off_ctrans ? reinterpret_cast<const uint32_t *>(d->d_blob + h.off_ctrans) : nullptr;
+    d->vent = h.off_vent ? reinterpret_cast<const uint32_t *>(d->d_blob + h.off_vent) : nullptr;
+    d->vpairlen = h.off_vpairlen ? reinterpret_cast<const uint16_t *>(d->d_blob + h.off_vpairlen) : nullptr;
+    d->vpool = h.off_vpool ? d->d_blob + h.off_vpool : nullptr;
+    d->vpool_bytes = h.vpool_bytes;
     d->P.eout = h.off_eout ? reinterpret_cast<const uint32_t *>(d->d_blob + h.off_eout) : nullptr;
     d->P.pool_bytes = h.pool_bytes;
     d->P.n_states = h.dsa_states;
@@ -208,6 +218,8 @@ void launch_lines(bool backtrack, int grid, cudaStream_t st, const LineArgs &a) 
     else k_lines<MODE, false><<<grid, kLineThreads, 0, st>>>(a);
 }
 
+enum { PH_SIZE = 0, PH_ALL = 1, PH_WRITE = 2 };    // count+scan | count+scan+write | write (counts already there)
+
 LineArgs make_args(DeviceState *d, const uint8_t *d_in, size_t n, uint8_t *d_out, size_t out_cap, uint32_t *status) {
     LineArgs a{};
     a.P = d->P; a.in = d_in; a.out = d_out; a.n = n; a.out_cap = out_cap;
@@ -253,8 +265,6 @@ int launch_fast(const trre_prog *p, DeviceState *d, const uint8_t *d_in, size_t 
 }
 
 // The general path: count -> scan -> (write).  3 kernels (2 when only sizing).
-enum { PH_SIZE = 0, PH_ALL = 1, PH_WRITE = 2 };    // count+scan | count+scan+write | write (counts already there)
-
 int launch_general(const trre_prog *p, DeviceState *d, const uint8_t *d_in, size_t n, uint8_t *d_out,
                    size_t out_cap, cudaStream_t st, int phase, int *launches) {
     const bool backtrack = p->hdr.exec_kind == TRRE_EXEC_BACKTRACK;
@@ -265,6 +275,7 @@ int launch_general(const trre_prog *p, DeviceState *d, const uint8_t *d_in, size
     if (grid < 1) grid = 1;
     int rc = ensure_workspace(d, n_chunks, n_groups, backtrack, (size_t)grid * kLineThreads);
     if (rc != TRRE_OK) return rc;
+    if (phase != PH_WRITE) d->counts_kind = 1;
     LineArgs a = make_args(d, d_in, n, d_out, out_cap, d->d_status);
     const bool staged = !backtrack && d->P.ctrans && !std::getenv("TRRE_NO_STAGED_LINES");
     StagedArgs sa{};
@@ -303,6 +314,47 @@ int launch_general(const trre_prog *p, DeviceState *d, const uint8_t *d_in, size
     return TRRE_OK;
 }
 
+bool bmv_capable(const trre_prog *p, const DeviceState *d, const uint8_t *d_in) {
+    return (p->hdr.flags & PF_BYTEMAP_VAR) && d->vent && (reinterpret_cast<uintptr_t>(d_in) & 15) == 0 &&
+           !std::getenv("TRRE_NO_BMV");
+}
+
+// variable-length byte map on a regular buffer: count -> scan -> write, all position parallel (bmv_kernel.cuh)
+int launch_bmv(const trre_prog *p, DeviceState *d, const uint8_t *d_in, size_t n, uint8_t *d_out, size_t out_cap,
+               cudaStream_t st, int phase, int *launches) {
+    const size_t n_tiles = (n + kBmvTile - 1) / kBmvTile;
+    size_t n_spans = std::min<size_t>(std::max<size_t>(n_tiles / 16, 1), (size_t)d->sm_count * 64);
+    const size_t tiles_per_span = (n_tiles + n_spans - 1) / n_spans;
+    n_spans = (n_tiles + tiles_per_span - 1) / tiles_per_span;
+    int rc = ensure_workspace(d, 0, n_spans, false, 0);
+    if (rc != TRRE_OK) return rc;
+    if (!d->bmv_attr) {
+        d->bmv_smem = 256 * 32 * 4 + ((d->vpool_bytes + 15) & ~15u) + (size_t)(kBmvWriteThreads / 32) * kBmvWarpSmem;
+        CUDA_TRY(cudaFuncSetAttribute(k_bmv_count, cudaFuncAttributeMaxDynamicSharedMemorySize, kPairLutBytes));
+        CUDA_TRY(cudaFuncSetAttribute(k_bmv_write, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)d->bmv_smem));
+        d->bmv_attr = true;
+    }
+    BmvArgs a{};
+    a.in = d_in; a.out = d_out; a.n = n; a.out_cap = out_cap;
+    a.vent = d->vent; a.vpairlen = d->vpairlen; a.vpool = d->vpool; a.vpool_bytes = d->vpool_bytes;
+    a.gsum = d->d_gsum; a.total = d->d_total; a.status = d->d_status;
+    a.n_spans = n_spans; a.tiles_per_span = tiles_per_span;
+    if (phase != PH_WRITE) {
+        k_bmv_count<<<d->sm_count, kBmvCountThreads, kPairLutBytes, st>>>(a);
+        k_scan_groups<<<1, kScanThreads, 0, st>>>(d->d_gsum, n_spans, d->d_total);
+        *launches += 2;
+        d->counts_kind = 2;
+    }
+    if (phase != PH_SIZE) {
+        const size_t per = kBmvWriteThreads / 32;
+        int grid = (int)std::min<size_t>((n_spans + per - 1) / per, (size_t)d->sm_count * 2);
+        k_bmv_write<<<grid < 1 ? 1 : grid, kBmvWriteThreads, d->bmv_smem, st>>>(a);
+        *launches += 1;
+    }
+    CUDA_TRY(cudaGetLastError());
+    return TRRE_OK;
+}
+
 int clear_status(DeviceState *d, cudaStream_t st) {
     CUDA_TRY(cudaMemsetAsync(d->d_status, 0, sizeof(uint32_t), st));
     CUDA_TRY(cudaMemsetAsync(d->d_total, 0, sizeof(unsigned long long), st));
@@ -319,15 +371,22 @@ int enqueue_scan(const trre_prog *p, DeviceState *d, const uint8_t *d_in, size_t
     d->pend_in = d_in; d->pend_out = d_out; d->pend_n = n; d->pend_cap = out_cap;
     if (d->status_dirty) { int rc = clear_status(d, st); if (rc != TRRE_OK) return rc; }
     if (n == 0) return TRRE_OK;
+    d->pend_phase = size_only ? PH_SIZE : PH_ALL;
     if (!size_only && fast_capable(p->hdr) && out_cap >= n) {
         int rc = launch_fast(p, d, d_in, n, d_out, d->d_status, st);
         if (rc != TRRE_OK) return rc;
         d->launches = 1;
         d->pend_fast = true;
+        d->pend_total_is_n = true;
         return TRRE_OK;
     }
     d->status_dirty = true;                 // k_scan_groups writes d_total
-    return launch_general(p, d, d_in, n, d_out, out_cap, st, size_only ? PH_SIZE : PH_ALL, &d->launches);
+    if (bmv_capable(p, d, d_in)) {
+        d->pend_fast = true;
+        d->pend_total_is_n = false;
+        return launch_bmv(p, d, d_in, n, d_out, out_cap, st, d->pend_phase, &d->launches);
+    }
+    return launch_general(p, d, d_in, n, d_out, out_cap, st, d->pend_phase, &d->launches);
 }
 
 int status_to_rc(uint32_t s) {
@@ -340,17 +399,18 @@ int status_to_rc(uint32_t s) {
 // Synchronise, finish what the enqueue left open, report size and status.
 int collect(const trre_prog *p, DeviceState *d, cudaStream_t st, size_t *out_n) {
     CUDA_TRY(cudaMemcpyAsync(d->h_status, d->d_status, sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
-    if (!d->pend_fast) CUDA_TRY(cudaMemcpyAsync(d->h_total, d->d_total, sizeof(unsigned long long), cudaMemcpyDeviceToHost, st));
+    const bool total_is_n = d->pend_fast && d->pend_total_is_n;
+    if (!total_is_n) CUDA_TRY(cudaMemcpyAsync(d->h_total, d->d_total, sizeof(unsigned long long), cudaMemcpyDeviceToHost, st));
     CUDA_TRY(cudaStreamSynchronize(st));
     uint32_t s = *d->h_status;
-    size_t total = d->pend_fast ? d->pend_n : (size_t)*d->h_total;
+    size_t total = total_is_n ? d->pend_n : (size_t)*d->h_total;
     if (d->pend_fast && (s & ST_IRREGULAR)) {
         // NUL bytes or no trailing newline: same buffers, general path
         int rc = clear_status(d, st);
         if (rc != TRRE_OK) return rc;
         d->pend_fast = false;
         d->status_dirty = true;
-        rc = launch_general(p, d, d->pend_in, d->pend_n, d->pend_out, d->pend_cap, st, PH_ALL, &d->launches);
+        rc = launch_general(p, d, d->pend_in, d->pend_n, d->pend_out, d->pend_cap, st, d->pend_phase, &d->launches);
         if (rc != TRRE_OK) return rc;
         CUDA_TRY(cudaMemcpyAsync(d->h_status, d->d_status, sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
         CUDA_TRY(cudaMemcpyAsync(d->h_total, d->d_total, sizeof(unsigned long long), cudaMemcpyDeviceToHost, st));
@@ -593,7 +653,8 @@ int trre_scan_into(const trre_prog *p, int device, const uint8_t *in, size_t n, 
     {
         if (d->status_dirty) { CUDA_TRY(cudaMemsetAsync(d->d_status, 0, sizeof(uint32_t), st)); }
         int wl = 0;
-        rc = launch_general(p, d, d->buf_in, n, d->buf_out, total, st, PH_WRITE, &wl);
+        rc = d->counts_kind == 2 ? launch_bmv(p, d, d->buf_in, n, d->buf_out, total, st, PH_WRITE, &wl)
+                                 : launch_general(p, d, d->buf_in, n, d->buf_out, total, st, PH_WRITE, &wl);
         if (rc != TRRE_OK) return rc;
         d->pend_fast = false;
         d->status_dirty = true;
