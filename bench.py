@@ -56,6 +56,7 @@ def dictionary_words(k=10000, seed=7):
 _DICT = dictionary_words()
 WORKLOADS["cfg5"] = ("|".join("%s:%s" % (w, w.upper()) for w in _DICT), 1, 8 * GiB, _DICT, 0.30, True, 0x72726505, "trre_dft")
 WORKLOADS["del"] = ("a:", 0, 1 * GiB, None, 0.0, False, 0x72726506, "trre")
+WORKLOADS["sub"] = ("cat:mouse|dog:d", 0, 1 * GiB, ["cat", "dog", "catdog", "dogcat", "ca", "do", "cot", "dig"], 0.25, False, 0x72726507, "trre")
 
 DESCR = {
     "cfg1": "'cat:dog' over 1 MB ASCII (NFT flavour)",
@@ -63,6 +64,7 @@ DESCR = {
     "cfg3": "'(cat:dog|dog:cat)' over 8 GiB synthetic text per GPU, NFT flavour (BASELINE configs[2])",
     "cfg4": "Caesar '[a:b-y:zz:a]' over 8 GiB synthetic ASCII per GPU, DFT flavour (BASELINE configs[3], 64 GiB at 8 GPUs)",
     "cfg5": "10k-alternation word:WORD dictionary (18 402-state DFT) over 8 GiB synthetic lowercase text per GPU, DFT flavour (BASELINE configs[4])",
+    "sub": "'cat:mouse|dog:d' (matches print more / fewer bytes than they consume) over 1 GiB synthetic text, NFT flavour",
     "del": "'a:' (delete every a; NOT length preserving: count + scan + write path) over 1 GiB synthetic ASCII, NFT flavour",
 }
 METRIC = "input GB/s (scan mode)"
@@ -313,7 +315,8 @@ def main():
     for r in range(reps):
         d_in[r * tile_n:(r + 1) * tile_n].copy_(d_tile)
     del d_tile
-    d_out = torch.empty(n + 64, dtype=torch.uint8, device=dev)
+    out_cap = n + 64 if info["length_preserving"] else 2 * n + 64      # expanding programs: room for 2x
+    d_out = torch.empty(out_cap, dtype=torch.uint8, device=dev)
     stream = torch.cuda.current_stream()
     sp = stream.cuda_stream
 
@@ -398,7 +401,7 @@ def main():
         h_in = torch.empty(n, dtype=torch.uint8, pin_memory=True)
         for r in range(reps):
             h_in[r * tile_n:(r + 1) * tile_n].copy_(h_tile)
-        h_out = torch.empty(n + 64, dtype=torch.uint8, pin_memory=True)
+        h_out = torch.empty(out_cap, dtype=torch.uint8, pin_memory=True)
         prog.scan_into(h_in.data_ptr(), n, h_out.data_ptr(), h_out.numel(), device=local_rank)   # warm-up
         barrier()
         t0 = time.perf_counter()

@@ -261,3 +261,50 @@ def test_bytemap_var_device_api_unaligned_output_and_capacity():
     with pytest.raises(T.TrreError) as ei:
         prog.scan_device(d_in.data_ptr(), d_in.numel(), buf.data_ptr(), 1000, stream=torch.cuda.current_stream().cuda_stream)
     assert ei.value.code == 4 and ei.value.needed == len(want)
+
+
+# ---- variable-length matches (k_match<OP_COUNT/OP_WRITE>): s/cat/mouse/ and friends ------------------------
+
+MV_PATTERNS = [("cat:mouse", NFT), ("cat:mouse", DFT), ("(cat):", NFT), ("(cat):", DFT), ("cat:mouse|dog:d", NFT),
+               ("ab:X|abc:Y|a:Z", NFT), ("ab:X|abc:Y|a:Z", DFT), ("(aa):b", NFT), ("aba:xy", DFT),
+               ("abab:w|ba:XYZ", NFT), ("(abcabcabcabcabca):Q|bc:XYZW", NFT), ("a(b:XY)c", NFT)]
+
+
+@pytest.mark.parametrize("expr,flavor", MV_PATTERNS)
+def test_variable_length_matches(expr, flavor, monkeypatch):
+    prog = T.compile(expr, flavor)
+    assert prog.info["max_depth"] <= 16          # (the DFT flavour of ab:X|abc:Y|a:Z always takes a:Z: length preserving)
+    for seed, alphabet, hi, size in ((51, b"abc", 200, 2 << 20), (52, b"ab", 60, 1 << 20), (53, b"cat dogma", 120, 2 << 20)):
+        data = _ab_text(seed, size, alphabet, 0, hi)
+        rc, want, _ = oracle_run(expr.encode(), data, flavor=flavor)
+        assert rc == 0
+        assert prog.scan(data) == want, (expr, flavor, seed, "k_match var")
+        monkeypatch.setenv("TRRE_NO_MATCH_KERNEL", "1")
+        assert prog.scan(data) == want, (expr, flavor, seed, "general")
+        monkeypatch.delenv("TRRE_NO_MATCH_KERNEL")
+    for data in (b"", b"cat", b"cat\n", b"catcat\ncat", b"ab\0ab\nab\n", b"a" * 9000 + b"\n", b"abab" * 3000 + b"\n"):
+        check(expr, flavor, data)
+
+
+def test_variable_length_dictionary_and_device_api():
+    torch = pytest.importorskip("torch")
+    rng = random.Random(5)
+    words = sorted({"".join(rng.choice("abcdefgh") for _ in range(rng.randint(2, 6))) for _ in range(300)})
+    # prefix-free is not required: the NFT flavour takes the first alternative, the DFT flavour the shortest
+    expr = "|".join("%s:%s" % (w, w.upper() * rng.randint(0, 2)) for w in words)
+    text = bytes(T.synth_text(77, 3 << 20, words[:40], 0.3, True)).replace(b"z", b"a")
+    for flavor in (NFT, DFT):
+        rc, want, _ = oracle_run(expr.encode(), text, flavor=flavor)
+        assert rc == 0
+        prog = T.compile(expr, flavor)
+        assert prog.scan(text) == want, flavor
+    prog = T.compile("cat:mouse", NFT)
+    data = _ab_text(61, 4 << 20, b"cat dog", 1, 100)
+    rc, want, _ = oracle_run(b"cat:mouse", data, flavor=NFT)
+    d_in = torch.frombuffer(bytearray(data), dtype=torch.uint8).cuda()
+    buf = torch.zeros(2 * len(data) + 64, dtype=torch.uint8, device="cuda")
+    for shift in (0, 3, 15):
+        d_out = buf[shift:]
+        n = prog.scan_device(d_in.data_ptr(), d_in.numel(), d_out.data_ptr(), d_out.numel(),
+                             stream=torch.cuda.current_stream().cuda_stream)
+        assert n == len(want) and bytes(d_out[:n].cpu().numpy().tobytes()) == want, shift

@@ -450,14 +450,16 @@ void analyse_and_pack(const std::vector<RawState> &st, const StringPool &sp, int
                 if (!(st[e.next].flags & DSA_S_DECIDED) && !sp.get(e.out_id).empty()) { late = false; break; }
         if (late) {
             std::unordered_map<std::string, uint32_t> placed;
-            auto place = [&](const std::string &str) -> uint32_t {
+            bool fits = true;
+            auto place = [&](const std::string &str) -> uint32_t {             // -> offset(24) | length(8)
                 if (str.empty()) return 0;
+                if (str.size() > 255) { fits = false; return 0; }
                 auto it = placed.find(str);
                 if (it != placed.end()) return it->second;
-                uint32_t off = (uint32_t)pw.bytes.size();
+                uint32_t ref = (uint32_t)pw.bytes.size() | ((uint32_t)str.size() << 24);
                 pw.bytes.insert(pw.bytes.end(), str.begin(), str.end());
-                placed.emplace(str, off);
-                return off;
+                placed.emplace(str, ref);
+                return ref;
             };
             P.eout.assign((size_t)S * P.n_classes + S, 0);
             for (uint32_t s = 0; s < S; ++s) {
@@ -467,7 +469,7 @@ void analyse_and_pack(const std::vector<RawState> &st, const StringPool &sp, int
                     if (st[e.next].flags & DSA_S_DECIDED)
                         P.eout[(size_t)s * P.n_classes + P.classmap[e.byte]] = place(sp.get(e.out_id) + sp.get(st[e.next].fin_id));
             }
-            if (pw.bytes.size() >= (1u << 24)) P.eout.clear();
+            if (pw.bytes.size() >= (1u << 24) || !fits) P.eout.clear();
         }
     }
     P.pool = std::move(pw.bytes);
@@ -614,10 +616,15 @@ std::vector<uint8_t> assemble(const Program &P, const Nft &g) {
         h.off_vpairlen = (uint32_t)off; off += 65536 * 2;
         h.off_vpool = (uint32_t)off; h.vpool_bytes = (uint32_t)vpool.size(); off += vpool.size(); off = align16(off);
     }
+    // the same, but a match may print more or fewer bytes than it consumes (s/cat/mouse/): needs the single
+    // output string per match (PF_OUT_LATE tables); byte maps have their own kernels
+    const bool matchable_var = P.exec_kind == TRRE_EXEC_TABLE && !(P.flags & PF_LENGTH_PRESERVING) && (P.flags & PF_ACYCLIC) &&
+                               !(P.flags & (PF_CAN_MATCH_EMPTY | PF_HAS_DIVERGE)) && P.max_depth >= 1 && P.max_depth <= 16 &&
+                               !P.eout.empty() && !P.vmap;
     if (!P.trans.empty()) {                                   // compact tables: every table program
         h.off_row0 = (uint32_t)off; off += 256 * 4;
         h.off_ctrans = (uint32_t)off; off += P.trans.size() * 4; off = align16(off);
-        if (matchable && !P.eout.empty()) { h.off_eout = (uint32_t)off; off += P.eout.size() * 4; off = align16(off); }
+        if ((matchable || matchable_var) && !P.eout.empty()) { h.off_eout = (uint32_t)off; off += P.eout.size() * 4; off = align16(off); }
     }
     if (off >= (1ull << 31)) throw PatternError{TRRE_E_UNSUPPORTED, "error: compiled tables exceed 2 GiB\n"};
     h.magic = 0x32425254u;  // "TRB2"
@@ -625,7 +632,8 @@ std::vector<uint8_t> assemble(const Program &P, const Nft &g) {
     h.total_bytes = (uint32_t)off;
     h.flavor = (uint32_t)P.flavor;
     h.exec_kind = P.exec_kind;
-    h.flags = P.flags | (matchable ? (uint32_t)PF_MATCHABLE : 0u) | (P.vmap ? (uint32_t)PF_BYTEMAP_VAR : 0u);
+    h.flags = P.flags | (matchable ? (uint32_t)PF_MATCHABLE : 0u) | (P.vmap ? (uint32_t)PF_BYTEMAP_VAR : 0u) |
+              (matchable_var ? (uint32_t)PF_MATCHABLE_VAR : 0u);
     h.nft_states = (uint32_t)g.st.size();
     h.nft_start = g.start;
     h.dsa_states = (uint32_t)P.sinfo.size();

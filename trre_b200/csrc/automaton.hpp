@@ -49,7 +49,8 @@ enum : uint32_t {
     PF_NUL_IN_OUTPUT     = 8u,       // some PROD byte is 0: NFT flavour truncates at it (fputs)
     PF_HAS_DIVERGE       = 16u,
     PF_MATCHABLE         = 64u,
-    PF_BYTEMAP_VAR       = 128u,     // every attempt is decided by one byte; that byte prints 0..255 bytes (k_bmv_*)      // k_match applies: length preserving, acyclic, attempts <= 16 bytes, no empty match
+    PF_BYTEMAP_VAR       = 128u,
+    PF_MATCHABLE_VAR     = 256u,     // k_mv_* apply: like PF_MATCHABLE but matches may print more or less than they consume     // every attempt is decided by one byte; that byte prints 0..255 bytes (k_bmv_*)      // k_match applies: length preserving, acyclic, attempts <= 16 bytes, no empty match
     PF_OUT_LATE          = 32u       // every transition into a non-DECIDED state emits nothing: a match's output
                                      // is out(last transition) + fin(last state)
 };
@@ -82,8 +83,8 @@ struct BlobHeader {
     uint32_t off_vpairlen;     // (PF_BYTEMAP_VAR) u16[65536]: len[c0] + len[c1], bank-swizzled like the pair LUT
     uint32_t off_vpool;        // (PF_BYTEMAP_VAR) strings longer than one byte
     uint32_t vpool_bytes;
-    uint32_t off_eout;         // u32[dsa_states * n_classes]: (PF_OUT_LATE) pool offset of out(edge)+fin(target) for edges
-                               // into DECIDED states; u32[dsa_states] fin offsets follow (pending FINAL). 0 if absent
+    uint32_t off_eout;         // u32[dsa_states * n_classes]: (PF_OUT_LATE) offset(24) | length(8) of out(edge)+fin(target) in the
+                               // pool for edges into DECIDED states; u32[dsa_states] for pending FINALs follow. 0 if absent
 };
 
 struct NftFlat {               // 12 bytes, device layout of trre_nft.c:334-340

@@ -34,6 +34,13 @@ void set_err(char *err, size_t cap, const std::string &s) {
 
 constexpr int kSlots = 3;                 // pipelined host path: chunks in flight
 
+struct MatchPlan {
+    uint32_t repl = 0, states = 0, pool = 0;
+    int tab = 0;
+    size_t smem = 0;
+    int blocks = 0;
+};
+
 struct DeviceState {
     int device = -1;
     uint8_t *d_blob = nullptr;
@@ -57,7 +64,7 @@ struct DeviceState {
     bool pend_fast = false;        // only a fast path ran; on ST_IRREGULAR collect() reruns the buffer generally
     bool pend_total_is_n = false;  // fast path was length preserving: total = n, else total comes from d_total
     int pend_phase = 1;            // PH_* the fast path stood for
-    int counts_kind = 0;           // whose counts sit in the workspace: 1 general (cnt/gsum per group), 2 k_bmv (gsum per span)
+    int counts_kind = 0;           // whose counts sit in the workspace: 1 general (cnt/gsum per group), 2 k_bmv, 3 k_match<OP_COUNT> (gsum per span)
     size_t bmv_smem = 0; bool bmv_attr = false;
     const uint8_t *pend_in = nullptr; uint8_t *pend_out = nullptr; size_t pend_n = 0, pend_cap = 0;
     // host-buffer path: cached device buffers
@@ -65,12 +72,8 @@ struct DeviceState {
     uint8_t *slot_in[kSlots] = {nullptr, nullptr, nullptr}, *slot_out[kSlots] = {nullptr, nullptr, nullptr};
     cudaStream_t slot_stream[kSlots] = {nullptr, nullptr, nullptr};
     size_t slot_cap = 0;
-    // k_match launch plan
-    uint32_t match_repl = 0, match_states = 0, match_pool = 0;
-    int match_tab = 0;
+    MatchPlan mp, mpv;             // k_match launch plans: length preserving / variable length
     bool staged_attr = false;
-    size_t match_smem = 0;
-    int match_blocks = 0;
 };
 
 }  // namespace
@@ -102,6 +105,41 @@ struct DeviceGuard {
     }
     ~DeviceGuard() { if (prev >= 0) cudaSetDevice(prev); }
 };
+
+// shared-memory plan of k_match: bank-replicated live table when everything fits; raw-byte rows for small
+// automata; otherwise the first (shallowest: states are numbered breadth first) rows of the compact table
+int plan_match(const BlobHeader &h, size_t warp_bytes, size_t budget, int sm_count, int op, MatchPlan *mp) {
+    const size_t ct_full = (((size_t)h.dsa_states * h.n_classes + 3) & ~(size_t)3) * 4;
+    mp->pool = h.pool_bytes <= 4096 ? 1 : 0;
+    const size_t fixed = 1024 + 256 + (mp->pool ? ((h.pool_bytes + 15) & ~15u) : 0) + warp_bytes;
+    mp->tab = TAB_PART;
+    size_t ct_bytes;
+    if (32768 + fixed + (size_t)h.dsa_states * 1024 <= budget) {              // small automaton: raw-byte rows
+        mp->repl = 1; mp->states = h.dsa_states; mp->tab = TAB_WIDE;
+        ct_bytes = (size_t)h.dsa_states * 1024;
+    } else if (32768 + fixed + ct_full <= budget) {
+        mp->repl = 1; mp->states = h.dsa_states; mp->tab = TAB_ALL;
+        ct_bytes = ct_full;
+    } else {
+        mp->repl = 0;
+        size_t rows = (budget - fixed) / ((size_t)h.n_classes * 4);
+        mp->states = (uint32_t)std::min<size_t>(rows, h.dsa_states);
+        if (mp->states == h.dsa_states) mp->tab = TAB_ALL;
+        ct_bytes = (((size_t)mp->states * h.n_classes + 3) & ~(size_t)3) * 4;
+    }
+    mp->smem = (mp->repl ? 32768 : 0) + fixed + ct_bytes;
+    int per_sm = 1;
+    const void *fns[3][3] = {
+        {(const void *)k_match<TAB_PART, OP_INPLACE>, (const void *)k_match<TAB_PART, OP_COUNT>, (const void *)k_match<TAB_PART, OP_WRITE>},
+        {(const void *)k_match<TAB_ALL, OP_INPLACE>, (const void *)k_match<TAB_ALL, OP_COUNT>, (const void *)k_match<TAB_ALL, OP_WRITE>},
+        {(const void *)k_match<TAB_WIDE, OP_INPLACE>, (const void *)k_match<TAB_WIDE, OP_COUNT>, (const void *)k_match<TAB_WIDE, OP_WRITE>}};
+    for (int o = (op == OP_INPLACE ? OP_INPLACE : OP_COUNT); o <= (op == OP_INPLACE ? OP_INPLACE : OP_WRITE); ++o) {
+        CUDA_TRY(cudaFuncSetAttribute(fns[mp->tab][o], cudaFuncAttributeMaxDynamicSharedMemorySize, (int)mp->smem));
+        CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fns[mp->tab][o], kMatchThreads, mp->smem));
+    }
+    mp->blocks = sm_count * (per_sm < 1 ? 1 : per_sm);
+    return TRRE_OK;
+}
 
 int get_state(const trre_prog *cp, int device, DeviceState **out) {
     trre_prog *p = const_cast<trre_prog *>(cp);
@@ -149,35 +187,12 @@ int get_state(const trre_prog *cp, int device, DeviceState **out) {
     d->P.nft_start = h.nft_start;
     CUDA_TRY(cudaFuncSetAttribute(k_bytemap, cudaFuncAttributeMaxDynamicSharedMemorySize, kPairLutBytes));
     if (h.flags & PF_MATCHABLE) {
-        // shared-memory plan of k_match: replicate row0 per bank when everything fits, else cache the
-        // first (shallowest: states are numbered breadth first) rows of the compact table
-        const size_t warp_bytes = (size_t)kMatchWarps * kWarpSmem;
-        const size_t ct_full = (((size_t)h.dsa_states * h.n_classes + 3) & ~(size_t)3) * 4;
-        const size_t budget = 108 * 1024;                       // two CTAs per SM
-        d->match_pool = h.pool_bytes <= 4096 ? 1 : 0;
-        const size_t fixed = 1024 + 256 + (d->match_pool ? ((h.pool_bytes + 15) & ~15u) : 0) + warp_bytes;
-        d->match_tab = TAB_PART;
-        size_t ct_bytes;
-        if (32768 + fixed + (size_t)h.dsa_states * 1024 <= budget) {          // small automaton: raw-byte rows
-            d->match_repl = 1; d->match_states = h.dsa_states; d->match_tab = TAB_WIDE;
-            ct_bytes = (size_t)h.dsa_states * 1024;
-        } else if (32768 + fixed + ct_full <= budget) {
-            d->match_repl = 1; d->match_states = h.dsa_states; d->match_tab = TAB_ALL;
-            ct_bytes = ct_full;
-        } else {
-            d->match_repl = 0;
-            size_t rows = (budget - fixed) / ((size_t)h.n_classes * 4);
-            d->match_states = (uint32_t)std::min<size_t>(rows, h.dsa_states);
-            if (d->match_states == h.dsa_states) d->match_tab = TAB_ALL;
-            ct_bytes = (((size_t)d->match_states * h.n_classes + 3) & ~(size_t)3) * 4;
-        }
-        d->match_smem = (d->match_repl ? 32768 : 0) + fixed + ct_bytes;
-        int per_sm = 1;
-        const void *fn = d->match_tab == TAB_WIDE ? (const void *)k_match<TAB_WIDE>
-                       : d->match_tab == TAB_ALL  ? (const void *)k_match<TAB_ALL> : (const void *)k_match<TAB_PART>;
-        CUDA_TRY(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)d->match_smem));
-        CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fn, kMatchThreads, d->match_smem));
-        d->match_blocks = d->sm_count * (per_sm < 1 ? 1 : per_sm);
+        int rc2 = plan_match(h, (size_t)kMatchWarps * kWarpSmem, 108 * 1024, d->sm_count, OP_INPLACE, &d->mp);
+        if (rc2 != TRRE_OK) return rc2;
+    }
+    if (h.flags & PF_MATCHABLE_VAR) {
+        int rc2 = plan_match(h, (size_t)kMatchWarps * kVarWarpSmem, 108 * 1024, d->sm_count, OP_COUNT, &d->mpv);
+        if (rc2 != TRRE_OK) return rc2;
     }
     p->dev[device] = d;
     *out = d;
@@ -246,15 +261,15 @@ int launch_fast(const trre_prog *p, DeviceState *d, const uint8_t *d_in, size_t 
     } else if ((d->P.flags & PF_MATCHABLE) && d->P.row0 && aligned && (reinterpret_cast<uintptr_t>(d_in) & 15) == 0 && !std::getenv("TRRE_NO_MATCH_KERNEL")) {
         MatchArgs m{};
         m.P = d->P; m.in = d_in; m.out = d_out; m.n = n; m.status = status;
-        m.smem_states = d->match_states; m.row0_replicated = d->match_repl; m.pool_in_smem = d->match_pool;
+        m.smem_states = d->mp.states; m.row0_replicated = d->mp.repl; m.pool_in_smem = d->mp.pool;
         const size_t n_tiles = (n + kTile - 1) / kTile;
         // every warp owns a contiguous span of tiles; keep spans >= 16 tiles so the warm-up stays cheap
-        size_t blocks = std::min<size_t>((size_t)d->match_blocks, (n_tiles + 16 * kMatchWarps - 1) / (16 * kMatchWarps));
+        size_t blocks = std::min<size_t>((size_t)d->mp.blocks, (n_tiles + 16 * kMatchWarps - 1) / (16 * kMatchWarps));
         if (blocks < 1) blocks = 1;
         m.tiles_per_warp = (n_tiles + blocks * kMatchWarps - 1) / (blocks * kMatchWarps);
-        if (d->match_tab == TAB_WIDE) k_match<TAB_WIDE><<<(int)blocks, kMatchThreads, d->match_smem, st>>>(m);
-        else if (d->match_tab == TAB_ALL) k_match<TAB_ALL><<<(int)blocks, kMatchThreads, d->match_smem, st>>>(m);
-        else k_match<TAB_PART><<<(int)blocks, kMatchThreads, d->match_smem, st>>>(m);
+        if (d->mp.tab == TAB_WIDE) k_match<TAB_WIDE, OP_INPLACE><<<(int)blocks, kMatchThreads, d->mp.smem, st>>>(m);
+        else if (d->mp.tab == TAB_ALL) k_match<TAB_ALL, OP_INPLACE><<<(int)blocks, kMatchThreads, d->mp.smem, st>>>(m);
+        else k_match<TAB_PART, OP_INPLACE><<<(int)blocks, kMatchThreads, d->mp.smem, st>>>(m);
     } else {
         LineArgs a = make_args(d, d_in, n, d_out, n, status);
         int grid = (int)std::min<size_t>(a.n_groups, (size_t)d->sm_count * 64);
@@ -355,6 +370,44 @@ int launch_bmv(const trre_prog *p, DeviceState *d, const uint8_t *d_in, size_t n
     return TRRE_OK;
 }
 
+bool mv_capable(const trre_prog *p, const DeviceState *d, const uint8_t *d_in) {
+    return (p->hdr.flags & PF_MATCHABLE_VAR) && d->P.eout && d->mpv.smem && (reinterpret_cast<uintptr_t>(d_in) & 15) == 0 &&
+           !std::getenv("TRRE_NO_MATCH_KERNEL");
+}
+
+// variable-length matches on a regular buffer: k_match<OP_COUNT> -> scan over the warp spans -> k_match<OP_WRITE>
+int launch_mv(const trre_prog *p, DeviceState *d, const uint8_t *d_in, size_t n, uint8_t *d_out, size_t out_cap,
+              cudaStream_t st, int phase, int *launches) {
+    const size_t n_tiles = (n + kTile - 1) / kTile;
+    size_t blocks = std::min<size_t>((size_t)d->mpv.blocks, (n_tiles + 16 * kMatchWarps - 1) / (16 * kMatchWarps));
+    if (blocks < 1) blocks = 1;
+    const size_t n_spans = blocks * kMatchWarps;
+    int rc = ensure_workspace(d, 0, n_spans, false, 0);
+    if (rc != TRRE_OK) return rc;
+    MatchArgs m{};
+    m.P = d->P; m.in = d_in; m.out = d_out; m.n = n; m.status = d->d_status;
+    m.smem_states = d->mpv.states; m.row0_replicated = d->mpv.repl; m.pool_in_smem = d->mpv.pool;
+    m.tiles_per_warp = (n_tiles + n_spans - 1) / n_spans;
+    m.gsum = d->d_gsum; m.total = d->d_total; m.out_cap = out_cap;
+    const int tab = d->mpv.tab;
+    if (phase != PH_WRITE) {
+        if (tab == TAB_WIDE) k_match<TAB_WIDE, OP_COUNT><<<(int)blocks, kMatchThreads, d->mpv.smem, st>>>(m);
+        else if (tab == TAB_ALL) k_match<TAB_ALL, OP_COUNT><<<(int)blocks, kMatchThreads, d->mpv.smem, st>>>(m);
+        else k_match<TAB_PART, OP_COUNT><<<(int)blocks, kMatchThreads, d->mpv.smem, st>>>(m);
+        k_scan_groups<<<1, kScanThreads, 0, st>>>(d->d_gsum, n_spans, d->d_total);
+        *launches += 2;
+        d->counts_kind = 3;
+    }
+    if (phase != PH_SIZE) {
+        if (tab == TAB_WIDE) k_match<TAB_WIDE, OP_WRITE><<<(int)blocks, kMatchThreads, d->mpv.smem, st>>>(m);
+        else if (tab == TAB_ALL) k_match<TAB_ALL, OP_WRITE><<<(int)blocks, kMatchThreads, d->mpv.smem, st>>>(m);
+        else k_match<TAB_PART, OP_WRITE><<<(int)blocks, kMatchThreads, d->mpv.smem, st>>>(m);
+        *launches += 1;
+    }
+    CUDA_TRY(cudaGetLastError());
+    return TRRE_OK;
+}
+
 int clear_status(DeviceState *d, cudaStream_t st) {
     CUDA_TRY(cudaMemsetAsync(d->d_status, 0, sizeof(uint32_t), st));
     CUDA_TRY(cudaMemsetAsync(d->d_total, 0, sizeof(unsigned long long), st));
@@ -385,6 +438,11 @@ int enqueue_scan(const trre_prog *p, DeviceState *d, const uint8_t *d_in, size_t
         d->pend_fast = true;
         d->pend_total_is_n = false;
         return launch_bmv(p, d, d_in, n, d_out, out_cap, st, d->pend_phase, &d->launches);
+    }
+    if (mv_capable(p, d, d_in)) {
+        d->pend_fast = true;
+        d->pend_total_is_n = false;
+        return launch_mv(p, d, d_in, n, d_out, out_cap, st, d->pend_phase, &d->launches);
     }
     return launch_general(p, d, d_in, n, d_out, out_cap, st, d->pend_phase, &d->launches);
 }
@@ -653,8 +711,9 @@ int trre_scan_into(const trre_prog *p, int device, const uint8_t *in, size_t n, 
     {
         if (d->status_dirty) { CUDA_TRY(cudaMemsetAsync(d->d_status, 0, sizeof(uint32_t), st)); }
         int wl = 0;
-        rc = d->counts_kind == 2 ? launch_bmv(p, d, d->buf_in, n, d->buf_out, total, st, PH_WRITE, &wl)
-                                 : launch_general(p, d, d->buf_in, n, d->buf_out, total, st, PH_WRITE, &wl);
+        rc = d->counts_kind == 2   ? launch_bmv(p, d, d->buf_in, n, d->buf_out, total, st, PH_WRITE, &wl)
+             : d->counts_kind == 3 ? launch_mv(p, d, d->buf_in, n, d->buf_out, total, st, PH_WRITE, &wl)
+                                   : launch_general(p, d, d->buf_in, n, d->buf_out, total, st, PH_WRITE, &wl);
         if (rc != TRRE_OK) return rc;
         d->pend_fast = false;
         d->status_dirty = true;

@@ -42,7 +42,15 @@ struct MatchArgs {
     uint32_t row0_replicated;    // 1: a 32x replicated live/dead table (bank = lane) serves step B
     uint32_t pool_in_smem;       // 1: the string pool is copied to shared memory
     size_t tiles_per_warp;
+    // variable-length form (k_match<.., OP_COUNT / OP_WRITE>): one output-length sum / offset per warp span
+    unsigned long long *gsum;
+    const unsigned long long *total;
+    size_t out_cap;
 };
+
+enum { OP_INPLACE = 0, OP_COUNT = 1, OP_WRITE = 2 };
+constexpr int kVarWindow = 1024;                              // output bytes assembled per tile before falling back
+constexpr int kVarWarpSmem = 544 + 16 + 2048 + (16 + kVarWindow + 32);   // s_in, count, match list / entries, window
 
 __device__ __forceinline__ uint4 ldg_vec(const uint8_t *p) {
     uint4 r;
@@ -115,7 +123,7 @@ __device__ __forceinline__ void emit_match(const MatchArgs &a, const MatchTables
         }
         const uint32_t slot = (lo & DSA_E_DECIDED) ? from * T.n_classes + T.classmap_s[by]
                                                    : a.P.n_states * T.n_classes + (lo & 0xFFFFFFu);
-        const uint8_t *src = T.pool + __ldg(a.P.eout + slot);
+        const uint8_t *src = T.pool + (__ldg(a.P.eout + slot) & 0xFFFFFFu);
         for (uint32_t k = 0; k < m; ++k) s_out[p + k] = src[k];
         return;
     }
@@ -137,21 +145,17 @@ __device__ __forceinline__ void emit_match(const MatchArgs &a, const MatchTables
     if (o.n - p != m) status |= ST_IRREGULAR;                        // cannot happen for a length-preserving program
 }
 
-template <bool STORE, int TAB>
-__device__ __forceinline__ void match_tile(const MatchArgs &a, const MatchTables &T, uint8_t *s_in,
-                                           uint8_t *s_out, uint16_t *s_list, uint32_t *s_count, size_t base, uint4 x, uint4 halo_in,
-                                           uint32_t lane, uint32_t first_valid, uint32_t &carry_e, uint4 &carry_halo,
-                                           uint32_t &nul_acc, uint32_t &status) {
-    // ---- A: stage the tile (input and default output = raw copy) -----------------------------------
-    *reinterpret_cast<uint4 *>(s_in + lane * 16) = x;
-    *reinterpret_cast<uint4 *>(s_out + lane * 16) = x;
-    if (lane == 0) {
-        *reinterpret_cast<uint4 *>(s_in + kTile) = halo_in;
-        *reinterpret_cast<uint4 *>(s_out + kTile) = halo_in;
-        *s_count = 0;
-    }
-    nul_acc |= ((x.x - 0x01010101u) & ~x.x) | ((x.y - 0x01010101u) & ~x.y) | ((x.z - 0x01010101u) & ~x.z) | ((x.w - 0x01010101u) & ~x.w);
+// Steps B-D of a tile, shared by k_match and the variable-length kernels (matchvar_kernel.cuh): which
+// matches of this lane's 16 positions are real, their lengths, and the overhangs in and out of the lane.
+struct Front {
+    uint32_t real;               // bit j: a real match starts at position j of this lane
+    unsigned long long lens;     // (m - 1) in 4 bits per position
+    uint32_t e_in, e_out;        // positions covered at the start of this lane / of the next one
+};
 
+template <int TAB>
+__device__ __forceinline__ Front tile_frontend(const MatchTables &T, const uint8_t *s_in, uint4 x, uint32_t lane,
+                                               uint32_t first_valid, uint32_t carry_e) {
     // ---- B: can an attempt starting with this byte survive its first transition? -> candidate mask ---
     uint32_t cand = 0;
     {
@@ -175,16 +179,17 @@ __device__ __forceinline__ void match_tile(const MatchArgs &a, const MatchTables
         const uint32_t my0 = lane * 16;
         if (first_valid > my0) cand &= (first_valid - my0 >= 16) ? 0u : (0xFFFFu << (first_valid - my0));
     }
-    __syncwarp();
+    __syncwarp();                                                     // the staged tile is visible
 
     // ---- C: candidates finish their walk; matches stay in registers: C = mask, lens = 4 bits each ----
     uint32_t C = 0;
-    unsigned long long lens = 0;                                     // (m - 1) per position
+    Front f;
+    f.lens = 0;
     while (cand) {
         const uint32_t j = __ffs(cand) - 1;
         cand &= cand - 1;
         const uint32_t m = walk_from<TAB>(T, s_in, lane * 16 + j);
-        if (m) { C |= 1u << j; lens |= (unsigned long long)(m - 1) << (4 * j); }
+        if (m) { C |= 1u << j; f.lens |= (unsigned long long)(m - 1) << (4 * j); }
     }
 
     // ---- D: which matches are real (start outside every earlier match) ---------------------------------
@@ -196,7 +201,7 @@ __device__ __forceinline__ void match_tile(const MatchArgs &a, const MatchTables
         while (Cm) {
             uint32_t j = __ffs(Cm) - 1;
             r |= 1u << j;
-            pos = j + 1 + ((uint32_t)(lens >> (4 * j)) & 15u);
+            pos = j + 1 + ((uint32_t)(f.lens >> (4 * j)) & 15u);
             Cm = pos < 16 ? (C & (0xFFFFu << pos)) : 0u;
         }
         real = r;
@@ -212,6 +217,29 @@ __device__ __forceinline__ void match_tile(const MatchArgs &a, const MatchTables
         if (!__any_sync(0xFFFFFFFFu, need)) break;
         if (need) chain(e_used);
     }
+    f.real = real; f.e_in = e_used; f.e_out = e_out;
+    return f;
+}
+
+template <bool STORE, int TAB>
+__device__ __forceinline__ void match_tile(const MatchArgs &a, const MatchTables &T, uint8_t *s_in,
+                                           uint8_t *s_out, uint16_t *s_list, uint32_t *s_count, size_t base, uint4 x, uint4 halo_in,
+                                           uint32_t lane, uint32_t first_valid, uint32_t &carry_e, uint4 &carry_halo,
+                                           uint32_t &nul_acc, uint32_t &status) {
+    // ---- A: stage the tile (input and default output = raw copy) -----------------------------------
+    *reinterpret_cast<uint4 *>(s_in + lane * 16) = x;
+    *reinterpret_cast<uint4 *>(s_out + lane * 16) = x;
+    if (lane == 0) {
+        *reinterpret_cast<uint4 *>(s_in + kTile) = halo_in;
+        *reinterpret_cast<uint4 *>(s_out + kTile) = halo_in;
+        *s_count = 0;
+    }
+    nul_acc |= ((x.x - 0x01010101u) & ~x.x) | ((x.y - 0x01010101u) & ~x.y) | ((x.z - 0x01010101u) & ~x.z) | ((x.w - 0x01010101u) & ~x.w);
+
+    const Front f = tile_frontend<TAB>(T, s_in, x, lane, first_valid, carry_e);
+    uint32_t real = f.real;
+    const unsigned long long lens = f.lens;
+    const uint32_t e_out = f.e_out;
 
     // ---- E: real matches overwrite their span of the output tile; the work is dealt round the warp ------
     if (lane == 0 && carry_e) {
@@ -249,7 +277,177 @@ __device__ __forceinline__ void match_tile(const MatchArgs &a, const MatchTables
     __syncwarp();
 }
 
+// ---- variable-length matches (PF_MATCHABLE_VAR): s/cat/mouse/, (cat):, dictionaries of unequal words ----
+// Same front end; what changes is the output side: every uncovered non-match position prints its byte,
+// every real match prints its string (offset | length from the eout table), covered positions print
+// nothing -> per-span length sums (OP_COUNT), scan, then placement through a shared-memory window (OP_WRITE).
+
+// offset(24) | length(8) of what the real match at tile position p prints
 template <int TAB>
+__device__ __forceinline__ uint32_t match_entry(const MatchArgs &a, const MatchTables &T, const uint8_t *s_in, uint32_t p) {
+    uint32_t lo = T.row0_s[s_in[p]], i = 1;
+    uint32_t from = 0, by = s_in[p];
+    while (!(lo & DSA_E_DECIDED)) {
+        const uint32_t c = s_in[p + i];
+        const uint32_t nx = next_entry<TAB>(T, lo & 0xFFFFFFu, c);
+        if ((nx & 0xFFFFFFu) == DSA_DEAD) break;
+        from = lo & 0xFFFFFFu; by = c;
+        lo = nx; ++i;
+        if (i >= 16) break;
+    }
+    const uint32_t slot = (lo & DSA_E_DECIDED) ? from * T.n_classes + T.classmap_s[by]
+                                               : a.P.n_states * T.n_classes + (lo & 0xFFFFFFu);
+    return __ldg(a.P.eout + slot);
+}
+
+// positions of this lane covered by a match (its own real ones or the one hanging in from before)
+__device__ __forceinline__ uint32_t covered_mask(const Front &f) {
+    uint32_t cov = (1u << f.e_in) - 1u;
+    uint32_t r = f.real;
+    while (r) {
+        const uint32_t j = __ffs(r) - 1;
+        r &= r - 1;
+        const uint32_t m = 1 + ((uint32_t)(f.lens >> (4 * j)) & 15u);
+        cov |= ((1u << m) - 1u) << j;
+    }
+    return cov & 0xFFFFu;
+}
+
+struct VarWarp {
+    uint8_t *s_in; uint32_t *s_count; uint32_t *s_ent; uint8_t *s_win;   // s_ent: tile position, then its entry
+};
+
+// hand the lane's real matches to the warp: list slots [slot0, slot0 + popc(real)), ascending position
+__device__ __forceinline__ uint32_t publish_matches(const Front &f, const VarWarp &W, uint32_t lane) {
+    uint32_t real = f.real;
+    const uint32_t slot0 = real ? atomicAdd(W.s_count, (uint32_t)__popc(real)) : 0u;
+    uint32_t slot = slot0;
+    while (real) {
+        const uint32_t j = __ffs(real) - 1;
+        real &= real - 1;
+        W.s_ent[slot++] = lane * 16 + j;
+    }
+    return slot0;
+}
+
+template <bool ACTIVE, int TAB>
+__device__ __forceinline__ void var_count_tile(const MatchArgs &a, const MatchTables &T, const VarWarp &W, size_t base, uint4 x,
+                                               uint4 halo_in, uint32_t lane, uint32_t first_valid, uint32_t &carry_e,
+                                               uint32_t &nul_acc, unsigned long long &span_sum) {
+    *reinterpret_cast<uint4 *>(W.s_in + lane * 16) = x;
+    if (lane == 0) { *reinterpret_cast<uint4 *>(W.s_in + kTile) = halo_in; *W.s_count = 0; }
+    nul_acc |= ((x.x - 0x01010101u) & ~x.x) | ((x.y - 0x01010101u) & ~x.y) | ((x.z - 0x01010101u) & ~x.z) | ((x.w - 0x01010101u) & ~x.w);
+    const Front f = tile_frontend<TAB>(T, W.s_in, x, lane, first_valid, carry_e);
+    carry_e = __shfl_sync(0xFFFFFFFFu, f.e_out, 31);
+    if (ACTIVE) {
+        const size_t my = base + (size_t)lane * 16;
+        const uint32_t vmask = my + 16 <= a.n ? 0xFFFFu : (my < a.n ? (1u << (a.n - my)) - 1u : 0u);
+        uint32_t mine = __popc(~covered_mask(f) & vmask);            // raw bytes
+        publish_matches(f, W, lane);
+        __syncwarp();
+        const uint32_t total = *W.s_count;
+        for (uint32_t q = lane; q < total; q += 32) mine += match_entry<TAB>(a, T, W.s_in, W.s_ent[q]) >> 24;
+#pragma unroll
+        for (int d = 16; d; d >>= 1) mine += __shfl_xor_sync(0xFFFFFFFFu, mine, d);
+        span_sum += mine;
+    }
+    __syncwarp();
+}
+
+// the warp's output window: s_win[0] is the 16-byte aligned output address out + gpos; the first `foreign`
+// bytes belong to the previous span and are never stored (same scheme as k_bmv_write)
+struct OutWindow {
+    unsigned long long gpos;
+    uint32_t fill, foreign;
+};
+
+template <bool ACTIVE, int TAB>
+__device__ __forceinline__ void var_write_tile(const MatchArgs &a, const MatchTables &T, const VarWarp &W, size_t base, uint4 x,
+                                               uint4 halo_in, uint32_t lane, uint32_t first_valid, uint32_t &carry_e,
+                                               OutWindow &ow) {
+    *reinterpret_cast<uint4 *>(W.s_in + lane * 16) = x;
+    if (lane == 0) { *reinterpret_cast<uint4 *>(W.s_in + kTile) = halo_in; *W.s_count = 0; }
+    const Front f = tile_frontend<TAB>(T, W.s_in, x, lane, first_valid, carry_e);
+    carry_e = __shfl_sync(0xFFFFFFFFu, f.e_out, 31);
+    if (!ACTIVE) { __syncwarp(); return; }
+    const uint32_t slot0 = publish_matches(f, W, lane);
+    __syncwarp();
+    {
+        const uint32_t total = *W.s_count;
+        for (uint32_t q = lane; q < total; q += 32) W.s_ent[q] = match_entry<TAB>(a, T, W.s_in, W.s_ent[q]);
+    }
+    __syncwarp();
+    // lengths of this lane's 16 positions
+    const size_t my = base + (size_t)lane * 16;
+    const uint32_t vmask = my + 16 <= a.n ? 0xFFFFu : (my < a.n ? (1u << (a.n - my)) - 1u : 0u);
+    const uint32_t rawmask = ~covered_mask(f) & vmask;
+    uint32_t mine = __popc(rawmask);
+    {
+        const uint32_t nreal = __popc(f.real);
+        for (uint32_t k = 0; k < nreal; ++k) mine += W.s_ent[slot0 + k] >> 24;
+    }
+    uint32_t incl = mine;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+        const uint32_t y = __shfl_up_sync(0xFFFFFFFFu, incl, d);
+        if (lane >= (uint32_t)d) incl += y;
+    }
+    const uint32_t tile_total = __shfl_sync(0xFFFFFFFFu, incl, 31);
+    const uint32_t w[4] = {x.x, x.y, x.z, x.w};
+    const bool fits = ow.fill + tile_total <= (uint32_t)kVarWindow + 16;
+    if (!fits) {                                                      // flush what is pending, then store directly
+        for (uint32_t k = ow.foreign + lane; k < ow.fill; k += 32) a.out[ow.gpos + k] = W.s_win[k];
+    }
+    // place: positions in order; matches come in ascending position, like their list slots
+    {
+        uint32_t at = ow.fill + incl - mine, k = 0;
+        uint8_t *dst = fits ? W.s_win : a.out + ow.gpos;
+#pragma unroll
+        for (int j = 0; j < 16; ++j) {
+            if (f.real & (1u << j)) {
+                const uint32_t ent = W.s_ent[slot0 + k++];
+                const uint8_t *src = T.pool + (ent & 0xFFFFFFu);
+                const uint32_t len = ent >> 24;
+                for (uint32_t q = 0; q < len; ++q) dst[at + q] = src[q];
+                at += len;
+            } else if (rawmask & (1u << j)) {
+                dst[at++] = (uint8_t)(w[j >> 2] >> ((j & 3) * 8));
+            }
+        }
+    }
+    if (fits) {
+        ow.fill += tile_total;
+        __syncwarp();
+        const uint32_t nvec = ow.fill / 16;
+        for (uint32_t v = lane; v < nvec; v += 32) {
+            const uint4 y = *reinterpret_cast<const uint4 *>(W.s_win + v * 16);
+            if (v == 0 && ow.foreign) {
+                const uint32_t yy[4] = {y.x, y.y, y.z, y.w};
+                for (uint32_t k = ow.foreign; k < 16; ++k) a.out[ow.gpos + k] = (uint8_t)(yy[k >> 2] >> ((k & 3) * 8));
+            } else {
+                *reinterpret_cast<uint4 *>(a.out + ow.gpos + (size_t)v * 16) = y;
+            }
+        }
+        const uint32_t rest = ow.fill - nvec * 16;
+        uint8_t keep = 0;
+        if (lane < rest) keep = W.s_win[nvec * 16 + lane];
+        __syncwarp();
+        if (nvec) {
+            if (lane < rest) W.s_win[lane] = keep;
+            ow.gpos += (unsigned long long)nvec * 16;
+            ow.fill = rest;
+            ow.foreign = 0;
+        }
+    } else {
+        const unsigned long long end = ow.gpos + ow.fill + tile_total;
+        ow.foreign = (uint32_t)((reinterpret_cast<uintptr_t>(a.out) + end) & 15);
+        ow.gpos = end - ow.foreign;
+        ow.fill = ow.foreign;
+    }
+    __syncwarp();
+}
+
+template <int TAB, int OP>
 __global__ void __launch_bounds__(kMatchThreads)
 k_match(MatchArgs a) {
     extern __shared__ __align__(16) uint8_t smem[];
@@ -265,7 +463,7 @@ k_match(MatchArgs a) {
     uint32_t *ctrans_s = reinterpret_cast<uint32_t *>(cur);
     const uint32_t ct_words = TAB == TAB_WIDE ? a.P.n_states * 256u : a.smem_states * a.P.n_classes;
     cur += ((ct_words + 3) & ~3u) * 4;
-    uint8_t *warp_base = cur + warp * kWarpSmem;
+    uint8_t *warp_base = cur + warp * (OP == OP_INPLACE ? kWarpSmem : kVarWarpSmem);
 
     if (live_s)
         for (uint32_t k = threadIdx.x; k < 256u * 32u; k += blockDim.x)
@@ -289,6 +487,18 @@ k_match(MatchArgs a) {
     uint8_t *s_in = warp_base, *s_out = warp_base + 544;
     uint16_t *s_list = reinterpret_cast<uint16_t *>(warp_base + 1088);
     uint32_t *s_count = reinterpret_cast<uint32_t *>(warp_base + 1088 + 1024);
+    VarWarp W;                                                    // layout of the variable-length forms
+    W.s_in = warp_base;
+    W.s_count = reinterpret_cast<uint32_t *>(warp_base + 544);
+    W.s_ent = reinterpret_cast<uint32_t *>(warp_base + 544 + 16);
+    W.s_win = warp_base + 544 + 16 + 2048;
+    if (OP == OP_WRITE) {
+        if (*a.status & ST_IRREGULAR) return;                      // the count pass saw a NUL / no final newline / long line
+        if (*a.total > a.out_cap) {
+            if (threadIdx.x == 0 && blockIdx.x == 0) atomicOr(a.status, ST_NOSPACE);
+            return;
+        }
+    }
     const size_t n = a.n;
     const size_t n_tiles = (n + kTile - 1) / kTile;
     const size_t gwarp = (size_t)blockIdx.x * kMatchWarps + warp;
@@ -296,9 +506,19 @@ k_match(MatchArgs a) {
     size_t t1 = t0 + a.tiles_per_warp;
     if (t1 > n_tiles) t1 = n_tiles;
     uint32_t status = 0, nul_acc = 0;
+    if (OP == OP_COUNT && t0 >= t1 && lane == 0) a.gsum[gwarp] = 0;   // the scan runs over every warp of the grid
     if (t0 < t1) {
         uint32_t carry_e = 0;
         uint4 carry_halo = make_uint4(0, 0, 0, 0);
+        unsigned long long span_sum = 0;
+        OutWindow ow;
+        ow.gpos = 0; ow.fill = 0; ow.foreign = 0;
+        if (OP == OP_WRITE) {
+            const unsigned long long span_off = a.gsum[gwarp];
+            ow.foreign = (uint32_t)((reinterpret_cast<uintptr_t>(a.out) + span_off) & 15);
+            ow.gpos = span_off - ow.foreign;
+            ow.fill = ow.foreign;
+        }
         // ---- warm-up: the chain state at t0 is only known from the last '\n' before it -------------
         size_t tw = t0;
         uint32_t first_valid = 0;
@@ -333,10 +553,22 @@ k_match(MatchArgs a) {
             uint4 halo_in = load_padded(a.in, base + kTile, n);
             uint4 x_next = make_uint4(0x0A0A0A0Au, 0x0A0A0A0Au, 0x0A0A0A0Au, 0x0A0A0A0Au);
             if (t + 1 < t1) x_next = load_padded(a.in, base + kTile + lane * 16, n);   // prefetch
-            if (t < t0) match_tile<false, TAB>(a, T, s_in, s_out, s_list, s_count, base, x, halo_in, lane, first_valid, carry_e, carry_halo, nul_acc, status);
-            else        match_tile<true, TAB>(a, T, s_in, s_out, s_list, s_count, base, x, halo_in, lane, first_valid, carry_e, carry_halo, nul_acc, status);
+            if (OP == OP_INPLACE) {
+                if (t < t0) match_tile<false, TAB>(a, T, s_in, s_out, s_list, s_count, base, x, halo_in, lane, first_valid, carry_e, carry_halo, nul_acc, status);
+                else        match_tile<true, TAB>(a, T, s_in, s_out, s_list, s_count, base, x, halo_in, lane, first_valid, carry_e, carry_halo, nul_acc, status);
+            } else if (OP == OP_COUNT) {
+                if (t < t0) var_count_tile<false, TAB>(a, T, W, base, x, halo_in, lane, first_valid, carry_e, nul_acc, span_sum);
+                else        var_count_tile<true, TAB>(a, T, W, base, x, halo_in, lane, first_valid, carry_e, nul_acc, span_sum);
+            } else {
+                if (t < t0) var_write_tile<false, TAB>(a, T, W, base, x, halo_in, lane, first_valid, carry_e, ow);
+                else        var_write_tile<true, TAB>(a, T, W, base, x, halo_in, lane, first_valid, carry_e, ow);
+            }
             first_valid = 0;
             x = x_next;
+        }
+        if (OP == OP_COUNT && lane == 0) a.gsum[gwarp] = span_sum;
+        if (OP == OP_WRITE) {
+            for (uint32_t k = ow.foreign + lane; k < ow.fill; k += 32) a.out[ow.gpos + k] = W.s_win[k];   // the span's last < 16 bytes
         }
     }
     if (nul_acc & 0x80808080u) status |= ST_IRREGULAR;
