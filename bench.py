@@ -433,16 +433,10 @@ def main():
                 traffic = json.load(f).get("dram_bytes_per_launch")
         except Exception:
             pass
-    if info["exec_kind"] == T.EXEC_BYTEMAP:
-        kernel = "k_bytemap"
-    elif info["exec_kind"] == T.EXEC_BACKTRACK:
-        kernel = "k_lines<dfs> (count, scan, write)"
-    elif info["length_preserving"] and info["max_depth"] <= 16 and not info["can_match_empty"]:
-        kernel = "k_match"
-    elif info["length_preserving"]:
-        kernel = "k_lines<inplace>"
-    else:
-        kernel = "k_lines_s<count> + k_scan_groups + k_lines_s<write>"
+    kernel = {0: "k_lines_s<count> + k_scan_groups + k_lines_s<write>" if info["exec_kind"] != T.EXEC_BACKTRACK
+                 else "k_lines<dfs> count + k_scan_groups + k_lines<dfs> write",
+              1: "k_bytemap", 2: "k_match", 3: "k_bmv_count + k_scan_groups + k_bmv_write",
+              4: "k_match<count> + k_scan_groups + k_match<write>", 5: "k_lines<inplace>"}[info["fast_path"]]
     line = {
         "metric": METRIC, "value": value, "unit": "GB/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,

@@ -60,6 +60,17 @@ enum {
     TRRE_EXEC_BACKTRACK = 2    /* NFT flavour only: per-line priority DFS over the flat NFT                  */
 };
 
+/* the kernel family that serves a regular buffer (no NUL byte, final newline); irregular buffers and
+ * everything else run the per-line kernels */
+enum {
+    TRRE_FAST_NONE      = 0,   /* per-line kernels only (cycles, empty matches, DFS executor)                */
+    TRRE_FAST_BYTEMAP   = 1,   /* k_bytemap: one byte in, one byte out                                       */
+    TRRE_FAST_MATCH     = 2,   /* k_match: length-preserving acyclic program, attempts <= 16 bytes           */
+    TRRE_FAST_BYTEMAP_VAR = 3, /* k_bmv_*: one byte in, 0..255 bytes out                                     */
+    TRRE_FAST_MATCH_VAR = 4,   /* k_match count/write: acyclic program, matches of any output length         */
+    TRRE_FAST_INPLACE   = 5    /* k_lines in place: other length-preserving programs                         */
+};
+
 typedef struct trre_prog trre_prog;
 
 typedef struct trre_prog_info {
@@ -73,6 +84,7 @@ typedef struct trre_prog_info {
     uint32_t length_preserving;  /* 1: every match emits exactly as many bytes as it consumes                */
     uint32_t can_match_empty;    /* 1: an attempt can succeed without consuming                              */
     uint32_t table_bytes;        /* size of the device-resident tables                                       */
+    uint32_t fast_path;          /* TRRE_FAST_*: which position-parallel kernel serves a regular buffer      */
 } trre_prog_info;
 
 /* ---- host side: pattern -> program (no GPU needed) ------------------------------------------- */

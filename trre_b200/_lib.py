@@ -4,6 +4,7 @@ import os
 
 FLAVOR_NFT, FLAVOR_DFT = 0, 1
 EXEC_BYTEMAP, EXEC_TABLE, EXEC_BACKTRACK = 0, 1, 2
+FAST_NONE, FAST_BYTEMAP, FAST_MATCH, FAST_BYTEMAP_VAR, FAST_MATCH_VAR, FAST_INPLACE = 0, 1, 2, 3, 4, 5
 
 OK, E_PATTERN, E_UNSUPPORTED, E_CUDA, E_NOSPACE, E_STACK, E_ARG, E_ASSERT = 0, 1, 2, 3, 4, 5, 7, 134
 
@@ -26,7 +27,7 @@ class TrreError(RuntimeError):
 class _Info(ctypes.Structure):
     _fields_ = [(n, ctypes.c_uint32) for n in (
         "abi_version", "flavor", "exec_kind", "nft_states", "dsa_states", "byte_classes",
-        "max_depth", "length_preserving", "can_match_empty", "table_bytes")]
+        "max_depth", "length_preserving", "can_match_empty", "table_bytes", "fast_path")]
 
 
 _L = None

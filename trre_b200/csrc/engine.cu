@@ -634,6 +634,12 @@ int trre_prog_get_info(const trre_prog *p, trre_prog_info *info) {
     info->length_preserving = (h.flags & PF_LENGTH_PRESERVING) ? 1 : 0;
     info->can_match_empty = (h.flags & PF_CAN_MATCH_EMPTY) ? 1 : 0;
     info->table_bytes = h.total_bytes;
+    info->fast_path = h.exec_kind == TRRE_EXEC_BYTEMAP    ? TRRE_FAST_BYTEMAP
+                      : (h.flags & PF_MATCHABLE)        ? TRRE_FAST_MATCH
+                      : (h.flags & PF_BYTEMAP_VAR)      ? TRRE_FAST_BYTEMAP_VAR
+                      : (h.flags & PF_MATCHABLE_VAR)    ? TRRE_FAST_MATCH_VAR
+                      : ((h.flags & PF_LENGTH_PRESERVING) && h.exec_kind == TRRE_EXEC_TABLE) ? TRRE_FAST_INPLACE
+                                                        : TRRE_FAST_NONE;
     return TRRE_OK;
 }
 
