@@ -56,6 +56,7 @@ def dictionary_words(k=10000, seed=7):
 _DICT = dictionary_words()
 WORKLOADS["cfg5"] = ("|".join("%s:%s" % (w, w.upper()) for w in _DICT), 1, 8 * GiB, _DICT, 0.30, True, 0x72726505, "trre_dft")
 WORKLOADS["del"] = ("a:", 0, 1 * GiB, None, 0.0, False, 0x72726506, "trre")
+WORKLOADS["num"] = ("[0-9]+:#", 0, 1 * GiB, None, 0.0, False, 0x72726508, "trre")
 WORKLOADS["sub"] = ("cat:mouse|dog:d", 0, 1 * GiB, ["cat", "dog", "catdog", "dogcat", "ca", "do", "cot", "dig"], 0.25, False, 0x72726507, "trre")
 
 DESCR = {
@@ -64,6 +65,7 @@ DESCR = {
     "cfg3": "'(cat:dog|dog:cat)' over 8 GiB synthetic text per GPU, NFT flavour (BASELINE configs[2])",
     "cfg4": "Caesar '[a:b-y:zz:a]' over 8 GiB synthetic ASCII per GPU, DFT flavour (BASELINE configs[3], 64 GiB at 8 GPUs)",
     "cfg5": "10k-alternation word:WORD dictionary (18 402-state DFT) over 8 GiB synthetic lowercase text per GPU, DFT flavour (BASELINE configs[4])",
+    "num": "'[0-9]+:#' (collapse digit runs: cyclic automaton, per-line kernels) over 1 GiB synthetic ASCII, NFT flavour",
     "sub": "'cat:mouse|dog:d' (matches print more / fewer bytes than they consume) over 1 GiB synthetic text, NFT flavour",
     "del": "'a:' (delete every a; NOT length preserving: count + scan + write path) over 1 GiB synthetic ASCII, NFT flavour",
 }

@@ -303,7 +303,7 @@ int launch_general(const trre_prog *p, DeviceState *d, const uint8_t *d_in, size
         sa.L = a;
         sa.smem_states = (uint32_t)rows;
         const size_t ct = ((rows * d->P.n_classes + 3) & ~(size_t)3) * 4;
-        smem_count = 256 + 1024 + ct + kGroupBytes + 16;
+        smem_count = 256 + 1024 + ct + kGroupBytes + 16 + kGroupBytes / 8;
         smem_write = smem_count + kStageOut + 16;
         if (!d->staged_attr) {
             CUDA_TRY(cudaFuncSetAttribute(k_lines_s<MODE_COUNT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_count));

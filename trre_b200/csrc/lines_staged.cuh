@@ -29,6 +29,7 @@ struct StagedView {
     uint32_t tile_len;
     uint32_t lim_rel, n_rel;     // end of payload bytes / end of buffer, relative (clamped to 0xFFFFFFF0)
     const uint32_t *row0_s;      // first transition by raw byte
+    const uint32_t *s_mark;      // bit per staged byte: 1 = terminator (NUL, newline) or a byte an attempt can start with
     const uint8_t *classmap_s;
     const uint32_t *ctrans_s;
     const uint32_t *ctrans_g;
@@ -51,6 +52,12 @@ struct StagedSink {
         if (s_out) s_out[n] = b;
         else if (g_out) g_out[n] = b;
         ++n;
+    }
+    // a run of bytes no attempt can start with: copied verbatim (shared memory source)
+    __device__ __forceinline__ void put_run(const uint8_t *src, uint32_t len) {
+        if (s_out) { for (uint32_t k = 0; k < len; ++k) s_out[n + k] = src[k]; }
+        else if (g_out) { for (uint32_t k = 0; k < len; ++k) g_out[n + k] = src[k]; }
+        n += len;
     }
     __device__ __forceinline__ void put_ref(const uint8_t *pool, uint32_t hi) {
         uint32_t len = hi >> 24, off = hi & 0xFFFFFFu;
@@ -91,7 +98,21 @@ __device__ __forceinline__ int attempt_tail(const DevProg &P, const StagedView &
 __device__ __forceinline__ uint32_t run_record_staged(const DevProg &P, const StagedView &V, uint32_t p,
                                                       StagedSink &o, uint32_t &status) {
     const bool start_accepts = (P.start_info & DSA_S_HAS_FINAL) != 0;   // an attempt can succeed without consuming
+    const bool can_skip = (P.start_info & (DSA_S_HAS_FINAL | DSA_S_DIVERGE)) == 0;
     for (;;) {
+        if (can_skip && p < V.tile_len) {
+            // every attempt between here and the next marked byte fails on its first byte: one raw run
+            uint32_t q = p, word = V.s_mark[p >> 5] >> (p & 31);
+            if (word) q = p + (uint32_t)__ffs(word) - 1;
+            else {
+                q = (p | 31u) + 1;
+                while (q < V.tile_len && V.s_mark[q >> 5] == 0) q += 32;
+                if (q < V.tile_len) q += (uint32_t)__ffs(V.s_mark[q >> 5]) - 1;
+            }
+            if (q > V.tile_len) q = V.tile_len;
+            if (q > V.lim_rel) q = V.lim_rel;                         // never past the payload
+            if (q > p) { o.put_run(V.s_in + p, q - p); p = q; }
+        }
         uint8_t c = '\n';
         if (p < V.lim_rel) c = V.at(p);
         const bool at_end = (c == 0 || c == '\n');
@@ -132,7 +153,8 @@ k_lines_s(StagedArgs sa) {
     uint32_t *ctrans_s = row0_s + 256;
     const uint32_t ct_words = sa.smem_states * a.P.n_classes;
     uint8_t *s_in = reinterpret_cast<uint8_t *>(ctrans_s + ((ct_words + 3) & ~3u));
-    uint8_t *s_out = s_in + kGroupBytes + 16;
+    uint32_t *s_mark = reinterpret_cast<uint32_t *>(s_in + kGroupBytes + 16);     // kGroupBytes / 32 words
+    uint8_t *s_out = reinterpret_cast<uint8_t *>(s_mark + kGroupBytes / 32);
 
     const uint8_t *__restrict__ in = a.in;
     const size_t n = a.n;
@@ -162,6 +184,32 @@ k_lines_s(StagedArgs sa) {
         } else {
             for (size_t k = threadIdx.x; k < tile_len; k += blockDim.x) s_in[k] = __ldg(in + tile_beg + k);
         }
+        __syncthreads();
+        // ---- mark the bytes where the record loop has something to decide: terminators and bytes whose first
+        // transition is alive; the runs in between are copied verbatim without an attempt per byte
+        {
+            const uint32_t cb = threadIdx.x * kChunk;                 // this thread's 128 bytes = 4 mark words
+#pragma unroll
+            for (int wd = 0; wd < kChunk / 32; ++wd) {
+                uint32_t bits = 0;
+                const uint32_t b0 = cb + wd * 32;
+                if (b0 < tile_len) {
+#pragma unroll
+                    for (int v = 0; v < 2; ++v) {
+                        const uint4 y = *reinterpret_cast<const uint4 *>(s_in + b0 + v * 16);
+                        const uint32_t ww[4] = {y.x, y.y, y.z, y.w};
+#pragma unroll
+                        for (int j = 0; j < 16; ++j) {
+                            const uint32_t c = (ww[j >> 2] >> ((j & 3) * 8)) & 0xFFu;
+                            const uint32_t hot = (c == 0u || c == '\n' || (row0_s[c] & 0xFFFFFFu) != DSA_DEAD) ? 1u : 0u;
+                            bits |= hot << (v * 16 + j);
+                        }
+                    }
+                    if (b0 + 32 > tile_len) bits |= ~0u << (tile_len - b0);   // bytes beyond the tile: decide one by one
+                }
+                s_mark[(cb >> 5) + wd] = bits;
+            }
+        }
         const size_t chunk = g * kLineThreads + threadIdx.x;
         unsigned long long my_off = 0;
         if (MODE == MODE_WRITE) {
@@ -189,7 +237,7 @@ k_lines_s(StagedArgs sa) {
             V.n_rel = (uint32_t)(nr < cap ? nr : cap);
             if (nr >= cap) status |= 0;                               // (a single record cannot span 4 GB: see ST_NOSPACE below)
         }
-        V.row0_s = row0_s; V.classmap_s = classmap_s; V.ctrans_s = ctrans_s; V.ctrans_g = a.P.ctrans;
+        V.row0_s = row0_s; V.s_mark = s_mark; V.classmap_s = classmap_s; V.ctrans_s = ctrans_s; V.ctrans_g = a.P.ctrans;
         V.smem_states = sa.smem_states; V.n_classes = a.P.n_classes;
         StagedSink o;
         o.g_out = nullptr; o.s_out = nullptr;
