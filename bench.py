@@ -397,6 +397,46 @@ def main():
             ok = ok and bool(torch.equal(d_out[:tile_n], d_out[r * tile_n:(r + 1) * tile_n]))
         verified = ok
 
+    # ---- N > 1: the final gather of the output shards to rank 0 over NVLink, timed on its own (it is
+    # NVLink-bound, 7 x shard / ~770 GB/s into one GPU, and would hide the scan if it sat inside the clock)
+    gather = None
+    if world > 1:
+        offs = [0]
+        for sz in sizes_all[:-1]:
+            offs.append(offs[-1] + sz)
+        total_out = offs[-1] + sizes_all[-1]
+        full = torch.empty(total_out if rank == 0 else 1, dtype=torch.uint8, device=dev)
+
+        def do_gather():
+            ops = []
+            if rank == 0:
+                full[:out_n].copy_(d_out[:out_n])
+                for r in range(1, world):
+                    ops.append(dist.P2POp(dist.irecv, full[offs[r]:offs[r] + sizes_all[r]], r))
+            else:
+                ops.append(dist.P2POp(dist.isend, d_out[:out_n], 0))
+            for w in dist.batch_isend_irecv(ops):
+                w.wait()
+
+        do_gather()                                   # warm-up (NCCL channel setup)
+        barrier()
+        g0, g1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        g0.record(stream)
+        do_gather()
+        g1.record(stream)
+        torch.cuda.synchronize()
+        gt = torch.tensor([g0.elapsed_time(g1)], dtype=torch.float64, device=dev)
+        dist.all_reduce(gt, op=dist.ReduceOp.MAX)
+        gms = float(gt.item())
+        moved = total_out - sizes_all[0]
+        gather = {"ms": gms, "bytes_into_rank0": moved, "GB/s_into_rank0": moved / (gms * 1e-3) / 1e9,
+                  "note": "NCCL point-to-point over NVLink 5 / NVSwitch, not part of value; measured peer-copy reference 770 GB/s"}
+        if rank == 0 and info["fast_path"] == 1:
+            lut_g = torch.frombuffer(bytearray(prog.bytemap()), dtype=torch.uint8).to(dev)
+            gather["first_shard_verified"] = bool(torch.equal(full[:out_n], lut_g[d_in.long()][:out_n]))
+            del lut_g
+        del full
+
     # ---- end to end through the C ABI with host buffers (H2D + kernels + D2H inside the clock) -------------
     e2e = None
     if args.e2e_steps > 0:
@@ -457,6 +497,7 @@ def main():
                      "torch_copy_same_size_gbs": copy_gbs},
         "verified": verified,
         "output_bytes_per_rank": sizes_all,
+        "gather": gather,
     }
     if world == 1 and not args.no_cpu_baseline:
         line["cpu_baseline"] = cpu_baseline(T, spec)
