@@ -154,3 +154,19 @@ def test_blob_round_trip_is_what_gets_broadcast():
         T.from_blob(p.blob()[:-8])
     with pytest.raises(T.TrreError):
         T.from_blob(b"\0" * 200)
+
+
+def test_fast_path_classification():
+    """Which kernel family serves a regular buffer (trre_prog_info.fast_path) - decided on the host."""
+    F = {"none": 0, "bytemap": 1, "match": 2, "bytemap_var": 3, "match_var": 4, "inplace": 5}
+    cases = [
+        ("[a:A-z:Z]", DFT, "bytemap"), ("[a:A-z:Z]", NFT, "bytemap"), ("[a:b-y:zz:a]", DFT, "bytemap"),
+        ("a+:x", DFT, "bytemap"),                       # shortest match: every a -> x
+        ("cat:dog", NFT, "match"), ("(cat:dog|dog:cat)", NFT, "match"), ("(cat:dog|dog:cat)", DFT, "match"),
+        ("a:", NFT, "bytemap_var"), ("a:xy", DFT, "bytemap_var"), ("[a-c]:|d:DD", NFT, "bytemap_var"),
+        ("cat:mouse", NFT, "match_var"), ("(cat):", DFT, "match_var"), ("ab:X|abc:Y|a:Z", NFT, "match_var"),
+        ("(a:b)+", NFT, "inplace"),                     # length preserving but cyclic
+        ("a+:x", NFT, "none"), (":=", NFT, "none"), ("(a:x)*b|a", NFT, "none"), ("[0-9]+:#", NFT, "none"),
+    ]
+    for expr, flavor, want in cases:
+        assert T.compile(expr, flavor).info["fast_path"] == F[want], (expr, flavor, want)
