@@ -308,3 +308,31 @@ def test_variable_length_dictionary_and_device_api():
         n = prog.scan_device(d_in.data_ptr(), d_in.numel(), d_out.data_ptr(), d_out.numel(),
                              stream=torch.cuda.current_stream().cuda_stream)
         assert n == len(want) and bytes(d_out[:n].cpu().numpy().tobytes()) == want, shift
+
+
+@pytest.mark.parametrize("seed", range(4))
+def test_random_patterns_on_inputs_that_span_many_tiles(seed):
+    """Random expressions whose program gets a position-parallel kernel, on inputs large enough to cross tiles,
+    warp spans and CTAs (the small-input tests above never leave one tile)."""
+    rng = random.Random(7000 + seed)
+    seen = {}
+    tried = 0
+    while tried < 400 and sum(seen.values()) < 24:
+        tried += 1
+        pat = rand_expr(rng, 2)
+        for flavor in (NFT, DFT):
+            try:
+                prog = T.compile(pat, flavor)
+            except T.TrreError:
+                continue
+            fp = prog.info["fast_path"]
+            if fp not in (2, 3, 4, 5) or seen.get(fp, 0) >= 8:
+                continue
+            data = _ab_text(rng.randrange(1 << 30), 200000, b"abcd ", 0, rng.choice([8, 60, 400]))
+            rc, want, _ = oracle_run(pat.encode(), data, flavor=flavor)
+            if rc != 0:
+                continue
+            seen[fp] = seen.get(fp, 0) + 1
+            got = prog.scan(data)
+            assert got == want, (pat, flavor, fp, prog.info)
+    assert sum(seen.values()) >= 8, seen
