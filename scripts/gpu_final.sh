@@ -9,7 +9,7 @@ ncu --metrics gpu__time_duration.sum --clock-control none -c 80 --csv --log-file
     python bench.py --steps 5 --warmup 3 --no-cpu-baseline --e2e-steps 0 > /dev/null 2>&1
 ncu --set full --clock-control none --import-source on -k regex:k_bytemap -s 3 -c 1 -o gpurun_out/prof_$TAG -f \
     python bench.py --steps 2 --warmup 3 --no-cpu-baseline --e2e-steps 0 > /dev/null 2>&1
-for w in cfg1 cfg3 cfg5 del cfg4; do
+for w in cfg1 cfg3 cfg5 del sub num cfg4; do
   python bench.py --workload $w --bytes 1073741824 --steps 5 --warmup 3 --no-cpu-baseline --e2e-steps 1 2>/dev/null | tail -1 > gpurun_out/bench_${w}_$TAG.json
   python -c "
 import json,sys
