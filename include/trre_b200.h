@@ -113,6 +113,13 @@ int  trre_scan(const trre_prog *p, int device,
 int  trre_scan_into(const trre_prog *p, int device,
                     const uint8_t *in, size_t n, uint8_t *out, size_t out_cap, size_t *out_n);
 
+/* trre_scan over `ndev` GPUs of one box: the buffer is cut at line boundaries (trre_shard_lines), shard k is
+ * scanned on devices[k] (one host thread per device, each with its own H2D / kernels / D2H pipeline), the
+ * outputs are concatenated in shard order - byte-identical to the single-GPU result because lines are
+ * independent (trre_nft.c:778-781).  The CLI uses it when TRRE_GPUS=N is set. */
+int  trre_scan_multi(const trre_prog *p, const int *devices, int ndev,
+                     const uint8_t *in, size_t n, uint8_t **out, size_t *out_n);
+
 /* Device-resident scan: d_in/d_out are device pointers on `device`; work is enqueued on `stream`
  * (a cudaStream_t).  If out_n != NULL the call synchronises the stream and returns the output size
  * and status; if out_n == NULL it only enqueues: the result is complete, and its size/status known,

@@ -49,3 +49,18 @@ def test_cli_match_flags_stay_on_the_host():
     assert r.stdout == b"xxx\nxxa\nxaa\naaa\n"
     r = subprocess.run([BIN[NFT], "-a", "a:x|a:y"], input=b"ab\n", capture_output=True)
     assert r.stdout == b"xyab\n"                                  # -a in scan mode
+
+
+def test_multi_gpu_scan_equals_single(monkeypatch):
+    torch = pytest.importorskip("torch")
+    ndev = torch.cuda.device_count()
+    if ndev < 2:
+        pytest.skip("needs 2 GPUs")
+    data = bytes(T.synth_text(5, 8 << 20, ["cat", "dog"], 0.25))
+    for expr, flavor in (("(cat:dog|dog:cat)", NFT), ("a:", NFT), ("[a:A-z:Z]", DFT), ("a+:x", NFT)):
+        prog = T.compile(expr, flavor)
+        assert prog.scan_multi(data, list(range(min(ndev, 4)))) == prog.scan(data), expr
+    monkeypatch.setenv("TRRE_GPUS", "2")
+    r = subprocess.run([BIN[NFT], "cat:dog"], input=data, capture_output=True)
+    monkeypatch.delenv("TRRE_GPUS")
+    assert r.returncode == 0 and r.stdout == T.compile("cat:dog", NFT).scan(data)

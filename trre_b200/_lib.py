@@ -57,6 +57,8 @@ def _lib():
     L.trre_prog_bytemap.argtypes = [vp, ctypes.c_char_p]
     L.trre_scan.restype = ctypes.c_int
     L.trre_scan.argtypes = [vp, ctypes.c_int, u8p, sz, ctypes.POINTER(vp), ctypes.POINTER(sz)]
+    L.trre_scan_multi.restype = ctypes.c_int
+    L.trre_scan_multi.argtypes = [vp, ctypes.POINTER(ctypes.c_int), ctypes.c_int, u8p, sz, ctypes.POINTER(vp), ctypes.POINTER(sz)]
     L.trre_scan_into.restype = ctypes.c_int
     L.trre_scan_into.argtypes = [vp, ctypes.c_int, u8p, sz, u8p, sz, ctypes.POINTER(sz)]
     L.trre_scan_device.restype = ctypes.c_int
@@ -159,6 +161,18 @@ class Program:
         addr, n, keep = _as_buffer(data)
         out, out_n = ctypes.c_void_p(), ctypes.c_size_t()
         rc = _lib().trre_scan(self._h, device, addr, n, ctypes.byref(out), ctypes.byref(out_n))
+        if rc:
+            raise TrreError(rc, _last_error())
+        res = ctypes.string_at(out, out_n.value) if out.value else b""
+        _lib().trre_free(out)
+        return res
+
+    def scan_multi(self, data, devices) -> bytes:
+        """The buffer cut at line boundaries, shard k on devices[k], outputs joined in order."""
+        addr, n, keep = _as_buffer(data)
+        devs = (ctypes.c_int * len(devices))(*devices)
+        out, out_n = ctypes.c_void_p(), ctypes.c_size_t()
+        rc = _lib().trre_scan_multi(self._h, devs, len(devices), addr, n, ctypes.byref(out), ctypes.byref(out_n))
         if rc:
             raise TrreError(rc, _last_error())
         res = ctypes.string_at(out, out_n.value) if out.value else b""

@@ -2,7 +2,8 @@
 // trre_dft.c:1199-1302): `trre [-d] [-m] [-a] EXPR [FILE]`, stdin when no FILE, same stderr texts and
 // exit codes.  Scan mode hands the WHOLE input to the GPU engine through the C ABI; -m / -a stay on
 // the host (trre_match_host).  Built twice: -DTRRE_CLI_FLAVOR=0 -> bin/trre, =1 -> bin/trre_dft.
-// GPU knobs come from the environment so the argv surface stays the reference's: TRRE_DEVICE (default 0).
+// GPU knobs come from the environment so the argv surface stays the reference's: TRRE_DEVICE (default 0),
+// TRRE_GPUS (default 1: number of devices, starting at TRRE_DEVICE, the lines are sharded over).
 #include <unistd.h>
 
 #include <cstdio>
@@ -88,9 +89,16 @@ int main(int argc, char **argv) {
     uint8_t *out = nullptr;
     size_t out_n = 0;
     if (!match && !all) {
-        int device = 0;
+        int device = 0, gpus = 1;
         if (const char *e = std::getenv("TRRE_DEVICE")) device = std::atoi(e);
-        rc = trre_scan(prog, device, in.data(), in.size(), &out, &out_n);
+        if (const char *e = std::getenv("TRRE_GPUS")) gpus = std::atoi(e);
+        if (gpus > 1) {                                           // lines sharded over TRRE_GPUS devices of this box
+            std::vector<int> devs;
+            for (int k = 0; k < gpus; ++k) devs.push_back(device + k);
+            rc = trre_scan_multi(prog, devs.data(), gpus, in.data(), in.size(), &out, &out_n);
+        } else {
+            rc = trre_scan(prog, device, in.data(), in.size(), &out, &out_n);
+        }
         if (rc != TRRE_OK) {
             const char *msg = trre_last_error();
             std::fputs(msg, stderr);

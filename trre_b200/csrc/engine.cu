@@ -9,6 +9,7 @@
 #include <map>
 #include <mutex>
 #include <string>
+#include <thread>
 #include <vector>
 
 #include "../../include/trre_b200.h"
@@ -753,6 +754,43 @@ int trre_scan(const trre_prog *p, int device, const uint8_t *in, size_t n, uint8
     if (rc != TRRE_OK) { std::free(buf); return rc; }
     *out = buf; *out_n = need;
     return TRRE_OK;
+}
+
+int trre_scan_multi(const trre_prog *p, const int *devices, int ndev, const uint8_t *in, size_t n, uint8_t **out,
+                    size_t *out_n) {
+    if (!p || !devices || ndev < 1 || !out || !out_n || (n && !in)) { g_last_error = "bad argument"; return TRRE_E_ARG; }
+    *out = nullptr; *out_n = 0;
+    if (ndev == 1) return trre_scan(p, devices[0], in, n, out, out_n);
+    std::vector<size_t> cuts((size_t)ndev + 1);
+    int rc = trre_shard_lines(in, n, ndev, cuts.data());
+    if (rc != TRRE_OK) return rc;
+    std::vector<uint8_t *> part((size_t)ndev, nullptr);
+    std::vector<size_t> part_n((size_t)ndev, 0);
+    std::vector<int> part_rc((size_t)ndev, TRRE_OK);
+    std::vector<std::string> part_err((size_t)ndev);
+    std::vector<std::thread> workers;
+    for (int k = 0; k < ndev; ++k)
+        workers.emplace_back([&, k]() {
+            part_rc[k] = trre_scan(p, devices[k], in + cuts[k], cuts[k + 1] - cuts[k], &part[k], &part_n[k]);
+            if (part_rc[k] != TRRE_OK) part_err[k] = trre_last_error();     // thread-local text
+        });
+    for (auto &w : workers) w.join();
+    size_t total = 0;
+    for (int k = 0; k < ndev; ++k) {
+        if (part_rc[k] != TRRE_OK && rc == TRRE_OK) { rc = part_rc[k]; g_last_error = part_err[k]; }
+        total += part_n[k];
+    }
+    if (rc == TRRE_OK) {
+        uint8_t *buf = static_cast<uint8_t *>(std::malloc(total ? total : 1));
+        if (!buf) rc = TRRE_E_ARG;
+        else {
+            size_t off = 0;
+            for (int k = 0; k < ndev; ++k) { if (part_n[k]) std::memcpy(buf + off, part[k], part_n[k]); off += part_n[k]; }
+            *out = buf; *out_n = total;
+        }
+    }
+    for (int k = 0; k < ndev; ++k) std::free(part[k]);
+    return rc;
 }
 
 int trre_shard_lines(const uint8_t *in, size_t n, int parts, size_t *cuts) {
