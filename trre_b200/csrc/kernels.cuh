@@ -1,15 +1,20 @@
-// kernels.cuh - sm_100a kernels of the scan path.
+// kernels.cuh - sm_100a kernels of the scan path (1/4).  The kernel families, by what serves a REGULAR
+// buffer (no NUL byte, final newline) - see trre_prog_info.fast_path:
 //
-//  k_bytemap      TRRE_EXEC_BYTEMAP, regular input: out[i] = LUT[in[i]], 16-byte vector loads/stores,
-//                 128 KB two-bytes-at-once table staged into shared memory by TMA, NUL / missing-final-
-//                 newline detection folded in (raises ST_IRREGULAR -> the general path reruns the buffer).
-//  k_lines        every other case: one 128-byte input chunk per thread, the thread owns the lines
-//                 that START in its chunk and runs the reference's per-line driver on them
-//                 (table executor or DFS executor), in one of three modes:
-//                   MODE_INPLACE  length-preserving program + regular input: out offset == in offset
-//                   MODE_COUNT    output bytes per chunk  -> cnt[], per-group sums -> gsum[]
-//                   MODE_WRITE    offsets = scan(gsum)[group] + block-scan(cnt) ; write
-//  k_scan_groups  exclusive scan of the per-group sums (single CTA) + grand total.
+//  k_bytemap      (here)               one byte in, one byte out: 16-byte vector loads/stores, 128 KB
+//                                      two-bytes-at-once table staged into shared memory by TMA
+//  k_match        (match_kernel.cuh)   position-parallel matcher for acyclic programs with short attempts:
+//                                      in place when length preserving, count/scan/write otherwise
+//  k_bmv_*        (bmv_kernel.cuh)     one byte in, 0..255 bytes out (deletions, expansions)
+//  k_lines_s      (lines_staged.cuh)   the reference's per-line loop, shared-memory staged: everything else
+//                                      and every IRREGULAR buffer (the fast kernels raise ST_IRREGULAR
+//                                      themselves and the engine reruns the buffer here)
+//  k_lines        (here)               the same loop without staging: in-place form for length-preserving
+//                                      cyclic programs, and the DFS executor (TRRE_EXEC_BACKTRACK)
+//                   modes: MODE_INPLACE  out offset == in offset
+//                          MODE_COUNT    output bytes per 128-byte chunk -> cnt[], per-group sums -> gsum[]
+//                          MODE_WRITE    offsets = scan(gsum)[group] + block-scan(cnt); write
+//  k_scan_groups  (here)               exclusive scan of per-group / per-span sums (one CTA) + grand total
 #pragma once
 #include <cstdint>
 
