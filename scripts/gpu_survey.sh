@@ -1,6 +1,7 @@
-for v in 0 1 2 3 0; do
-  echo -n "variant $v: "
-  TRRE_BM_VARIANT=$v python bench.py --steps 40 --warmup 5 --no-cpu-baseline --e2e-steps 0 2>&1 | tail -1 | python -c "
+python -m pytest tests/test_gpu_parity.py tests/test_gpu_cli.py tests/test_gpu_golden.py -x -q -m gpu 2>&1 | tail -3
+for w in del sub; do
+  echo -n "== $w: "
+  python bench.py --workload $w --bytes 1073741824 --steps 3 --warmup 3 --no-cpu-baseline --e2e-steps 3 2>&1 | tail -1 | python -c "
 import json,sys
-d=json.loads(sys.stdin.read()); print(d['value'], d['ms_per_step'], d['roofline']['frac'], d['verified'])"
+d=json.loads(sys.stdin.read()); print(d['value'],'GB/s e2e', d['e2e'])"
 done

@@ -35,6 +35,12 @@ void set_err(char *err, size_t cap, const std::string &s) {
 
 constexpr int kSlots = 3;                 // pipelined host path: chunks in flight
 
+// where a count/scan/write launch keeps its sums and reports: the per-device workspace, or one pipeline slot's
+struct Ws {
+    unsigned long long *gsum, *total;
+    uint32_t *status;
+};
+
 struct MatchPlan {
     uint32_t repl = 0, states = 0, pool = 0;
     int tab = 0;
@@ -72,7 +78,10 @@ struct DeviceState {
     uint8_t *buf_in = nullptr, *buf_out = nullptr; size_t cap_in = 0, cap_out = 0;
     uint8_t *slot_in[kSlots] = {nullptr, nullptr, nullptr}, *slot_out[kSlots] = {nullptr, nullptr, nullptr};
     cudaStream_t slot_stream[kSlots] = {nullptr, nullptr, nullptr};
-    size_t slot_cap = 0;
+    size_t slot_cap = 0, slot_out_cap = 0;
+    unsigned long long *slot_gsum[kSlots] = {nullptr, nullptr, nullptr};   // per-slot span sums (k_bmv / k_match var)
+    unsigned long long *d_slot_total = nullptr, *h_slot_total = nullptr;     // [kSlots]
+    cudaEvent_t slot_done[kSlots] = {nullptr, nullptr, nullptr};
     MatchPlan mp, mpv;             // k_match launch plans: length preserving / variable length
     bool staged_attr = false;
 };
@@ -337,13 +346,12 @@ bool bmv_capable(const trre_prog *p, const DeviceState *d, const uint8_t *d_in) 
 
 // variable-length byte map on a regular buffer: count -> scan -> write, all position parallel (bmv_kernel.cuh)
 int launch_bmv(const trre_prog *p, DeviceState *d, const uint8_t *d_in, size_t n, uint8_t *d_out, size_t out_cap,
-               cudaStream_t st, int phase, int *launches) {
+               cudaStream_t st, int phase, int *launches, const Ws *ws = nullptr) {
     const size_t n_tiles = (n + kBmvTile - 1) / kBmvTile;
     size_t n_spans = std::min<size_t>(std::max<size_t>(n_tiles / 16, 1), (size_t)d->sm_count * 64);
     const size_t tiles_per_span = (n_tiles + n_spans - 1) / n_spans;
     n_spans = (n_tiles + tiles_per_span - 1) / tiles_per_span;
-    int rc = ensure_workspace(d, 0, n_spans, false, 0);
-    if (rc != TRRE_OK) return rc;
+    if (!ws) { int rc = ensure_workspace(d, 0, n_spans, false, 0); if (rc != TRRE_OK) return rc; }
     if (!d->bmv_attr) {
         d->bmv_smem = 256 * 32 * 4 + ((d->vpool_bytes + 15) & ~15u) + (size_t)(kBmvWriteThreads / 32) * kBmvWarpSmem;
         CUDA_TRY(cudaFuncSetAttribute(k_bmv_count, cudaFuncAttributeMaxDynamicSharedMemorySize, kPairLutBytes));
@@ -353,13 +361,13 @@ int launch_bmv(const trre_prog *p, DeviceState *d, const uint8_t *d_in, size_t n
     BmvArgs a{};
     a.in = d_in; a.out = d_out; a.n = n; a.out_cap = out_cap;
     a.vent = d->vent; a.vpairlen = d->vpairlen; a.vpool = d->vpool; a.vpool_bytes = d->vpool_bytes;
-    a.gsum = d->d_gsum; a.total = d->d_total; a.status = d->d_status;
+    a.gsum = ws ? ws->gsum : d->d_gsum; a.total = ws ? ws->total : d->d_total; a.status = ws ? ws->status : d->d_status;
     a.n_spans = n_spans; a.tiles_per_span = tiles_per_span;
     if (phase != PH_WRITE) {
         k_bmv_count<<<d->sm_count, kBmvCountThreads, kPairLutBytes, st>>>(a);
-        k_scan_groups<<<1, kScanThreads, 0, st>>>(d->d_gsum, n_spans, d->d_total);
+        k_scan_groups<<<1, kScanThreads, 0, st>>>(a.gsum, n_spans, const_cast<unsigned long long *>(a.total));
         *launches += 2;
-        d->counts_kind = 2;
+        if (!ws) d->counts_kind = 2;
     }
     if (phase != PH_SIZE) {
         const size_t per = kBmvWriteThreads / 32;
@@ -378,26 +386,25 @@ bool mv_capable(const trre_prog *p, const DeviceState *d, const uint8_t *d_in) {
 
 // variable-length matches on a regular buffer: k_match<OP_COUNT> -> scan over the warp spans -> k_match<OP_WRITE>
 int launch_mv(const trre_prog *p, DeviceState *d, const uint8_t *d_in, size_t n, uint8_t *d_out, size_t out_cap,
-              cudaStream_t st, int phase, int *launches) {
+              cudaStream_t st, int phase, int *launches, const Ws *ws = nullptr) {
     const size_t n_tiles = (n + kTile - 1) / kTile;
     size_t blocks = std::min<size_t>((size_t)d->mpv.blocks, (n_tiles + 16 * kMatchWarps - 1) / (16 * kMatchWarps));
     if (blocks < 1) blocks = 1;
     const size_t n_spans = blocks * kMatchWarps;
-    int rc = ensure_workspace(d, 0, n_spans, false, 0);
-    if (rc != TRRE_OK) return rc;
+    if (!ws) { int rc = ensure_workspace(d, 0, n_spans, false, 0); if (rc != TRRE_OK) return rc; }
     MatchArgs m{};
-    m.P = d->P; m.in = d_in; m.out = d_out; m.n = n; m.status = d->d_status;
+    m.P = d->P; m.in = d_in; m.out = d_out; m.n = n; m.status = ws ? ws->status : d->d_status;
     m.smem_states = d->mpv.states; m.row0_replicated = d->mpv.repl; m.pool_in_smem = d->mpv.pool;
     m.tiles_per_warp = (n_tiles + n_spans - 1) / n_spans;
-    m.gsum = d->d_gsum; m.total = d->d_total; m.out_cap = out_cap;
+    m.gsum = ws ? ws->gsum : d->d_gsum; m.total = ws ? ws->total : d->d_total; m.out_cap = out_cap;
     const int tab = d->mpv.tab;
     if (phase != PH_WRITE) {
         if (tab == TAB_WIDE) k_match<TAB_WIDE, OP_COUNT><<<(int)blocks, kMatchThreads, d->mpv.smem, st>>>(m);
         else if (tab == TAB_ALL) k_match<TAB_ALL, OP_COUNT><<<(int)blocks, kMatchThreads, d->mpv.smem, st>>>(m);
         else k_match<TAB_PART, OP_COUNT><<<(int)blocks, kMatchThreads, d->mpv.smem, st>>>(m);
-        k_scan_groups<<<1, kScanThreads, 0, st>>>(d->d_gsum, n_spans, d->d_total);
+        k_scan_groups<<<1, kScanThreads, 0, st>>>(m.gsum, n_spans, const_cast<unsigned long long *>(m.total));
         *launches += 2;
-        d->counts_kind = 3;
+        if (!ws) d->counts_kind = 3;
     }
     if (phase != PH_SIZE) {
         if (tab == TAB_WIDE) k_match<TAB_WIDE, OP_WRITE><<<(int)blocks, kMatchThreads, d->mpv.smem, st>>>(m);
@@ -484,6 +491,7 @@ int collect(const trre_prog *p, DeviceState *d, cudaStream_t st, size_t *out_n) 
 
 int ensure_host_path_buffers(DeviceState *d, size_t need_in, size_t need_out) {
     if (need_in > d->cap_in) {
+        if (d->d_slot_total) { cudaFree(d->d_slot_total); cudaFreeHost(d->h_slot_total); }
         if (d->buf_in) cudaFree(d->buf_in);
         d->buf_in = nullptr; d->cap_in = 0;
         CUDA_TRY(cudaMalloc(&d->buf_in, need_in));
@@ -498,30 +506,100 @@ int ensure_host_path_buffers(DeviceState *d, size_t need_in, size_t need_out) {
     return TRRE_OK;
 }
 
-int ensure_slots(DeviceState *d, size_t chunk) {
-    if (d->slot_cap >= chunk) return TRRE_OK;
+int ensure_slots(DeviceState *d, size_t chunk, size_t out_cap) {
+    if (d->slot_cap >= chunk && d->slot_out_cap >= out_cap) return TRRE_OK;
     for (int k = 0; k < kSlots; ++k) {
         if (d->slot_in[k]) cudaFree(d->slot_in[k]);
         if (d->slot_out[k]) cudaFree(d->slot_out[k]);
         d->slot_in[k] = d->slot_out[k] = nullptr;
     }
-    d->slot_cap = 0;
+    d->slot_cap = d->slot_out_cap = 0;
+    const size_t max_spans = (size_t)d->sm_count * 64;            // >= the spans of k_bmv and of k_match<var>
     for (int k = 0; k < kSlots; ++k) {
         CUDA_TRY(cudaMalloc(&d->slot_in[k], chunk));
-        CUDA_TRY(cudaMalloc(&d->slot_out[k], chunk));
+        CUDA_TRY(cudaMalloc(&d->slot_out[k], out_cap));
         if (!d->slot_stream[k]) CUDA_TRY(cudaStreamCreateWithFlags(&d->slot_stream[k], cudaStreamNonBlocking));
+        if (!d->slot_gsum[k]) CUDA_TRY(cudaMalloc(&d->slot_gsum[k], max_spans * sizeof(unsigned long long)));
+        if (!d->slot_done[k]) CUDA_TRY(cudaEventCreateWithFlags(&d->slot_done[k], cudaEventDisableTiming));
+    }
+    if (!d->d_slot_total) {
+        CUDA_TRY(cudaMalloc(&d->d_slot_total, kSlots * sizeof(unsigned long long)));
+        CUDA_TRY(cudaMallocHost(&d->h_slot_total, kSlots * sizeof(unsigned long long)));
     }
     d->slot_cap = chunk;
+    d->slot_out_cap = out_cap;
     return TRRE_OK;
+}
+
+size_t host_chunk_bytes() {
+    size_t chunk = 32u << 20;
+    if (const char *e = std::getenv("TRRE_CHUNK_MB")) { long v = std::atol(e); if (v >= 1 && v <= 1024) chunk = (size_t)v << 20; }
+    return chunk;
+}
+
+// Host buffers, position-parallel program whose output length differs from the input's (k_bmv / k_match var):
+// same 3-slot pipeline, but a chunk's D2H can only be issued once its size is known, so chunk k is finished
+// (size read back, D2H enqueued at the running host offset) while chunks k+1 and k+2 are already in flight.
+// Returns 0 done, 1 = fall back to the one-shot path (irregular buffer, expansion beyond the slot, no room).
+int pipelined_var(const trre_prog *p, DeviceState *d, const uint8_t *in, size_t n, uint8_t *out, size_t out_cap,
+                  size_t *out_total, int *launches, bool bmv) {
+    const size_t chunk = host_chunk_bytes();
+    int rc = ensure_slots(d, chunk, 2 * chunk + 64);
+    if (rc != TRRE_OK) return rc;
+    CUDA_TRY(cudaMemsetAsync(d->d_status + 1, 0, kSlots * sizeof(uint32_t), d->slot_stream[0]));
+    CUDA_TRY(cudaStreamSynchronize(d->slot_stream[0]));
+    struct Piece { size_t pos, len; };
+    std::vector<Piece> pieces;
+    for (size_t pos = 0; pos < n;) {
+        size_t end = std::min(pos + chunk, n);
+        if (end < n) {
+            const void *nl = memrchr(in + pos, '\n', end - pos);
+            if (!nl) return 1;                                     // a line longer than a chunk
+            end = (size_t)(static_cast<const uint8_t *>(nl) - in) + 1;
+        }
+        pieces.push_back(Piece{pos, end - pos});
+        pos = end;
+    }
+    size_t host_off = 0;
+    bool give_up = false;
+    auto finish = [&](size_t k) -> int {
+        const int slot = (int)(k % kSlots);
+        CUDA_TRY(cudaEventSynchronize(d->slot_done[slot]));
+        const size_t total = (size_t)d->h_slot_total[slot];
+        if (d->h_status[1 + slot] || total > d->slot_out_cap || host_off + total > out_cap) { give_up = true; return TRRE_OK; }
+        CUDA_TRY(cudaMemcpyAsync(out + host_off, d->slot_out[slot], total, cudaMemcpyDeviceToHost, d->slot_stream[slot]));
+        host_off += total;
+        return TRRE_OK;
+    };
+    for (size_t k = 0; k < pieces.size() && !give_up; ++k) {
+        const int slot = (int)(k % kSlots);
+        cudaStream_t st = d->slot_stream[slot];
+        Ws ws{d->slot_gsum[slot], d->d_slot_total + slot, d->d_status + 1 + slot};
+        CUDA_TRY(cudaMemcpyAsync(d->slot_in[slot], in + pieces[k].pos, pieces[k].len, cudaMemcpyHostToDevice, st));
+        rc = bmv ? launch_bmv(p, d, d->slot_in[slot], pieces[k].len, d->slot_out[slot], d->slot_out_cap, st, PH_ALL, launches, &ws)
+                 : launch_mv(p, d, d->slot_in[slot], pieces[k].len, d->slot_out[slot], d->slot_out_cap, st, PH_ALL, launches, &ws);
+        if (rc != TRRE_OK) return rc;
+        CUDA_TRY(cudaMemcpyAsync(d->h_slot_total + slot, d->d_slot_total + slot, sizeof(unsigned long long), cudaMemcpyDeviceToHost, st));
+        CUDA_TRY(cudaMemcpyAsync(d->h_status + 1 + slot, d->d_status + 1 + slot, sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
+        CUDA_TRY(cudaEventRecord(d->slot_done[slot], st));
+        if (k + 1 >= (size_t)kSlots) { rc = finish(k + 1 - kSlots); if (rc != TRRE_OK) return rc; }
+    }
+    for (size_t k = pieces.size() >= (size_t)kSlots ? pieces.size() - kSlots + 1 : 0; k < pieces.size() && !give_up; ++k) {
+        rc = finish(k);
+        if (rc != TRRE_OK) return rc;
+    }
+    for (int s2 = 0; s2 < kSlots; ++s2) CUDA_TRY(cudaStreamSynchronize(d->slot_stream[s2]));
+    if (give_up) return 1;
+    *out_total = host_off;
+    return 0;
 }
 
 // Host buffers, length-preserving program: the input is cut at line boundaries into chunks that flow
 // through kSlots (H2D -> fast kernel -> D2H) on separate streams, so the two copy engines and the SMs
 // overlap.  Returns 1 when the buffer turned out irregular (caller falls back), 0 when done.
 int pipelined_lp(const trre_prog *p, DeviceState *d, const uint8_t *in, size_t n, uint8_t *out, int *launches) {
-    size_t chunk = 32u << 20;
-    if (const char *e = std::getenv("TRRE_CHUNK_MB")) { long v = std::atol(e); if (v >= 1 && v <= 1024) chunk = (size_t)v << 20; }
-    int rc = ensure_slots(d, chunk);
+    const size_t chunk = host_chunk_bytes();
+    int rc = ensure_slots(d, chunk, std::max(d->slot_out_cap, chunk));
     if (rc != TRRE_OK) return rc;
     CUDA_TRY(cudaMemsetAsync(d->d_status + 1, 0, kSlots * sizeof(uint32_t), d->slot_stream[0]));
     CUDA_TRY(cudaStreamSynchronize(d->slot_stream[0]));
@@ -604,12 +682,15 @@ void trre_prog_free(trre_prog *p) {
         cudaFree(d->d_blob); cudaFree(d->d_cnt); cudaFree(d->d_gsum); cudaFree(d->d_total); cudaFree(d->d_status);
         cudaFreeHost(d->h_total); cudaFreeHost(d->h_status);
         if (d->bt_s) { cudaFree(d->bt_s); cudaFree(d->bt_i); cudaFree(d->bt_o); cudaFree(d->bt_obuf); }
+        if (d->d_slot_total) { cudaFree(d->d_slot_total); cudaFreeHost(d->h_slot_total); }
         if (d->buf_in) cudaFree(d->buf_in);
         if (d->buf_out) cudaFree(d->buf_out);
         for (int k = 0; k < kSlots; ++k) {
             if (d->slot_in[k]) cudaFree(d->slot_in[k]);
             if (d->slot_out[k]) cudaFree(d->slot_out[k]);
             if (d->slot_stream[k]) cudaStreamDestroy(d->slot_stream[k]);
+            if (d->slot_gsum[k]) cudaFree(d->slot_gsum[k]);
+            if (d->slot_done[k]) cudaEventDestroy(d->slot_done[k]);
         }
         delete d;
     }
@@ -701,6 +782,15 @@ int trre_scan_into(const trre_prog *p, int device, const uint8_t *in, size_t n, 
         if (rc == 0) { if (out_n) *out_n = n; return TRRE_OK; }
         if (rc != 1) return rc;                                  // 1 = irregular buffer: general path below
     }
+    if (out && out_cap && ((p->hdr.flags & PF_BYTEMAP_VAR) || (p->hdr.flags & PF_MATCHABLE_VAR)) &&
+        (bmv_capable(p, d, nullptr) || mv_capable(p, d, nullptr))) {
+        int launches = 0;
+        size_t total = 0;
+        rc = pipelined_var(p, d, in, n, out, out_cap, &total, &launches, bmv_capable(p, d, nullptr));
+        d->launches = launches;
+        if (rc == 0) { if (out_n) *out_n = total; return TRRE_OK; }
+        if (rc != 1) return rc;                                  // 1: irregular / too large for the slots: one-shot path below
+    }
     rc = ensure_host_path_buffers(d, n, 0);
     if (rc != TRRE_OK) return rc;
     CUDA_TRY(cudaMemcpyAsync(d->buf_in, in, n, cudaMemcpyHostToDevice, st));
@@ -740,7 +830,9 @@ int trre_scan(const trre_prog *p, int device, const uint8_t *in, size_t n, uint8
     // size first (cheap when length preserving: n), then fill
     size_t need = 0;
     const bool lp = p && (p->hdr.flags & PF_LENGTH_PRESERVING) && p->hdr.exec_kind != TRRE_EXEC_BACKTRACK;
-    size_t cap = lp ? n : 0;
+    // length preserving: exactly n; otherwise guess a little more than n (one pipelined pass when it fits,
+    // the exact size comes back with TRRE_E_NOSPACE when it does not)
+    size_t cap = lp ? n : n + n / 4 + 4096;
     uint8_t *buf = static_cast<uint8_t *>(std::malloc(cap ? cap : 1));
     if (!buf) return TRRE_E_ARG;
     int rc = trre_scan_into(p, device, in, n, buf, cap, &need);
