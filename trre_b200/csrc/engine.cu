@@ -491,7 +491,6 @@ int collect(const trre_prog *p, DeviceState *d, cudaStream_t st, size_t *out_n) 
 
 int ensure_host_path_buffers(DeviceState *d, size_t need_in, size_t need_out) {
     if (need_in > d->cap_in) {
-        if (d->d_slot_total) { cudaFree(d->d_slot_total); cudaFreeHost(d->h_slot_total); }
         if (d->buf_in) cudaFree(d->buf_in);
         d->buf_in = nullptr; d->cap_in = 0;
         CUDA_TRY(cudaMalloc(&d->buf_in, need_in));
