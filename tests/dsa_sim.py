@@ -75,7 +75,7 @@ class Blob:
         steps = 0
         while stack or s >= 0:
             steps += 1
-            if steps > 2_000_000 or len(stack) > 65536:
+            if steps > 2_000_000 or len(stack) > 65536 or len(o) > 1 << 16:
                 raise Diverged()
             if s < 0:
                 s, i, o = stack.pop()
