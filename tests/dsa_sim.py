@@ -15,6 +15,12 @@ FIELDS = ("magic abi total_bytes flavor exec_kind flags nft_states nft_start dsa
           "start_info off_classmap off_lut off_startrow off_trans off_sinfo off_pool pool_bytes off_nft").split()
 
 
+# header words beyond FIELDS (automaton.hpp BlobHeader): index -> name
+EXT = {28: "swar_n", 29: "swar0", 30: "swar1", 31: "swar2", 32: "swar3", 33: "gram_depth", 34: "gram_entries",
+       35: "gram_len", 36: "gram_flags", 37: "off_gbits", 38: "off_gout", 39: "off_gpool", 40: "gpool_bytes"}
+PF_MATCHABLE, PF_GRAM = 64, 512
+
+
 class Diverged(Exception):
     pass
 
@@ -34,6 +40,61 @@ class Blob:
         self.sinfo = struct.unpack_from("<%dQ" % ns, raw, h["off_sinfo"]) if ns else ()
         self.pool = raw[h["off_pool"]:h["off_pool"] + h["pool_bytes"]]
         self.nft = [struct.unpack_from("<BBBBii", raw, h["off_nft"] + 12 * k) for k in range(h["nft_states"])]
+        words = struct.unpack_from("<41I", raw, 0)
+        for k, name in EXT.items():
+            h[name] = words[k]
+
+    # ---- table-free byte map (k_bytemap_swar): the LUT rebuilt from the ranges the kernel is given ----------
+    def swar_lut(self):
+        h = self.h
+        if not h["swar_n"]:
+            return None
+        lut = bytearray(range(256))
+        for k in range(h["swar_n"]):
+            w = h["swar%d" % k]
+            lo, hi, delta = w & 0xFF, (w >> 8) & 0xFF, (w >> 16) & 0xFF
+            assert lo <= hi and (lo < 0x80) == (hi < 0x80)
+            for c in range(256):
+                # the kernel's test: 7-bit compare inside the selected half of the byte space
+                if (c < 0x80) == (lo < 0x80) and (lo & 0x7F) <= (c & 0x7F) <= (hi & 0x7F):
+                    lut[c] = (c + delta) & 0xFF
+        return bytes(lut)
+
+    # ---- gram tables (k_gram): position-parallel form of the scan over a REGULAR buffer ----------------------
+    def scan_gram(self, data: bytes) -> bytes:
+        """What k_gram computes: a match starts at every position whose D-gram bit is set and that no earlier
+        match of the line covers; it prints gout.  Regular buffers only (no NUL, final newline)."""
+        h = self.h
+        assert h["flags"] & PF_GRAM and data.endswith(b"\n") and b"\0" not in data
+        D, ncls, n = h["gram_depth"], self.ncls, len(data)
+        bits = struct.unpack_from("<%dI" % ((h["gram_entries"] + 31) // 32), self.raw, h["off_gbits"])
+        gout = struct.unpack_from("<%dI" % h["gram_entries"], self.raw, h["off_gout"])
+        gpool = self.raw[h["off_gpool"]:h["off_gpool"] + h["gpool_bytes"]]
+        cm = self.classmap
+        out = bytearray(data)
+        covered_until = 0
+        for p in range(n):
+            if p < covered_until:
+                continue
+            idx = 0
+            for i in range(D - 1, -1, -1):
+                c = data[p + i] if p + i < n else 10
+                idx = idx * ncls + cm[c]
+            if not (bits[idx >> 5] >> (idx & 31)) & 1:
+                continue
+            g = gout[idx]
+            if h["gram_flags"] & 1:
+                m = h["gram_len"]
+                rep = bytes((g >> (8 * k)) & 0xFF for k in range(m))
+            else:
+                m = (g >> 28) + 1
+                ln = (g >> 20) & 0xFF
+                rep = gpool[g & 0xFFFFF:(g & 0xFFFFF) + ln]
+                assert h["gram_len"] in (0, m)
+            assert len(rep) == m, "k_gram serves length-preserving programs"
+            out[p:p + m] = rep
+            covered_until = p + m
+        return bytes(out)
 
     def ref(self, hi):
         ln, off = hi >> 24, hi & 0xFFFFFF

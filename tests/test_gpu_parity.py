@@ -115,6 +115,33 @@ def test_match_kernel_overlapping_matches(expr, flavor):
         assert got == want, (expr, flavor, seed)
 
 
+GRAM_PATTERNS = LP_PATTERNS[:11] + [
+    ("cat:dog", NFT), ("cat:dog", DFT), ("ca:xy|cat:dog", NFT), ("a:b|cat:dog", NFT), ("(c|d)(a|o)(t|g):xyz", NFT),
+    ("cat:dog|do:xy|c:z", NFT), ("[a-c][a-d]:pq", DFT), ("c(a:o)t|dog:cat", DFT), ("abcab:ABCAB|bca:xyz", NFT),
+    ("abcabc:ABCABC|cab:123|b:_", NFT), ("abcabc:ABCABC|cab:123|b:_", DFT), ("(a|b)(a|b)(a|b)(a|b)(a|b):vwxyz", NFT),
+]
+
+
+@pytest.mark.parametrize("expr,flavor", GRAM_PATTERNS)
+def test_gram_kernel_against_oracle_and_match_kernel(expr, flavor, monkeypatch):
+    """k_gram (every attempt tabulated by byte classes) vs the oracle, vs k_match (TRRE_NO_GRAM) on the same inputs."""
+    prog = T.compile(expr, flavor)
+    if prog.info["fast_path"] != 2:
+        pytest.skip("byte map")
+    assert prog.info["max_depth"] <= 6, prog.info
+    for seed, alphabet, hi in ((1, b"ab", 200), (2, b"abc", 60), (3, b"abcat dog", 400), (4, b"cat dog do", 9)):
+        data = _ab_text(seed, 1 << 20, alphabet, 0, hi)
+        rc, want, _ = oracle_run(expr.encode(), data, flavor=flavor)
+        assert rc == 0
+        assert prog.scan(data) == want, (expr, flavor, seed, "k_gram")
+        monkeypatch.setenv("TRRE_NO_GRAM", "1")
+        assert prog.scan(data) == want, (expr, flavor, seed, "k_match")
+        monkeypatch.delenv("TRRE_NO_GRAM")
+    for data in (b"", b"cat", b"cat\n", b"catcat\ncat", b"ab\0ab\nab\n", b"a" * 9000 + b"\n", b"abab" * 3000 + b"\n",
+                 b"ca\nt\n", b"c\n" * 700, b"cat" * 171 + b"\n"):
+        check(expr, flavor, data)
+
+
 def test_match_kernel_equals_line_kernel(monkeypatch):
     data = _ab_text(9, 3 << 20, b"abc ", 1, 3000)
     for expr, flavor in LP_PATTERNS[:8]:

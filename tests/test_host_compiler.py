@@ -170,3 +170,66 @@ def test_fast_path_classification():
     ]
     for expr, flavor, want in cases:
         assert T.compile(expr, flavor).info["fast_path"] == F[want], (expr, flavor, want)
+
+
+def test_swar_form_of_byte_maps_equals_the_lut():
+    """k_bytemap_swar gets ranges + deltas instead of a table: they must describe exactly the LUT."""
+    cases = [("[a:A-z:Z]", DFT, 1), ("[a:b-y:zz:a]", DFT, 2), ("[a:A-z:Z]|[0:a-9:j]", DFT, 2), ("a:b", NFT, 1),
+             ("[a:b-c:d]|x:y|[A:Z-C:X]", NFT, None), ("[\xf0:\x10-\xf5:\x15]", NFT, None)]
+    for expr, flavor, n_ranges in cases:
+        p = T.compile(expr.encode("latin1").decode("unicode_escape").encode("latin1"), flavor)
+        assert p.exec_kind == T.EXEC_BYTEMAP, expr
+        b = Blob(p.blob())
+        lut = b.swar_lut()
+        if n_ranges is not None:
+            assert b.h["swar_n"] == n_ranges, (expr, b.h["swar_n"])
+        if lut is not None:
+            assert lut == p.bytemap(), expr
+    # a map with more than four ranges keeps the pair table
+    many = "|".join("%s:%s" % (a, b) for a, b in zip("acegikm", "bdfhjln"))
+    assert Blob(T.compile(many, NFT).blob()).h["swar_n"] == 0
+
+
+def test_gram_tables_reproduce_the_scan():
+    """k_gram's tables (one bit + one output word per combination of byte classes) against the oracle."""
+    rng = random.Random(77)
+    words = ["cat", "dog", "catdog", "dogcat", "ca", "do", "cot", "dig"]
+    text = bytes(T.synth_text(3, 20000, words, 0.3))
+    for expr, flavor in [("cat:dog", NFT), ("cat:dog", DFT), ("(cat:dog|dog:cat)", NFT), ("(cat:dog|dog:cat)", DFT),
+                         ("ca:xy|cat:dog", NFT), ("ca:xy|cat:dog", DFT), ("a:b|cat:dog", NFT), ("(c|d)(a|o)(t|g):xyz", NFT),
+                         ("cat:dog|do:xy|c:z", NFT), ("[a-c][x-z]:pq", DFT), ("c(a:o)t", NFT), ("c(a:o)t|dog:cat", DFT)]:
+        p = T.compile(expr, flavor)
+        b = Blob(p.blob())
+        assert b.h["flags"] & 512 and p.info["fast_path"] == 2, (expr, p.info)
+        rc, want, _ = oracle_run(expr.encode(), text, flavor=flavor)
+        assert rc == 0 and b.scan_gram(text) == want, (expr, flavor)
+    for seed in range(40):
+        pat = rand_expr(rng, 2).encode()
+        for fl in (NFT, DFT):
+            try:
+                p = T.compile(pat, fl)
+            except T.TrreError:
+                continue
+            b = Blob(p.blob())
+            if not (b.h["flags"] & 512 and b.h["flags"] & 64):
+                continue
+            data = b"".join(rand_input(rng, final_newline=True).replace(b"\0", b"x") for _ in range(4))
+            if not data.endswith(b"\n"):
+                data += b"\n"
+            rc, want, _ = oracle_run(pat, data, flavor=fl)
+            assert rc == 0 and b.scan_gram(data) == want, (pat, fl, data)
+
+
+def test_gram_tables_of_the_dictionary():
+    rng = random.Random(7)
+    words = set()
+    while len(words) < 1500:
+        words.add("".join(rng.choice("abcdefghijklmnopqrstuvwxyz") for _ in range(4)))
+    words = sorted(words)
+    expr = "|".join("%s:%s" % (w, w.upper()) for w in words)
+    p = T.compile(expr, DFT)
+    b = Blob(p.blob())
+    assert b.h["flags"] & 512 and b.h["gram_depth"] == 4 and b.h["gram_len"] == 4 and b.h["gram_flags"] & 1
+    assert b.h["gram_entries"] == b.ncls ** 4
+    text = bytes(T.synth_text(12, 6000, words[:80], 0.3, True))
+    assert b.scan_gram(text) == oracle_run(expr.encode(), text, flavor=DFT)[1]

@@ -26,7 +26,8 @@ namespace trre {
 namespace {
 
 constexpr int32_t IT_FINAL = -2;      // pseudo item: an accepting path is pending
-constexpr int32_t IT_DIVERGE = -3;    // pseudo item: the reference's DFS never returns from here
+constexpr int32_t IT_DIVERGE = -3;
+constexpr uint32_t GRAM_DIRECT_FLAG = 1u;   // = GRAM_DIRECT in gram_kernel.cuh    // pseudo item: the reference's DFS never returns from here
 
 struct Item {
     int32_t q;
@@ -584,6 +585,93 @@ void analyse_and_pack(const std::vector<RawState> &st, const StringPool &sp, int
     }
 }
 
+// Gram tables (k_gram): the outcome of an attempt of an acyclic program is a function of the byte classes of its first
+// D = max_depth bytes.  Walk every combination here, once: bit = the attempt matches; out = what it prints, how much
+// it consumes.  Mirrors walk_from() in match_kernel.cuh (itself the table form of infer_dft / infer_backtrack).
+struct GramTables {
+    uint32_t depth = 0, entries = 0, uniform_len = 0, flags = 0;
+    std::vector<uint32_t> bits, out;
+    std::vector<uint8_t> pool;
+};
+
+bool build_grams(const Program &P, GramTables &G) {
+    const uint32_t D = P.max_depth, ncls = P.n_classes;
+    if (D < 1 || D > 6 || P.trans.empty()) return false;
+    uint64_t entries = 1;
+    for (uint32_t i = 0; i < D; ++i) { entries *= ncls; if (entries > 640u * 1024u) return false; }
+    const uint32_t S = (uint32_t)P.sinfo.size();
+    G.depth = D;
+    G.entries = (uint32_t)entries;
+    G.bits.assign((entries + 31) / 32, 0);
+    G.out.assign(entries, 0);
+    std::unordered_map<std::string, uint32_t> placed;
+    auto pool_str = [&](uint32_t hi, std::string &dst) {
+        uint32_t len = hi >> 24, off = hi & 0xFFFFFFu;
+        if (len == 255u) { std::memcpy(&len, P.pool.data() + off, 4); off += 4; }
+        dst.append(reinterpret_cast<const char *>(P.pool.data() + off), len);
+    };
+    std::vector<std::string> strs(entries);
+    std::vector<uint8_t> consumed(entries, 0);
+    bool uniform = true, all_short = true, lp = true;
+    uint32_t common = 0;
+    std::string str;
+    for (uint64_t idx = 0; idx < entries; ++idx) {
+        uint32_t s = 0, m = 0, lo_last = 0, steps = 0;
+        uint64_t rest = idx;
+        str.clear();
+        for (uint32_t i = 0; i < D; ++i) {
+            const uint32_t k = (uint32_t)(rest % ncls);
+            rest /= ncls;
+            const uint64_t e = P.trans[(size_t)s * ncls + k];
+            const uint32_t lo = (uint32_t)e;
+            if ((lo & 0xFFFFFFu) == DSA_DEAD) break;
+            pool_str((uint32_t)(e >> 32), str);
+            lo_last = lo;
+            s = lo & 0xFFFFFFu;
+            ++steps;
+            if (lo & DSA_E_MARK) m = steps;
+            if (lo & DSA_E_DECIDED) break;
+        }
+        if (!steps || !(lo_last & (DSA_E_DECIDED | DSA_E_HASFINAL)) || !m || s >= S) continue;
+        pool_str((uint32_t)(P.sinfo[s] >> 32), str);
+        if (str.size() > 255 || m > 16) return false;
+        G.bits[idx >> 5] |= 1u << (idx & 31);
+        strs[idx] = str;
+        consumed[idx] = (uint8_t)m;
+        if (!common) common = m; else if (common != m) uniform = false;
+        if (str.size() > 4) all_short = false;
+        if (str.size() != m) lp = false;
+    }
+    if (!common) return false;                                    // nothing can match: leave it to the generic kernels
+    G.uniform_len = uniform ? common : 0;
+    const bool direct = uniform && all_short && lp;
+    if (direct) G.flags |= GRAM_DIRECT_FLAG;
+    for (uint64_t idx = 0; idx < entries; ++idx) {
+        if (!consumed[idx]) continue;
+        const std::string &o = strs[idx];
+        if (direct) {
+            uint32_t w = 0;
+            for (size_t k = 0; k < o.size(); ++k) w |= (uint32_t)(uint8_t)o[k] << (8 * k);
+            G.out[idx] = w;
+        } else {
+            uint32_t off = 0;
+            if (!o.empty()) {
+                auto it = placed.find(o);
+                if (it == placed.end()) {
+                    off = (uint32_t)G.pool.size();
+                    G.pool.insert(G.pool.end(), o.begin(), o.end());
+                    placed.emplace(o, off);
+                } else off = it->second;
+            }
+            if (G.pool.size() >= (1u << 20)) return false;
+            G.out[idx] = off | ((uint32_t)o.size() << 20) | ((uint32_t)(consumed[idx] - 1) << 28);
+        }
+    }
+    while (G.pool.size() & 15) G.pool.push_back(0);
+    return true;
+}
+
+
 std::vector<uint8_t> assemble(const Program &P, const Nft &g) {
     BlobHeader h;
     std::memset(&h, 0, sizeof h);
@@ -626,6 +714,15 @@ std::vector<uint8_t> assemble(const Program &P, const Nft &g) {
         h.off_ctrans = (uint32_t)off; off += P.trans.size() * 4; off = align16(off);
         if ((matchable || matchable_var) && !P.eout.empty()) { h.off_eout = (uint32_t)off; off += P.eout.size() * 4; off = align16(off); }
     }
+    GramTables G;
+    const bool gram = (matchable || matchable_var) && build_grams(P, G);
+    if (gram) {
+        off = (off + 127) & ~(size_t)127;
+        h.off_gbits = (uint32_t)off; off += G.bits.size() * 4; off = align16(off);
+        h.off_gout = (uint32_t)off; off += G.out.size() * 4; off = align16(off);
+        h.off_gpool = (uint32_t)off; h.gpool_bytes = (uint32_t)G.pool.size(); off += G.pool.size(); off = align16(off);
+        h.gram_depth = G.depth; h.gram_entries = G.entries; h.gram_len = G.uniform_len; h.gram_flags = G.flags;
+    }
     if (off >= (1ull << 31)) throw PatternError{TRRE_E_UNSUPPORTED, "error: compiled tables exceed 2 GiB\n"};
     h.magic = 0x32425254u;  // "TRB2"
     h.abi = TRRE_B200_ABI_VERSION;
@@ -633,7 +730,7 @@ std::vector<uint8_t> assemble(const Program &P, const Nft &g) {
     h.flavor = (uint32_t)P.flavor;
     h.exec_kind = P.exec_kind;
     h.flags = P.flags | (matchable ? (uint32_t)PF_MATCHABLE : 0u) | (P.vmap ? (uint32_t)PF_BYTEMAP_VAR : 0u) |
-              (matchable_var ? (uint32_t)PF_MATCHABLE_VAR : 0u);
+              (matchable_var ? (uint32_t)PF_MATCHABLE_VAR : 0u) | (gram ? (uint32_t)PF_GRAM : 0u);
     h.nft_states = (uint32_t)g.st.size();
     h.nft_start = g.start;
     h.dsa_states = (uint32_t)P.sinfo.size();
@@ -641,6 +738,21 @@ std::vector<uint8_t> assemble(const Program &P, const Nft &g) {
     h.max_depth = P.max_depth;
     h.start_info = P.sinfo.empty() ? 0 : (uint32_t)(P.sinfo[0] & 0xFFFFFFFFu);
     h.pool_bytes = (uint32_t)P.pool.size();
+    if (P.exec_kind == TRRE_EXEC_BYTEMAP) {
+        // maximal runs of bytes that move by the same non-zero delta, cut at 0x80 (k_bytemap_swar tests 7-bit ranges)
+        std::vector<uint32_t> runs;
+        for (int c = 0; c < 256;) {
+            const uint32_t d = (uint32_t)(uint8_t)(P.lut[c] - c);
+            int e = c;
+            while (e + 1 < 256 && ((e + 1) & 0x7F) != 0 && (uint8_t)(P.lut[e + 1] - (e + 1)) == d) ++e;
+            if (d) runs.push_back((uint32_t)c | ((uint32_t)e << 8) | (d << 16));
+            c = e + 1;
+        }
+        if (!runs.empty() && runs.size() <= 4) {
+            h.swar_n = (uint32_t)runs.size();
+            for (size_t k = 0; k < runs.size(); ++k) h.swar[k] = runs[k];
+        }
+    }
     std::vector<uint8_t> blob(off, 0);
     std::memcpy(blob.data(), &h, sizeof h);
     std::memcpy(blob.data() + h.off_classmap, P.classmap, 256);
@@ -661,6 +773,11 @@ std::vector<uint8_t> assemble(const Program &P, const Nft &g) {
         for (size_t k = 0; k < P.trans.size(); ++k) ct[k] = (uint32_t)(P.trans[k] & 0xFFFFFFFFu);
     }
     if (h.off_eout) std::memcpy(blob.data() + h.off_eout, P.eout.data(), P.eout.size() * 4);
+    if (gram) {
+        std::memcpy(blob.data() + h.off_gbits, G.bits.data(), G.bits.size() * 4);
+        std::memcpy(blob.data() + h.off_gout, G.out.data(), G.out.size() * 4);
+        if (!G.pool.empty()) std::memcpy(blob.data() + h.off_gpool, G.pool.data(), G.pool.size());
+    }
     if (h.off_vent) {
         std::memcpy(blob.data() + h.off_vent, vent.data(), 1024);
         if (!vpool.empty()) std::memcpy(blob.data() + h.off_vpool, vpool.data(), vpool.size());

@@ -50,6 +50,7 @@ enum : uint32_t {
     PF_HAS_DIVERGE       = 16u,
     PF_MATCHABLE         = 64u,
     PF_BYTEMAP_VAR       = 128u,
+    PF_GRAM              = 512u,     // gram tables present (k_gram)
     PF_MATCHABLE_VAR     = 256u,     // k_mv_* apply: like PF_MATCHABLE but matches may print more or less than they consume     // every attempt is decided by one byte; that byte prints 0..255 bytes (k_bmv_*)      // k_match applies: length preserving, acyclic, attempts <= 16 bytes, no empty match
     PF_OUT_LATE          = 32u       // every transition into a non-DECIDED state emits nothing: a match's output
                                      // is out(last transition) + fin(last state)
@@ -85,6 +86,21 @@ struct BlobHeader {
     uint32_t vpool_bytes;
     uint32_t off_eout;         // u32[dsa_states * n_classes]: (PF_OUT_LATE) offset(24) | length(8) of out(edge)+fin(target) in the
                                // pool for edges into DECIDED states; u32[dsa_states] for pending FINALs follow. 0 if absent
+    // (TRRE_EXEC_BYTEMAP) table-free form of the LUT: it is the identity except on swar_n <= 4 byte ranges, each
+    // inside one half of the byte space, where it adds a constant mod 256 (cfg2: a-z -32; Caesar: a-y +1, z -25).
+    // 0 = no such form (k_bytemap's pair table serves).  swar[k] = lo | hi << 8 | delta << 16
+    uint32_t swar_n;
+    uint32_t swar[4];
+    // (PF_GRAM) every attempt tabulated by the byte classes of its first gram_depth bytes (k_gram, gram_kernel.cuh)
+    uint32_t gram_depth;       // D = max_depth, 1..6
+    uint32_t gram_entries;     // n_classes ^ D; index = sum cls(byte i) * n_classes^i
+    uint32_t gram_len;         // > 0: every match consumes exactly this many bytes
+    uint32_t gram_flags;       // GRAM_*
+    uint32_t off_gbits;        // u32[(gram_entries + 31) / 32]: the attempt matches
+    uint32_t off_gout;         // u32[gram_entries]: GRAM_DIRECT: the printed bytes; else offset into gpool(20) |
+                               // printed length(8) << 20 | (consumed - 1) << 28
+    uint32_t off_gpool;
+    uint32_t gpool_bytes;
 };
 
 struct NftFlat {               // 12 bytes, device layout of trre_nft.c:334-340

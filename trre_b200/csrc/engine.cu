@@ -16,6 +16,7 @@
 #include "automaton.hpp"
 #include "kernels.cuh"
 #include "match_kernel.cuh"
+#include "gram_kernel.cuh"
 #include "lines_staged.cuh"
 #include "bmv_kernel.cuh"
 #include "pattern.hpp"
@@ -84,6 +85,10 @@ struct DeviceState {
     cudaEvent_t slot_done[kSlots] = {nullptr, nullptr, nullptr};
     MatchPlan mp, mpv;             // k_match launch plans: length preserving / variable length
     bool staged_attr = false;
+    GramArgs gram{};               // k_gram tables (entries == 0: none)
+    size_t gram_smem = 0;
+    SwarMap swar{};                // table-free byte map (n == 0: not of that form)
+    int swar_ctas = 2;
 };
 
 }  // namespace
@@ -196,6 +201,17 @@ int get_state(const trre_prog *cp, int device, DeviceState **out) {
     d->P.flags = h.flags;
     d->P.nft_start = h.nft_start;
     CUDA_TRY(cudaFuncSetAttribute(k_bytemap, cudaFuncAttributeMaxDynamicSharedMemorySize, kPairLutBytes));
+    if (h.exec_kind == TRRE_EXEC_BYTEMAP && h.swar_n >= 1 && h.swar_n <= 4 && !std::getenv("TRRE_NO_SWAR")) {
+        d->swar.n = h.swar_n;
+        for (uint32_t k = 0; k < h.swar_n; ++k) {
+            const uint32_t lo = h.swar[k] & 0xFFu, hi = (h.swar[k] >> 8) & 0xFFu, delta = (h.swar[k] >> 16) & 0xFFu;
+            d->swar.add_lo[k] = (0x80u - (lo & 0x7Fu)) * 0x01010101u;
+            d->swar.add_hi[k] = (0x7Fu - (hi & 0x7Fu)) * 0x01010101u;
+            d->swar.half[k] = lo < 0x80u ? 0x80808080u : 0u;
+            d->swar.delta[k] = delta;
+        }
+        if (const char *e = std::getenv("TRRE_SWAR_CTAS")) { int v = std::atoi(e); if (v >= 1 && v <= 8) d->swar_ctas = v; }
+    }
     if (h.flags & PF_MATCHABLE) {
         int rc2 = plan_match(h, (size_t)kMatchWarps * kWarpSmem, 108 * 1024, d->sm_count, OP_INPLACE, &d->mp);
         if (rc2 != TRRE_OK) return rc2;
@@ -203,6 +219,32 @@ int get_state(const trre_prog *cp, int device, DeviceState **out) {
     if (h.flags & PF_MATCHABLE_VAR) {
         int rc2 = plan_match(h, (size_t)kMatchWarps * kVarWarpSmem, 108 * 1024, d->sm_count, OP_COUNT, &d->mpv);
         if (rc2 != TRRE_OK) return rc2;
+    }
+    if ((h.flags & PF_GRAM) && (h.flags & PF_MATCHABLE)) {
+        GramArgs &g = d->gram;
+        g.classmap = d->P.classmap;
+        g.gbits = reinterpret_cast<const uint32_t *>(d->d_blob + h.off_gbits);
+        g.gout = reinterpret_cast<const uint32_t *>(d->d_blob + h.off_gout);
+        g.gpool = d->d_blob + h.off_gpool;
+        g.gpool_bytes = h.gpool_bytes;
+        g.n_classes = h.n_classes;
+        g.entries = h.gram_entries;
+        g.uniform_len = h.gram_len;
+        g.gflags = h.gram_flags;
+        const uint32_t words = (h.gram_entries + 31) / 32;
+        g.bits_replicated = words <= 128 ? 1u : 0u;
+        g.gout_in_smem = h.gram_entries <= 4096 ? 1u : 0u;
+        g.pool_in_smem = (h.gpool_bytes && h.gpool_bytes <= 4096) ? 1u : 0u;
+        d->gram_smem = 256 * 32 * 4 + (size_t)((words * (g.bits_replicated ? 32u : 1u) + 3) & ~3u) * 4 +
+                       (g.gout_in_smem ? (size_t)((h.gram_entries + 3) & ~3u) * 4 : 0) +
+                       (g.pool_in_smem ? ((h.gpool_bytes + 15) & ~15u) : 0) + (size_t)kGramWarps * kWarpSmem;
+        const void *fns[6] = {(const void *)k_gram<1>, (const void *)k_gram<2>, (const void *)k_gram<3>,
+                              (const void *)k_gram<4>, (const void *)k_gram<5>, (const void *)k_gram<6>};
+        if (h.gram_depth >= 1 && h.gram_depth <= 6 && d->gram_smem <= 220 * 1024) {
+            CUDA_TRY(cudaFuncSetAttribute(fns[h.gram_depth - 1], cudaFuncAttributeMaxDynamicSharedMemorySize, (int)d->gram_smem));
+        } else {
+            g.entries = 0;
+        }
     }
     p->dev[device] = d;
     *out = d;
@@ -266,8 +308,31 @@ int launch_fast(const trre_prog *p, DeviceState *d, const uint8_t *d_in, size_t 
                 uint32_t *status, cudaStream_t st) {
     const BlobHeader &h = p->hdr;
     const bool aligned = ((reinterpret_cast<uintptr_t>(d_in) ^ reinterpret_cast<uintptr_t>(d_out)) & 15) == 0;
-    if (h.exec_kind == TRRE_EXEC_BYTEMAP && aligned && d->P.pairlut) {
+    if (h.exec_kind == TRRE_EXEC_BYTEMAP && aligned && d->swar.n) {
+        const int grid = d->sm_count * d->swar_ctas;
+        switch (d->swar.n) {
+            case 1: k_bytemap_swar<1><<<grid, kSwarThreads, 0, st>>>(d_in, d_out, n, d->swar, d->P.lut, status); break;
+            case 2: k_bytemap_swar<2><<<grid, kSwarThreads, 0, st>>>(d_in, d_out, n, d->swar, d->P.lut, status); break;
+            case 3: k_bytemap_swar<3><<<grid, kSwarThreads, 0, st>>>(d_in, d_out, n, d->swar, d->P.lut, status); break;
+            default: k_bytemap_swar<4><<<grid, kSwarThreads, 0, st>>>(d_in, d_out, n, d->swar, d->P.lut, status); break;
+        }
+    } else if (h.exec_kind == TRRE_EXEC_BYTEMAP && aligned && d->P.pairlut) {
         k_bytemap<<<d->sm_count, kBmThreads, kPairLutBytes, st>>>(d_in, d_out, n, d->P.pairlut, d->P.lut, status);
+    } else if (d->gram.entries && aligned && (reinterpret_cast<uintptr_t>(d_in) & 15) == 0 && !std::getenv("TRRE_NO_GRAM")) {
+        GramArgs g = d->gram;
+        g.in = d_in; g.out = d_out; g.n = n; g.status = status;
+        const size_t n_tiles = (n + kTile - 1) / kTile;
+        size_t blocks = std::min<size_t>((size_t)d->sm_count, (n_tiles + 16 * kGramWarps - 1) / (16 * kGramWarps));
+        if (blocks < 1) blocks = 1;
+        g.tiles_per_warp = (n_tiles + blocks * kGramWarps - 1) / (blocks * kGramWarps);
+        switch (p->hdr.gram_depth) {
+            case 1: k_gram<1><<<(int)blocks, kGramThreads, d->gram_smem, st>>>(g); break;
+            case 2: k_gram<2><<<(int)blocks, kGramThreads, d->gram_smem, st>>>(g); break;
+            case 3: k_gram<3><<<(int)blocks, kGramThreads, d->gram_smem, st>>>(g); break;
+            case 4: k_gram<4><<<(int)blocks, kGramThreads, d->gram_smem, st>>>(g); break;
+            case 5: k_gram<5><<<(int)blocks, kGramThreads, d->gram_smem, st>>>(g); break;
+            default: k_gram<6><<<(int)blocks, kGramThreads, d->gram_smem, st>>>(g); break;
+        }
     } else if ((d->P.flags & PF_MATCHABLE) && d->P.row0 && aligned && (reinterpret_cast<uintptr_t>(d_in) & 15) == 0 && !std::getenv("TRRE_NO_MATCH_KERNEL")) {
         MatchArgs m{};
         m.P = d->P; m.in = d_in; m.out = d_out; m.n = n; m.status = status;

@@ -1,0 +1,288 @@
+// gram_kernel.cuh - k_gram: position-parallel scan for length-preserving acyclic programs whose attempts are decided
+// by at most D <= 6 bytes and whose byte classes are few enough that EVERY possible attempt fits one table (sm_100a).
+//
+// k_match (match_kernel.cuh) walks the automaton from every live position: a dependent chain of table lookups per
+// candidate, divergent across the warp.  Here the host walks instead (automaton.cpp, build_grams): an attempt of an
+// acyclic program reads at most D = max_depth bytes, so its outcome is a function of the D byte CLASSES at the position -
+// n_classes^D combinations (cat:dog 4^3, (cat:dog|dog:cat) 7^3, the 10 000-word dictionary 27^4 = 531 441).  The device
+// keeps
+//     gbits  1 bit per combination: the attempt matches          (shared memory; 32x bank-replicated when small)
+//     gout   u32 per combination: what the match prints          (shared memory when small, else L2)
+// and a tile (512 bytes per warp, 16 positions per lane, as k_match) becomes straight-line code:
+//   A  16-byte vector load per lane (next tile prefetched); the D-1 bytes past a lane's end come from its neighbour
+//      by shuffle
+//   B  class of every byte: one conflict-free lookup each (32x replicated class table, bank = lane)
+//   C  index of the D-gram at each position by Horner steps over the classes (IMAD), one bitmap lookup -> candidate
+//      mask.  With matches of one common length (every BASELINE config) their lengths need no lookup at all.
+//   D  chain resolution (resolve_chain, shared with k_match): which candidates start outside an earlier match
+//   E  the real matches - a few per cent of the positions - are dealt round the warp; each fetches its output from
+//      gout (the bytes themselves when they fit a word) and overwrites its span of the staged output tile
+//   F  16-byte vector store per lane
+// Scan-driver semantics, warm-up from the last '\n' before a warp's span and ST_IRREGULAR handling are k_match's
+// (trre_nft.c:778-789 on a regular buffer: an attempt at every position not covered by an earlier match).
+#pragma once
+#include <cstdint>
+
+#include "match_kernel.cuh"
+
+namespace trre {
+
+constexpr int kGramThreads = 1024;
+constexpr int kGramWarps = kGramThreads / 32;
+constexpr int kGramMaxDepth = 6;
+
+enum : uint32_t {
+    GRAM_DIRECT = 1u,       // gout holds the output bytes themselves (every match prints <= 4 bytes, one common length)
+};
+
+struct GramArgs {
+    const uint8_t *in;
+    uint8_t *out;
+    size_t n;
+    uint32_t *status;
+    size_t tiles_per_warp;
+    const uint8_t *classmap;     // u8[256]
+    const uint32_t *gbits;       // u32[(entries + 31) / 32]
+    const uint32_t *gout;        // u32[entries]: GRAM_DIRECT: bytes; else pool offset(20) | printed length(8) << 20 | (consumed - 1) << 28
+    const uint8_t *gpool;
+    uint32_t gpool_bytes;
+    uint32_t n_classes;
+    uint32_t entries;            // n_classes ^ D
+    uint32_t uniform_len;        // > 0: every match consumes exactly this many bytes
+    uint32_t gflags;
+    uint32_t bits_replicated;    // 1: gbits sits 32x replicated in shared memory (bank = lane)
+    uint32_t gout_in_smem;
+    uint32_t pool_in_smem;
+};
+
+struct GramTables {
+    const uint32_t *cls_lane;    // shared: class of byte c at cls_lane[c * 32]  (already offset by the lane)
+    const uint32_t *cls_any;     // shared: same table, lane 0's column base (for lookups where banks do not matter)
+    const uint32_t *bits;        // shared: word w of the bitmap at bits[w * bstride]  (offset by the lane when replicated)
+    uint32_t bstride;
+    const uint32_t *gout;        // shared or global
+    const uint8_t *pool;         // shared or global
+};
+
+// index of the D-gram starting at tile position p, from the staged bytes (any lane, any position)
+template <int D>
+__device__ __forceinline__ uint32_t gram_index_at(const GramTables &T, const uint8_t *s_in, uint32_t p, uint32_t ncls) {
+    uint32_t idx = 0;
+#pragma unroll
+    for (int i = D - 1; i >= 0; --i) idx = idx * ncls + T.cls_lane[(uint32_t)s_in[p + i] << 5];
+    return idx;
+}
+
+template <int D, bool STORE>
+__device__ __forceinline__ void gram_tile(const GramArgs &a, const GramTables &T, uint8_t *s_in, uint8_t *s_out,
+                                          uint16_t *s_list, uint32_t *s_count, size_t base, uint4 x, uint4 x_next,
+                                          uint32_t lane, uint32_t first_valid, uint32_t &carry_e, uint4 &carry_halo,
+                                          uint32_t &nul_acc) {
+    // ---- A: stage the tile (input and default output = raw copy); lane 0 of the next tile is the halo ---------------
+    *reinterpret_cast<uint4 *>(s_in + lane * 16) = x;
+    *reinterpret_cast<uint4 *>(s_out + lane * 16) = x;
+    if (lane == 0) {
+        *reinterpret_cast<uint4 *>(s_in + kTile) = x_next;
+        *reinterpret_cast<uint4 *>(s_out + kTile) = x_next;
+        *s_count = 0;
+    }
+    nul_acc |= ((x.x - 0x01010101u) & ~x.x) | ((x.y - 0x01010101u) & ~x.y) | ((x.z - 0x01010101u) & ~x.z) | ((x.w - 0x01010101u) & ~x.w);
+    // the D-1 bytes after this lane's 16: the neighbour's first words (lane 31: the next tile's)
+    uint32_t h0 = __shfl_down_sync(0xFFFFFFFFu, x.x, 1), h1 = __shfl_down_sync(0xFFFFFFFFu, x.y, 1);
+    const uint32_t n0 = __shfl_sync(0xFFFFFFFFu, x_next.x, 0), n1 = __shfl_sync(0xFFFFFFFFu, x_next.y, 0);
+    if (lane == 31) { h0 = n0; h1 = n1; }
+
+    // ---- B: byte classes, conflict free (bank = lane) ------------------------------------------------------------------
+    const uint32_t ncls = a.n_classes;
+    uint32_t cls[16 + kGramMaxDepth - 1];
+    {
+        const uint32_t w[6] = {x.x, x.y, x.z, x.w, h0, h1};
+#pragma unroll
+        for (int t = 0; t < 16 + D - 1; ++t) {
+            const uint32_t c = (w[t >> 2] >> ((t & 3) * 8)) & 0xFFu;
+            cls[t] = T.cls_lane[c << 5];
+        }
+    }
+    // ---- C: D-gram index per position (Horner over the classes), one bitmap lookup each -> candidate mask -----------
+    uint32_t cand = 0;
+    {
+        const uint32_t n2 = ncls * ncls, n4 = n2 * n2;
+        uint32_t q[16 + kGramMaxDepth - 1];                       // pair codes cls[t] + ncls * cls[t+1]
+        if (D >= 3) {
+#pragma unroll
+            for (int t = 0; t < 16 + D - 2; ++t) q[t] = cls[t] + ncls * cls[t + 1];
+        }
+#pragma unroll
+        for (int j = 0; j < 16; ++j) {
+            uint32_t idx;
+            if (D == 1) idx = cls[j];
+            else if (D == 2) idx = cls[j] + ncls * cls[j + 1];
+            else if (D == 3) idx = q[j] + n2 * cls[j + 2];
+            else if (D == 4) idx = q[j] + n2 * q[j + 2];
+            else if (D == 5) idx = q[j] + n2 * q[j + 2] + n4 * cls[j + 4];
+            else idx = q[j] + n2 * q[j + 2] + n4 * q[j + 4];
+            const uint32_t wd = T.bits[(idx >> 5) * T.bstride];
+            cand |= ((wd >> (idx & 31u)) & 1u) << j;
+        }
+    }
+    {
+        const uint32_t my0 = lane * 16;
+        if (first_valid > my0) cand &= (first_valid - my0 >= 16) ? 0u : (0xFFFFu << (first_valid - my0));
+    }
+    __syncwarp();                                                     // the staged tile is visible
+
+    // ---- lengths: one common length needs no lookup; otherwise one gout lookup per candidate ----------------------------
+    Front f;
+    if (a.uniform_len) {
+        f.lens = 0x1111111111111111ull * (unsigned long long)(a.uniform_len - 1);
+    } else {
+        f.lens = 0;
+        uint32_t c2 = cand;
+        while (c2) {
+            const uint32_t j = __ffs(c2) - 1;
+            c2 &= c2 - 1;
+            const uint32_t g = T.gout[gram_index_at<D>(T, s_in, lane * 16 + j, ncls)];
+            f.lens |= (unsigned long long)(g >> 28) << (4 * j);
+        }
+    }
+    // ---- D ---------------------------------------------------------------------------------------------------------------
+    resolve_chain(f, cand, lane, carry_e);
+    uint32_t real = f.real;
+
+    // ---- E: real matches overwrite their span of the output tile; dealt round the warp ---------------------------------
+    if (lane == 0 && carry_e) {
+        const uint32_t h[4] = {carry_halo.x, carry_halo.y, carry_halo.z, carry_halo.w};
+        for (uint32_t k = 0; k < carry_e; ++k) s_out[k] = (uint8_t)(h[k >> 2] >> ((k & 3) * 8));
+    }
+    if (__any_sync(0xFFFFFFFFu, real != 0)) {
+        uint32_t slot = real ? atomicAdd(s_count, (uint32_t)__popc(real)) : 0u;
+        while (real) {
+            const uint32_t j = __ffs(real) - 1;
+            real &= real - 1;
+            s_list[slot++] = (uint16_t)(lane * 16 + j);
+        }
+        __syncwarp();
+        const uint32_t total = *s_count;
+        for (uint32_t qi = lane; qi < total; qi += 32) {
+            const uint32_t p = s_list[qi];
+            const uint32_t g = T.gout[gram_index_at<D>(T, s_in, p, ncls)];
+            if (a.gflags & GRAM_DIRECT) {
+                const uint32_t m = a.uniform_len;
+                for (uint32_t k = 0; k < m; ++k) s_out[p + k] = (uint8_t)(g >> (8 * k));
+            } else {
+                const uint8_t *src = T.pool + (g & 0xFFFFFu);
+                const uint32_t m = (g >> 28) + 1;                      // length preserving: printed == consumed
+                for (uint32_t k = 0; k < m; ++k) s_out[p + k] = src[k];
+            }
+        }
+    }
+    __syncwarp();
+    if (STORE) {
+        const size_t my = base + (size_t)lane * 16;
+        const uint4 y = *reinterpret_cast<const uint4 *>(s_out + lane * 16);
+        if (my + 16 <= a.n) {
+            *reinterpret_cast<uint4 *>(a.out + my) = y;
+        } else if (my < a.n) {
+            const uint32_t w[4] = {y.x, y.y, y.z, y.w};
+            for (int k = 0; k < 16 && my + k < a.n; ++k) a.out[my + k] = (uint8_t)(w[k >> 2] >> ((k & 3) * 8));
+        }
+    }
+    carry_e = __shfl_sync(0xFFFFFFFFu, f.e_out, 31);
+    carry_halo = *reinterpret_cast<const uint4 *>(s_out + kTile);     // every lane reads it; only lane 0 uses it
+    __syncwarp();
+}
+
+template <int D>
+__global__ void __launch_bounds__(kGramThreads, 1)
+k_gram(GramArgs a) {
+    extern __shared__ __align__(16) uint8_t smem[];
+    const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    // layout: [class table 32 KB] [bitmap (x32 when replicated)] [gout]? [pool]? [per warp: s_in, s_out, list, counter]
+    uint8_t *cur = smem;
+    uint32_t *cls_s = reinterpret_cast<uint32_t *>(cur); cur += 256 * 32 * 4;
+    uint32_t *bits_s = reinterpret_cast<uint32_t *>(cur);
+    const uint32_t words = (a.entries + 31) / 32;
+    cur += (size_t)((words * (a.bits_replicated ? 32u : 1u) + 3) & ~3u) * 4;
+    uint32_t *gout_s = nullptr;
+    if (a.gout_in_smem) { gout_s = reinterpret_cast<uint32_t *>(cur); cur += (size_t)((a.entries + 3) & ~3u) * 4; }
+    uint8_t *pool_s = nullptr;
+    if (a.pool_in_smem) { pool_s = cur; cur += (a.gpool_bytes + 15) & ~15u; }
+    uint8_t *warp_base = cur + warp * kWarpSmem;
+
+    for (uint32_t k = threadIdx.x; k < 256u * 32u; k += blockDim.x) cls_s[k] = __ldg(a.classmap + (k >> 5));
+    if (a.bits_replicated) {
+        for (uint32_t k = threadIdx.x; k < words * 32u; k += blockDim.x) bits_s[k] = __ldg(a.gbits + (k >> 5));
+    } else {
+        for (uint32_t k = threadIdx.x; k < words; k += blockDim.x) bits_s[k] = __ldg(a.gbits + k);
+    }
+    if (gout_s)
+        for (uint32_t k = threadIdx.x; k < a.entries; k += blockDim.x) gout_s[k] = __ldg(a.gout + k);
+    if (pool_s)
+        for (uint32_t k = threadIdx.x; k < a.gpool_bytes; k += blockDim.x) pool_s[k] = __ldg(a.gpool + k);
+    __syncthreads();
+
+    GramTables T;
+    T.cls_lane = cls_s + lane;
+    T.cls_any = cls_s;
+    T.bits = a.bits_replicated ? bits_s + lane : bits_s;
+    T.bstride = a.bits_replicated ? 32u : 1u;
+    T.gout = gout_s ? gout_s : a.gout;
+    T.pool = pool_s ? pool_s : a.gpool;
+
+    uint8_t *s_in = warp_base, *s_out = warp_base + 544;
+    uint16_t *s_list = reinterpret_cast<uint16_t *>(warp_base + 1088);
+    uint32_t *s_count = reinterpret_cast<uint32_t *>(warp_base + 1088 + 1024);
+
+    const size_t n = a.n;
+    const size_t n_tiles = (n + kTile - 1) / kTile;
+    const size_t gwarp = (size_t)blockIdx.x * kGramWarps + warp;
+    const size_t t0 = gwarp * a.tiles_per_warp;
+    size_t t1 = t0 + a.tiles_per_warp;
+    if (t1 > n_tiles) t1 = n_tiles;
+    uint32_t status = 0, nul_acc = 0;
+    if (t0 < t1) {
+        uint32_t carry_e = 0;
+        uint4 carry_halo = make_uint4(0, 0, 0, 0);
+        // ---- warm-up: the chain state at t0 is only known from the last '\n' before it (as k_match) ------------------
+        size_t tw = t0;
+        uint32_t first_valid = 0;
+        if (t0 > 0) {
+            bool found = false;
+            for (int k = 1; k <= kWarmTiles && !found; ++k) {
+                if ((size_t)k > t0) { tw = 0; first_valid = 0; found = true; break; }
+                const size_t tb = (t0 - k) * (size_t)kTile;
+                uint4 v = ldg_vec(a.in + tb + lane * 16);
+                const uint32_t w[4] = {v.x, v.y, v.z, v.w};
+                int last = -1;
+#pragma unroll
+                for (int j = 0; j < 16; ++j)
+                    if (((w[j >> 2] >> ((j & 3) * 8)) & 0xFFu) == '\n') last = j;
+                uint32_t has = __ballot_sync(0xFFFFFFFFu, last >= 0);
+                if (has) {
+                    int src = 31 - __clz(has);
+                    int lj = __shfl_sync(0xFFFFFFFFu, last, src);
+                    uint32_t pos_in_tile = (uint32_t)src * 16 + (uint32_t)lj + 1;
+                    if (pos_in_tile >= (uint32_t)kTile) { tw = t0 - k + 1; first_valid = 0; }
+                    else { tw = t0 - k; first_valid = pos_in_tile; }
+                    found = true;
+                }
+            }
+            if (!found) { status |= ST_IRREGULAR; tw = t0; }
+        }
+        size_t base = tw * (size_t)kTile;
+        uint4 x = load_padded(a.in, base + lane * 16, n);
+        for (size_t t = tw; t < t1; ++t) {
+            base = t * (size_t)kTile;
+            const uint4 x_next = load_padded(a.in, base + kTile + lane * 16, n);     // prefetch; its lane 0 is this tile's halo
+            if (t < t0) gram_tile<D, false>(a, T, s_in, s_out, s_list, s_count, base, x, x_next, lane, first_valid, carry_e, carry_halo, nul_acc);
+            else        gram_tile<D, true>(a, T, s_in, s_out, s_list, s_count, base, x, x_next, lane, first_valid, carry_e, carry_halo, nul_acc);
+            first_valid = 0;
+            x = x_next;
+        }
+    }
+    if (nul_acc & 0x80808080u) status |= ST_IRREGULAR;
+    if (blockIdx.x == 0 && threadIdx.x == 0 && n && a.in[n - 1] != '\n') status |= ST_IRREGULAR;
+    if (status) atomicOr(a.status, status);
+}
+
+}  // namespace trre

@@ -167,6 +167,98 @@ k_bytemap(const uint8_t *__restrict__ in, uint8_t *__restrict__ out, size_t n,
 }
 
 // ------------------------------------------------------------------------------------------------
+// k_bytemap_swar: table-free byte maps
+// ------------------------------------------------------------------------------------------------
+// Most byte maps people write are "add a constant on a few byte ranges" ([a:A-z:Z]: a-z -32; Caesar: a-y +1,
+// z -25).  Those need no table: per 32-bit word, a 7-bit SWAR range test per range (two adds whose carries stay
+// inside their byte), the selected bytes' deltas accumulated with one IMAD per range, and a carry-isolated
+// byte-wise add.  No shared memory, no LSU traffic besides the stream itself, 2 x 1024 threads per SM.
+// The host emits the ranges (BlobHeader::swar); maps that are not of this form keep k_bytemap's pair table.
+struct SwarMap {
+    uint32_t n;
+    uint32_t add_lo[4];      // (0x80 - (lo & 0x7F)) in every byte: bit 7 of (l + add_lo) <=> l >= lo
+    uint32_t add_hi[4];      // (0x7F - (hi & 0x7F)) in every byte: bit 7 of (l + add_hi) <=> l >  hi
+    uint32_t half[4];        // 0x80808080 when the range lies in 0x00-0x7F (bit 7 of the byte must be clear), else 0
+    uint32_t delta[4];       // added mod 256 to the bytes in range
+};
+
+template <int NR>
+__device__ __forceinline__ uint32_t swar_word(uint32_t x, const SwarMap &M, uint32_t &nul) {
+    const uint32_t l = x & 0x7F7F7F7Fu;
+    uint32_t d = 0;
+#pragma unroll
+    for (int r = 0; r < NR; ++r) {
+        const uint32_t ge = l + M.add_lo[r], gt = l + M.add_hi[r];
+        const uint32_t m = ge & ~gt & (x ^ M.half[r]) & 0x80808080u;      // bit 7 of every byte inside the range
+        d += (m >> 7) * M.delta[r];                                       // ranges are disjoint: no byte gets two deltas
+    }
+    nul |= (x - 0x01010101u) & ~x;
+    return (l + (d & 0x7F7F7F7Fu)) ^ ((x ^ d) & 0x80808080u);              // byte-wise x + d, carries cut at bit 7
+}
+
+template <int NR>
+__device__ __forceinline__ uint4 swar_vec(const uint4 &x, const SwarMap &M, uint32_t &nul) {
+    uint4 y;
+    y.x = swar_word<NR>(x.x, M, nul);
+    y.y = swar_word<NR>(x.y, M, nul);
+    y.z = swar_word<NR>(x.z, M, nul);
+    y.w = swar_word<NR>(x.w, M, nul);
+    return y;
+}
+
+constexpr int kSwarThreads = 512;
+constexpr int kSwarUnroll = 4;
+
+template <int NR>
+__global__ void __launch_bounds__(kSwarThreads, 2)
+k_bytemap_swar(const uint8_t *__restrict__ in, uint8_t *__restrict__ out, size_t n, const SwarMap M,
+               const uint8_t *__restrict__ lut, uint32_t *__restrict__ status) {
+    uint32_t nul = 0;
+    size_t head = ((16 - (reinterpret_cast<uintptr_t>(in) & 15)) & 15);
+    if (head > n) head = n;
+    const size_t nvec = (n - head) / 16;
+    const uint4 *vin = reinterpret_cast<const uint4 *>(in + head);
+    uint4 *vout = reinterpret_cast<uint4 *>(out + head);
+    // same sweep as k_bytemap: the whole grid inside one contiguous window, kSwarUnroll strided vectors per thread,
+    // the next batch's loads in flight while this one is mapped and stored
+    const size_t stride = (size_t)gridDim.x * blockDim.x;
+    size_t v = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (v + (kSwarUnroll - 1) * stride < nvec) {
+        uint4 x[kSwarUnroll];
+#pragma unroll
+        for (int u = 0; u < kSwarUnroll; ++u) x[u] = ld_stream(vin + v + u * stride);
+        for (;;) {
+            const size_t vn = v + kSwarUnroll * stride;
+            const bool more = vn + (kSwarUnroll - 1) * stride < nvec;
+            uint4 xn[kSwarUnroll];
+            if (more) {
+#pragma unroll
+                for (int u = 0; u < kSwarUnroll; ++u) xn[u] = ld_stream(vin + vn + u * stride);
+            }
+#pragma unroll
+            for (int u = 0; u < kSwarUnroll; ++u) st_stream(vout + v + u * stride, swar_vec<NR>(x[u], M, nul));
+            v = vn;
+            if (!more) break;
+#pragma unroll
+            for (int u = 0; u < kSwarUnroll; ++u) x[u] = xn[u];
+        }
+    }
+    for (; v < nvec; v += stride) {
+        uint4 x = ld_stream(vin + v);
+        st_stream(vout + v, swar_vec<NR>(x, M, nul));
+    }
+    nul &= 0x80808080u;
+    if (blockIdx.x == 0 && threadIdx.x == 0) {
+        for (size_t k = 0; k < head; ++k) { uint8_t c = in[k]; if (!c) nul = 1; out[k] = lut[c]; }
+        for (size_t k = head + nvec * 16; k < n; ++k) { uint8_t c = in[k]; if (!c) nul = 1; out[k] = lut[c]; }
+        if (n && in[n - 1] != '\n') nul = 1;
+    }
+    if (__any_sync(0xFFFFFFFFu, nul != 0)) {
+        if ((threadIdx.x & 31) == 0) atomicOr(status, ST_IRREGULAR);
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
 // k_lines
 // ------------------------------------------------------------------------------------------------
 enum { MODE_INPLACE = 0, MODE_COUNT = 1, MODE_WRITE = 2 };

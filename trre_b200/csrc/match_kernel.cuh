@@ -153,6 +153,38 @@ struct Front {
     uint32_t e_in, e_out;        // positions covered at the start of this lane / of the next one
 };
 
+// Step D of a tile: which candidate matches are real, i.e. start outside every earlier match of the line.  C = this
+// lane's candidate mask (16 positions), lens = (m - 1) in 4 bits per position, carry_e = positions of this tile still
+// covered by the last real match of the previous tile.  Speculate "nothing hangs into my lane", then repair through
+// warp shuffles until stable (matches are short and sparse: one or two rounds).
+__device__ __forceinline__ void resolve_chain(Front &f, uint32_t C, uint32_t lane, uint32_t carry_e) {
+    const uint32_t first = C ? (uint32_t)__ffs(C) - 1 : 16u;
+    uint32_t e_used = (lane == 0) ? carry_e : 0u, real = 0, e_out = 0;
+    auto chain = [&](uint32_t e) {
+        uint32_t pos = e, r = 0;
+        uint32_t Cm = C & (0xFFFFu << pos);                          // e <= 15
+        while (Cm) {
+            uint32_t j = __ffs(Cm) - 1;
+            r |= 1u << j;
+            pos = j + 1 + ((uint32_t)(f.lens >> (4 * j)) & 15u);
+            Cm = pos < 16 ? (C & (0xFFFFu << pos)) : 0u;
+        }
+        real = r;
+        e_out = pos > 16 ? pos - 16 : 0u;
+    };
+    chain(e_used);
+    for (;;) {
+        uint32_t prev = __shfl_up_sync(0xFFFFFFFFu, e_out, 1);
+        if (lane == 0) prev = carry_e;
+        const bool differs = prev != e_used;
+        const bool need = differs && (prev > first || e_used > first);
+        if (differs) e_used = prev;
+        if (!__any_sync(0xFFFFFFFFu, need)) break;
+        if (need) chain(e_used);
+    }
+    f.real = real; f.e_in = e_used; f.e_out = e_out;
+}
+
 template <int TAB>
 __device__ __forceinline__ Front tile_frontend(const MatchTables &T, const uint8_t *s_in, uint4 x, uint32_t lane,
                                                uint32_t first_valid, uint32_t carry_e) {
@@ -193,31 +225,7 @@ __device__ __forceinline__ Front tile_frontend(const MatchTables &T, const uint8
     }
 
     // ---- D: which matches are real (start outside every earlier match) ---------------------------------
-    const uint32_t first = C ? (uint32_t)__ffs(C) - 1 : 16u;
-    uint32_t e_used = (lane == 0) ? carry_e : 0u, real = 0, e_out = 0;
-    auto chain = [&](uint32_t e) {
-        uint32_t pos = e, r = 0;
-        uint32_t Cm = C & (0xFFFFu << pos);                          // e <= 15
-        while (Cm) {
-            uint32_t j = __ffs(Cm) - 1;
-            r |= 1u << j;
-            pos = j + 1 + ((uint32_t)(f.lens >> (4 * j)) & 15u);
-            Cm = pos < 16 ? (C & (0xFFFFu << pos)) : 0u;
-        }
-        real = r;
-        e_out = pos > 16 ? pos - 16 : 0u;
-    };
-    chain(e_used);
-    for (;;) {
-        uint32_t prev = __shfl_up_sync(0xFFFFFFFFu, e_out, 1);
-        if (lane == 0) prev = carry_e;
-        const bool differs = prev != e_used;
-        const bool need = differs && (prev > first || e_used > first);
-        if (differs) e_used = prev;
-        if (!__any_sync(0xFFFFFFFFu, need)) break;
-        if (need) chain(e_used);
-    }
-    f.real = real; f.e_in = e_used; f.e_out = e_out;
+    resolve_chain(f, C, lane, carry_e);
     return f;
 }
 
