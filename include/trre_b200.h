@@ -57,7 +57,9 @@ enum {
 enum {
     TRRE_EXEC_BYTEMAP   = 0,   /* every attempt is decided by one byte and emits one byte: 256-entry LUT     */
     TRRE_EXEC_TABLE     = 1,   /* deterministic scan automaton walked per line                               */
-    TRRE_EXEC_BACKTRACK = 2    /* NFT flavour only: per-line priority DFS over the flat NFT                  */
+    TRRE_EXEC_BACKTRACK = 2,   /* NFT flavour only: per-line priority DFS over the flat NFT                  */
+    TRRE_EXEC_LAZY      = 3    /* scan automaton too large to build ahead of time: rows are built on demand,  */
+                               /* as trre_dft does (trre_dft.c:1135-1175); the scan itself stays on the GPU   */
 };
 
 /* the kernel family that serves a regular buffer (no NUL byte, final newline); irregular buffers and
@@ -98,6 +100,17 @@ int  trre_prog_get_info(const trre_prog *p, trre_prog_info *info);
  * rank 0 (one ncclBroadcast / torch.distributed.broadcast) instead of recompiling per rank. */
 const void *trre_prog_blob(const trre_prog *p, size_t *nbytes);
 int  trre_prog_from_blob(const void *blob, size_t nbytes, trre_prog **out, char *err, size_t errcap);
+
+/* TRRE_EXEC_LAZY programs (trre_dft.c:1135-1175: rows of the deterministic transducer exist only for the states the
+ * input reached).  During a scan the GPU reports the rows it misses and the library builds them; these two calls
+ * expose the same builder to tooling: build the rows of `states` (+ up to `extra` more, breadth first), and look at
+ * what exists.  rows: u64[n_states * 256] by raw byte, lo = next | flags (0x00FFFFFE: row not built, 0x00FFFFFF:
+ * dead), hi = output ref into pool (offset(24) | length(8), length 255: u32 length at the offset); sinfo: u64 per
+ * state, lo = flags (1 final pending, 2 decided, 8 row built), hi = ref of the final output.  The pointers stay
+ * valid until the next build. */
+int  trre_lazy_build(trre_prog *p, const uint32_t *states, size_t n, uint32_t extra);
+int  trre_lazy_view(const trre_prog *p, uint32_t *n_states, const uint64_t **rows, const uint64_t **sinfo,
+                    const uint8_t **pool, size_t *pool_bytes);
 
 /* 256-entry map for TRRE_EXEC_BYTEMAP programs (returns TRRE_E_ARG otherwise). */
 int  trre_prog_bytemap(const trre_prog *p, uint8_t lut[256]);

@@ -162,9 +162,63 @@ class Blob:
                 return i, (o if z < 0 else o[:z])
         return -1, b""
 
+    # TRRE_EXEC_LAZY: rows by raw byte from the on-demand builder (Program.lazy_view / lazy_build), as the lazy
+    # kernel walks them; a missing row is built on the spot (the GPU reports it and repeats the pass instead)
+    def attach_lazy(self, prog):
+        self.lazy = prog
+        self.lazy_builds = 0
+
+    def attempt_lazy(self, payload, p):
+        import ctypes
+        prog = self.lazy
+        while True:
+            n, rows_a, sinfo_a, pool_a, pool_n = prog.lazy_view()
+            rows = (ctypes.c_uint64 * (n * 256)).from_address(rows_a)
+            sinfo = (ctypes.c_uint64 * n).from_address(sinfo_a)
+            pool = ctypes.string_at(pool_a, pool_n) if pool_n else b""
+
+            def ref(hi):
+                ln, off = hi >> 24, hi & 0xFFFFFF
+                if ln == 255:
+                    ln = struct.unpack_from("<I", pool, off)[0]
+                    off += 4
+                return pool[off:off + ln]
+
+            s, i, acc, m, miss = 0, 0, b"", -1, None
+            if sinfo[0] & S_HAS_FINAL:
+                m = 0
+            decided = bool(sinfo[0] & S_DECIDED)
+            while not decided and p + i < len(payload):
+                e = rows[s * 256 + payload[p + i]]
+                lo, hi = e & 0xFFFFFFFF, e >> 32
+                if lo & 0xFFFFFF == 0xFFFFFE:
+                    miss = s
+                    break
+                if lo & 0xFFFFFF == 0xFFFFFD:
+                    raise Diverged()
+                if lo & 0xFFFFFF == DEAD:
+                    break
+                acc += ref(hi)
+                s = lo & 0xFFFFFF
+                i += 1
+                if lo & E_MARK:
+                    m = i
+                if lo & E_DECIDED:
+                    decided = True
+            if miss is not None:
+                prog.lazy_build([miss], 0)
+                self.lazy_builds += 1
+                continue
+            sf = sinfo[s] & 0xFFFFFFFF
+            if sf & S_DIVERGE:
+                raise Diverged()
+            if not sf & S_HAS_FINAL:
+                return -1, b""
+            return m, acc + ref(sinfo[s] >> 32)
+
     def scan(self, data: bytes) -> bytes:
         """The reference's scan driver over getline records (trre_nft.c:775-790), tables from the blob."""
-        att = self.attempt_backtrack if self.h["exec_kind"] == 2 else self.attempt
+        att = {2: self.attempt_backtrack, 3: self.attempt_lazy}.get(self.h["exec_kind"], self.attempt)
         out = bytearray()
         pos, n = 0, len(data)
         while pos < n:

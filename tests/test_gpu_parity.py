@@ -363,3 +363,40 @@ def test_random_patterns_on_inputs_that_span_many_tiles(seed):
             got = prog.scan(data)
             assert got == want, (pat, flavor, fp, prog.info)
     assert sum(seen.values()) >= 8, seen
+
+
+# ---- TRRE_EXEC_LAZY: rows built on demand, the GPU reports what it misses (trre_dft.c:1135-1175) ----------------
+
+@pytest.mark.parametrize("expr", ["(a|b)*a(a|b){15}", "(a|b)*(a:x)(a|b){15}", "(a|b)*(a:x|b:y)(a|b){16}c", "(a:x)*b|(a:y)*c",
+                                  "((a|b)(a|b)(a|b))*(a:1)(a|b){17}c"])
+def test_lazy_tables_on_the_gpu(expr):
+    prog = T.compile(expr, DFT)
+    assert prog.exec_kind == T.EXEC_LAZY, prog.info
+    for seed, alphabet, hi, size in ((71, b"ab", 60, 1 << 18), (72, b"abc ", 400, 1 << 20), (73, b"ab", 5, 1 << 16)):
+        data = _ab_text(seed, size, alphabet, 0, hi)
+        rc, want, _ = oracle_run(expr.encode(), data, flavor=DFT)
+        assert rc == 0
+        assert prog.scan(data) == want, (expr, seed)
+    for data in (b"", b"a", b"ab\n", b"ab\0ab\nab", b"a" * 3000 + b"b\n", b"\n\n"):
+        check(expr, DFT, data)
+    q = T.from_blob(prog.blob())                          # what a rank gets from the broadcast
+    data = _ab_text(74, 1 << 16, b"abc", 0, 80)
+    assert q.scan(data) == oracle_run(expr.encode(), data, flavor=DFT)[1]
+
+
+def test_dfs_executor_has_the_reference_stack_capacity():
+    """trre's stack holds 65536 entries (trre_nft.c:34-36, 548-556); the DFS executor starts with 8192 per thread and
+    repeats the scan with the reference's capacity when a line needs more."""
+    expr = "(a:x)*b|a"
+    prog = T.compile(expr, NFT)
+    assert prog.exec_kind == T.EXEC_BACKTRACK
+    for run in (20000, 60000):
+        data = b"ab\n" + b"a" * run + b"\n" + b"aaab\n"
+        rc, want, _ = oracle_run(expr.encode(), data, flavor=NFT)
+        assert rc == 0 and prog.scan(data) == want, run
+    data = b"a" * 70000 + b"\n"
+    rc, _, err = oracle_run(expr.encode(), data, flavor=NFT)
+    assert rc == 1 and "stack max capacity" in err
+    with pytest.raises(T.TrreError) as ei:
+        T.compile(expr, NFT).scan(data)
+    assert ei.value.code == 5 and "stack max capacity reached" in ei.value.text

@@ -17,11 +17,18 @@ GOLDEN = load_golden()
 
 def sim_scan(expr, flavor, data):
     prog = T.compile(expr, flavor)
-    return prog, Blob(prog.blob()).scan(data)
+    return prog, blob_of(prog).scan(data)
+
+
+def blob_of(prog):
+    b = Blob(prog.blob())
+    if prog.exec_kind == T.EXEC_LAZY:
+        b.attach_lazy(prog)
+    return b
 
 
 def test_golden_scan_vectors_through_compiled_tables():
-    n = 0
+    n, refused, kinds = 0, 0, {}
     for v in GOLDEN:
         if v["mode"] != SCAN or v["all"]:
             continue
@@ -32,16 +39,18 @@ def test_golden_scan_vectors_through_compiled_tables():
                 assert v["rc"] == 1 and e.text == v["err"], (v["expr"], e.text, v["err"])
             else:
                 assert e.code == 2, (v["expr"], e.code)     # refused (limits): never a wrong answer
+                refused += v["rc"] == 0
             continue
         if v["rc"] != 0:
             continue
         try:
-            out = Blob(prog.blob()).scan(v["data"])
+            out = blob_of(prog).scan(v["data"])
         except Diverged:
             continue
         assert out == v["out"], (v["tag"], v["expr"], v["flavor"], v["data"], out, v["out"], prog.info)
         n += 1
-    assert n > 400
+        kinds[prog.exec_kind] = kinds.get(prog.exec_kind, 0) + 1
+    assert n > 400 and refused == 0 and kinds.get(T.EXEC_LAZY, 0) >= 15, (n, refused, kinds)
 
 
 def test_golden_match_vectors_through_match_host():
@@ -94,7 +103,7 @@ def test_random_patterns_tables_vs_oracle(seed):
                 continue
             kinds.add(prog.exec_kind)
             try:
-                out = Blob(prog.blob()).scan(data)
+                out = blob_of(prog).scan(data)
             except Diverged:
                 continue
             assert rc == 0 and out == want, (pat, fl, data, out, want, prog.info)
@@ -233,3 +242,18 @@ def test_gram_tables_of_the_dictionary():
     assert b.h["gram_entries"] == b.ncls ** 4
     text = bytes(T.synth_text(12, 6000, words[:80], 0.3, True))
     assert b.scan_gram(text) == oracle_run(expr.encode(), text, flavor=DFT)[1]
+
+
+def test_lazy_tables_for_automata_too_large_to_build_ahead():
+    """trre_dft determinizes only along the input (trre_dft.c:1135-1175): (a|b)*a(a|b){15} has 2^16 reachable
+    dstates but a short input visits a handful.  The DFT flavour keeps the builder and fills rows on demand."""
+    for expr in ("(a|b)*a(a|b){15}", "(a|b)*(a:x)(a|b){15}", "(a:x)*b|(a:y)*c"):
+        p = T.compile(expr, DFT)
+        assert p.exec_kind == T.EXEC_LAZY, (expr, p.info)
+        b = blob_of(p)
+        data = b"abbabababbbabaabababbbbbabababbaaaabab\nab\naaaaaaaaaaaaaaaaaaaaaaaaaaaaaaaaaaaab\nbbbbc\naaaac\n" * 2
+        rc, want, _ = oracle_run(expr.encode(), data, flavor=DFT)
+        assert rc == 0 and b.scan(data) == want, expr
+        assert 0 < b.lazy_builds < 400
+        q = T.from_blob(p.blob())                      # the broadcast blob rebuilds the same lazy program
+        assert q.exec_kind == T.EXEC_LAZY and blob_of(q).scan(data) == want

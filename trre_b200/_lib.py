@@ -3,7 +3,7 @@ import ctypes
 import os
 
 FLAVOR_NFT, FLAVOR_DFT = 0, 1
-EXEC_BYTEMAP, EXEC_TABLE, EXEC_BACKTRACK = 0, 1, 2
+EXEC_BYTEMAP, EXEC_TABLE, EXEC_BACKTRACK, EXEC_LAZY = 0, 1, 2, 3
 FAST_NONE, FAST_BYTEMAP, FAST_MATCH, FAST_BYTEMAP_VAR, FAST_MATCH_VAR, FAST_INPLACE = 0, 1, 2, 3, 4, 5
 
 OK, E_PATTERN, E_UNSUPPORTED, E_CUDA, E_NOSPACE, E_STACK, E_ARG, E_ASSERT = 0, 1, 2, 3, 4, 5, 7, 134
@@ -53,6 +53,11 @@ def _lib():
     L.trre_prog_blob.argtypes = [vp, ctypes.POINTER(sz)]
     L.trre_prog_from_blob.restype = ctypes.c_int
     L.trre_prog_from_blob.argtypes = [vp, sz, ctypes.POINTER(vp), ctypes.c_char_p, sz]
+    L.trre_lazy_build.restype = ctypes.c_int
+    L.trre_lazy_build.argtypes = [vp, ctypes.POINTER(ctypes.c_uint32), sz, ctypes.c_uint32]
+    L.trre_lazy_view.restype = ctypes.c_int
+    L.trre_lazy_view.argtypes = [vp, ctypes.POINTER(ctypes.c_uint32), ctypes.POINTER(vp), ctypes.POINTER(vp),
+                                 ctypes.POINTER(vp), ctypes.POINTER(sz)]
     L.trre_prog_bytemap.restype = ctypes.c_int
     L.trre_prog_bytemap.argtypes = [vp, ctypes.c_char_p]
     L.trre_scan.restype = ctypes.c_int
@@ -138,6 +143,21 @@ class Program:
         if rc:
             raise TrreError(rc, "program is not a byte map")
         return buf.raw
+
+    def lazy_build(self, states, extra=0):
+        """TRRE_EXEC_LAZY: build the rows of `states` (+ `extra` more, breadth first)."""
+        arr = (ctypes.c_uint32 * len(states))(*states)
+        rc = _lib().trre_lazy_build(self._h, arr, len(states), extra)
+        if rc:
+            raise TrreError(rc, _last_error())
+
+    def lazy_view(self):
+        """TRRE_EXEC_LAZY: (n_states, rows address, sinfo address, pool address, pool bytes) of the tables built so far."""
+        n, rows, sinfo, pool, pb = ctypes.c_uint32(), ctypes.c_void_p(), ctypes.c_void_p(), ctypes.c_void_p(), ctypes.c_size_t()
+        rc = _lib().trre_lazy_view(self._h, ctypes.byref(n), ctypes.byref(rows), ctypes.byref(sinfo), ctypes.byref(pool), ctypes.byref(pb))
+        if rc:
+            raise TrreError(rc, "not a lazily built program")
+        return n.value, rows.value, sinfo.value, pool.value, pb.value
 
     def match(self, data, all_=False, scan=False) -> bytes:
         """`-m` / `-ma` (scan=False) or scan-mode `-a` (scan=True): host C++, not a GPU path."""

@@ -107,6 +107,40 @@ class Determinizer {
     std::vector<RawState> states;
 
     void run() {
+        init();
+        for (uint32_t s = 0; s < states.size(); ++s) expand(s);
+    }
+
+    // one state's row: its transitions on every byte, creating the target states (the step trre_dft takes lazily,
+    // trre_dft.c:1135-1175; the eager construction takes it for every reachable state)
+    void expand(uint32_t s) {
+        if (states[s].flags & DSA_S_DECIDED) return;              // the attempt ends here
+        if (flavor_ == TRRE_FLAVOR_DFT) expand_dft(s); else expand_nft(s);
+    }
+
+    // DFT flavour, lazy use: whether a freshly created state is final is needed by the transitions INTO it, before
+    // its own row exists - the reference computes it at creation (trre_dft.c:1164-1174)
+    void finality_only(uint32_t sid) {
+        if (flavor_ != TRRE_FLAVOR_DFT || sid == 0) return;
+        ++gen_;
+        arrivals_.clear();
+        const ItemList items = states[sid].items;
+        for (const Item &it : items) {
+            std::string o = it.w;
+            close_dft(g_.st[it.q].a, o);
+        }
+        for (const Arrival &a : arrivals_) {
+            const NftState &n = g_.st[a.q];
+            if (n.op == N_FINAL || (n.op == N_CONS && n.val == 0)) {
+                states[sid].flags = DSA_S_HAS_FINAL | DSA_S_DECIDED;
+                states[sid].fin_id = pool_.intern(a.w);
+                break;
+            }
+        }
+        arrivals_.clear();
+    }
+
+    void init() {
         ItemList init;
         uint32_t flags0 = 0;
         if (flavor_ == TRRE_FLAVOR_DFT) {
@@ -120,10 +154,6 @@ class Determinizer {
             flags0 = flags_of(init);
         }
         add_state(std::move(init), flags0);
-        for (uint32_t s = 0; s < states.size(); ++s) {
-            if (states[s].flags & DSA_S_DECIDED) continue;       // the attempt ends here
-            if (flavor_ == TRRE_FLAVOR_DFT) expand_dft(s); else expand_nft(s);
-        }
     }
 
   private:
@@ -374,6 +404,7 @@ class PoolWriter {
     explicit PoolWriter(const StringPool &sp) : sp_(sp), refs_(sp.count(), 0xFFFFFFFFu) {}
     // -> hi word: off(24) | len(8)
     uint32_t ref(uint32_t id) {
+        if (id >= refs_.size()) refs_.resize(sp_.count(), 0xFFFFFFFFu);     // strings interned since (lazy construction)
         if (refs_[id] != 0xFFFFFFFFu) return refs_[id];
         const std::string &s = sp_.get(id);
         uint32_t r;
@@ -836,14 +867,10 @@ std::vector<uint8_t> compile_to_blob(const char *expr, int flavor, const Compile
             det.run();
             analyse_and_pack(det.states, sp, flavor, lim, P);
         } catch (const PatternError &pe) {
-            if (flavor == TRRE_FLAVOR_DFT || pe.code != TRRE_E_UNSUPPORTED) throw;
+            if (pe.code != TRRE_E_UNSUPPORTED) throw;
             tables = false;
         } catch (const NotSubsequential &ns) {
             if (std::getenv("TRRE_DEBUG")) std::fprintf(stderr, "trre_b200: table construction abandoned: %s\n", ns.why);
-            if (flavor == TRRE_FLAVOR_DFT)
-                throw PatternError{TRRE_E_UNSUPPORTED,
-                                   std::string("error: transducer is not determinizable within limits (") + ns.why +
-                                       "); trre_dft builds states for ever on such input\n"};
             tables = false;
         }
     }
@@ -852,12 +879,127 @@ std::vector<uint8_t> compile_to_blob(const char *expr, int flavor, const Compile
         P = Program();
         P.flavor = flavor;
         P.flags = keep;
-        P.exec_kind = TRRE_EXEC_BACKTRACK;
+        // no table ahead of time.  DFT flavour: build rows on demand, as trre_dft itself does (LazyDsa); NFT flavour:
+        // the reference's own DFS on the GPU
+        P.exec_kind = flavor == TRRE_FLAVOR_DFT ? TRRE_EXEC_LAZY : TRRE_EXEC_BACKTRACK;
         P.n_classes = 1;
         for (int c = 0; c < 256; ++c) { P.classmap[c] = 0; P.lut[c] = (uint8_t)c; P.startrow[c] = 1; }
         P.max_depth = 0xFFFFFFFFu;
     }
     return assemble(P, g);
+}
+
+// ---- LazyDsa ---------------------------------------------------------------------------------------------------------
+
+struct LazyDsa::Impl {
+    Nft g;
+    int flavor;
+    CompileLimits lim;
+    StringPool sp;
+    Determinizer det;
+    PoolWriter pw;
+    std::vector<uint64_t> rows, sinfo;
+    std::vector<uint32_t> log;
+    std::vector<uint8_t> built, poisoned;
+
+    // a closure that does not terminate (epsilon cycle, with or without output) is not a resource limit: the reference
+    // would recurse for ever if the input ever led there.  Such states are poisoned, not fatal - the input may never
+    // reach them (a row is built for all 256 bytes at once, the reference only follows the byte it sees).
+    static bool is_runaway(const char *why) { return std::strcmp(why, "residual limit") == 0; }
+
+    static CompileLimits lazy_limits() {
+        CompileLimits l;
+        l.max_states = 1u << 18;                   // 2 KB of row per state on the device
+        l.max_build_bytes = 2048ull << 20;
+        l.max_residual = 1u << 16;
+        l.max_work = ~0ull >> 1;
+        return l;
+    }
+    Impl(const Nft &gg, int fl) : g(gg), flavor(fl), lim(lazy_limits()), det(g, fl, lim, sp), pw(sp) {
+        det.init();
+        sync_states();
+    }
+    // rows / sinfo for states created since the last call
+    void sync_states() {
+        const size_t n = det.states.size();
+        const size_t old = sinfo.size();
+        if (n == old) return;
+        rows.resize(n * 256, pack64(LAZY_UNBUILT, 0));
+        sinfo.resize(n);
+        built.resize(n, 0);
+        poisoned.resize(n, 0);
+        for (size_t s = old; s < n; ++s) {
+            try {
+                det.finality_only((uint32_t)s);
+            } catch (const NotSubsequential &ns) {
+                if (!is_runaway(ns.why)) throw;
+                poisoned[s] = 1;
+            } catch (const PatternError &) {                   // recursion depth
+                poisoned[s] = 1;
+            }
+            const RawState &st = det.states[s];
+            sinfo[s] = pack64(st.flags, (st.flags & DSA_S_HAS_FINAL) ? pw.ref(st.fin_id) : 0);
+        }
+    }
+    void build_row(uint32_t s) {
+        if (s >= built.size() || built[s]) return;
+        bool runaway = poisoned[s] != 0;
+        if (!runaway) {
+            try {
+                det.expand(s);
+            } catch (const NotSubsequential &ns) {
+                if (!is_runaway(ns.why)) throw;
+                runaway = true;
+            } catch (const PatternError &) {
+                runaway = true;
+            }
+        }
+        sync_states();                                    // the targets' flags are needed by the entries below
+        RawState &st = det.states[s];
+        uint64_t *row = rows.data() + (size_t)s * 256;
+        for (int c = 0; c < 256; ++c) row[c] = pack64(runaway ? LAZY_POISON : DSA_DEAD, 0);
+        if (runaway) st.edges.clear();
+        for (const RawEdge &e : st.edges) {
+            if (poisoned[e.next]) { row[e.byte] = pack64(LAZY_POISON, 0); continue; }
+            const uint32_t tf = det.states[e.next].flags;
+            const bool decided = (tf & DSA_S_DECIDED) != 0;
+            const bool mark = e.mark || (flavor == TRRE_FLAVOR_DFT && decided);
+            const uint32_t lo = e.next | (mark ? (uint32_t)DSA_E_MARK : 0u) | (decided ? (uint32_t)DSA_E_DECIDED : 0u) |
+                                ((tf & DSA_S_HAS_FINAL) ? (uint32_t)DSA_E_HASFINAL : 0u) |
+                                ((tf & DSA_S_DIVERGE) ? (uint32_t)DSA_E_DIVERGE : 0u);
+            row[e.byte] = pack64(lo, pw.ref(e.out_id));
+        }
+        std::vector<RawEdge>().swap(st.edges);            // the packed row is what remains
+        built[s] = 1;
+        sinfo[s] |= DSA_S_ROW_BUILT;
+        log.push_back(s);
+    }
+};
+
+LazyDsa::LazyDsa(const Nft &g, int flavor) : im_(new Impl(g, flavor)) {}
+LazyDsa::~LazyDsa() { delete im_; }
+uint32_t LazyDsa::n_states() const { return (uint32_t)im_->sinfo.size(); }
+const std::vector<uint64_t> &LazyDsa::rows() const { return im_->rows; }
+const std::vector<uint64_t> &LazyDsa::sinfo() const { return im_->sinfo; }
+const std::vector<uint8_t> &LazyDsa::pool() const { return im_->pw.bytes; }
+const std::vector<uint32_t> &LazyDsa::log() const { return im_->log; }
+uint32_t LazyDsa::start_info() const { return (uint32_t)(im_->sinfo[0] & 0xFFFFFFFFu); }
+
+void LazyDsa::build(const uint32_t *req, size_t n_req, uint32_t extra) {
+    try {
+        std::vector<uint32_t> frontier;
+        size_t first_new = im_->sinfo.size();
+        for (size_t k = 0; k < n_req; ++k) im_->build_row(req[k]);
+        // breadth first behind the requests: the states they created, then the states those create ...
+        for (size_t s = first_new; s < im_->sinfo.size() && extra; ++s) {
+            if (im_->built[s] || (im_->det.states[s].flags & DSA_S_DECIDED)) continue;
+            im_->build_row((uint32_t)s);
+            --extra;
+        }
+    } catch (const NotSubsequential &ns) {
+        throw PatternError{TRRE_E_UNSUPPORTED,
+                           std::string("error: the scan automaton outgrew the on-demand table limits (") + ns.why + ")\n"};
+    }
 }
 
 bool blob_is_valid(const void *blob, size_t nbytes, std::string *why) {

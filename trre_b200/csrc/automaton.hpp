@@ -124,6 +124,39 @@ struct CompileLimits {
 // Builds the whole program blob for `expr`.  Throws PatternError.
 std::vector<uint8_t> compile_to_blob(const char *expr, int flavor, const CompileLimits &lim = CompileLimits());
 
+// ---- lazy construction (TRRE_EXEC_LAZY) -----------------------------------------------------------------------------
+// trre_dft determinizes lazily: a dstate's row is only built for the bytes the input actually shows it
+// (trre_dft.c:1135-1175), so it answers transducers whose full subset construction is astronomically large.  When the
+// eager construction above runs into its limits, the same expansion step is kept alive on the host and driven by the
+// GPU: the per-line kernel walks rows indexed by the raw byte; a state whose row is missing is reported back
+// (ST_MISS + request list), the host builds that row (plus a few behind it, breadth first), uploads it and the pass is
+// repeated.  The host only ever COMPILES - which rows exist never changes what a row says - the scan stays on the GPU.
+constexpr uint32_t LAZY_UNBUILT = 0x00FFFFFEu;     // `next` value of every entry of a row that has not been built
+constexpr uint32_t LAZY_POISON  = 0x00FFFFFDu;     // `next` value of an entry whose target's closure does not terminate:
+                                                    // trre_dft recurses for ever there (nft_step_, trre_dft.c:874-907)
+constexpr uint32_t DSA_S_ROW_BUILT = 8u;            // sinfo flag
+
+class LazyDsa {
+  public:
+    LazyDsa(const Nft &g, int flavor);
+    ~LazyDsa();
+    LazyDsa(const LazyDsa &) = delete;
+    LazyDsa &operator=(const LazyDsa &) = delete;
+    // Build the rows of the requested states and up to `extra` more rows breadth first behind them.
+    // Throws PatternError{TRRE_E_UNSUPPORTED} when the limits (states, memory, residual output) are reached.
+    void build(const uint32_t *req, size_t n_req, uint32_t extra);
+    uint32_t n_states() const;
+    const std::vector<uint64_t> &rows() const;     // [n_states * 256] by raw byte: lo = next | DSA_E_*, hi = out ref
+    const std::vector<uint64_t> &sinfo() const;    // [n_states]: lo = DSA_S_*, hi = fin ref
+    const std::vector<uint8_t> &pool() const;
+    const std::vector<uint32_t> &log() const;      // states whose row exists, in build order
+    uint32_t start_info() const;
+
+  private:
+    struct Impl;
+    Impl *im_;
+};
+
 // Validates a blob received from elsewhere (e.g. broadcast from rank 0).
 bool blob_is_valid(const void *blob, size_t nbytes, std::string *why);
 

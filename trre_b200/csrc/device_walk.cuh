@@ -16,7 +16,21 @@ enum : uint32_t {
     ST_DIVERGE     = 2u,    // an attempt entered an epsilon cycle (reference: stack max capacity)
     ST_STACK       = 4u,    // DFS stack of the backtracking executor overflowed
     ST_OBUF        = 8u,    // per-attempt output buffer of the backtracking executor overflowed
-    ST_NOSPACE     = 16u    // d_out too small
+    ST_NOSPACE     = 16u,   // d_out too small
+    ST_MISS        = 32u,   // lazy tables: a row the input needs has not been built yet (see LazyDev)
+    ST_RUNAWAY     = 64u    // lazy tables: the input leads into a closure that does not terminate (LAZY_POISON)
+};
+
+// TRRE_EXEC_LAZY: rows by raw byte, built on demand by the host between passes (automaton.hpp, LazyDsa)
+struct LazyDev {
+    const uint64_t *rows;          // [n_states * 256]
+    const uint64_t *sinfo;         // [n_states]
+    const uint8_t  *pool;
+    uint32_t *requested;           // [state capacity]: 1 once a state's row has been asked for
+    uint32_t *miss_list;           // [miss_cap] states whose row is missing
+    uint32_t *miss_count;
+    uint32_t  miss_cap;
+    uint32_t  start_info;
 };
 
 struct DevProg {
@@ -101,6 +115,56 @@ __device__ __forceinline__ long attempt_table(const DevProg &P, const uint8_t *_
         o.n += acc;
     }
     put_ref(o, P.pool, (uint32_t)(si >> 32));
+    return m;
+}
+
+// ---- lazy-table executor ------------------------------------------------------------------------------
+// attempt_table over rows indexed by the raw byte; a row that does not exist yet is reported (once per state) and
+// the attempt gives up with ST_MISS: the host builds the row and the pass is repeated.  Returns -2 on a miss.
+__device__ __forceinline__ long attempt_lazy(const LazyDev &L, const uint8_t *__restrict__ in,
+                                             size_t p, size_t lim, Sink &o, uint32_t &status) {
+    uint32_t s = 0, i = 0, acc = 0;
+    long m = (L.start_info & DSA_S_HAS_FINAL) ? 0 : -1;
+    bool decided = (L.start_info & DSA_S_DECIDED) != 0;
+    if (!decided) {
+        while (p + i < lim) {
+            const uint8_t c = __ldg(in + p + i);
+            if (c == 0 || c == '\n') break;                 // never consumed (rows are built for payload bytes only)
+            const uint64_t e = L.rows[(size_t)s * 256 + c];
+            const uint32_t lo = (uint32_t)e;
+            if ((lo & 0xFFFFFFu) == LAZY_UNBUILT) {
+                if (atomicExch(L.requested + s, 1u) == 0u) {
+                    const uint32_t k = atomicAdd(L.miss_count, 1u);
+                    if (k < L.miss_cap) L.miss_list[k] = s;
+                    else L.requested[s] = 0;                 // list full: ask again next pass
+                }
+                status |= ST_MISS;
+                return -2;
+            }
+            if ((lo & 0xFFFFFFu) == LAZY_POISON) { status |= ST_RUNAWAY; return -1; }
+            if ((lo & 0xFFFFFFu) == DSA_DEAD) break;
+            acc += ref_len(L.pool, (uint32_t)(e >> 32));
+            s = lo & 0xFFFFFFu;
+            ++i;
+            if (lo & DSA_E_MARK) m = i;
+            if (lo & DSA_E_DECIDED) { decided = true; break; }
+        }
+    }
+    const uint64_t si = L.sinfo[s];
+    const uint32_t sf = (uint32_t)si;
+    if (sf & DSA_S_DIVERGE) { status |= ST_DIVERGE; return -1; }
+    if (!(sf & DSA_S_HAS_FINAL)) return -1;
+    if (o.p) {
+        uint32_t t = 0;
+        for (uint32_t k = 0; k < i; ++k) {
+            const uint64_t e = L.rows[(size_t)t * 256 + __ldg(in + p + k)];
+            put_ref(o, L.pool, (uint32_t)(e >> 32));
+            t = (uint32_t)e & 0xFFFFFFu;
+        }
+    } else {
+        o.n += acc;
+    }
+    put_ref(o, L.pool, (uint32_t)(si >> 32));
     return m;
 }
 

@@ -64,6 +64,8 @@ struct DeviceState {
     // DFS scratch
     int32_t *bt_s = nullptr; uint32_t *bt_i = nullptr; uint32_t *bt_o = nullptr; uint8_t *bt_obuf = nullptr;
     size_t bt_threads = 0; uint32_t bt_cap = 0, bt_ocap = 0;
+    int bt_tier = 0;               // 0: 8192-entry stacks for every resident thread; 1: the reference's 65536 entries and
+                                   // 1 MiB of output per attempt, for few threads (entered when tier 0 overflows)
     int sm_count = 148;
     const uint32_t *vent = nullptr; const uint16_t *vpairlen = nullptr; const uint8_t *vpool = nullptr; uint32_t vpool_bytes = 0;
     // what the last enqueue left to do / to report
@@ -87,9 +89,20 @@ struct DeviceState {
     bool staged_attr = false;
     GramArgs gram{};               // k_gram tables (entries == 0: none)
     size_t gram_smem = 0;
+    bool gram_small = false;
+    const void *gram_fn = nullptr;
     SwarMap swar{};                // table-free byte map (n == 0: not of that form)
-    int swar_ctas = 2;
+    int swar_ctas = 2, swar_variant = 0;
+    // TRRE_EXEC_LAZY: device copies of the rows built so far (automaton.hpp, LazyDsa)
+    uint64_t *lz_rows = nullptr, *lz_sinfo = nullptr;
+    uint8_t *lz_pool = nullptr;
+    uint32_t *lz_requested = nullptr, *lz_miss = nullptr;      // lz_miss: [0] count, [1..] list
+    uint32_t *h_lz_miss = nullptr;                               // pinned mirror
+    size_t lz_cap_states = 0, lz_cap_pool = 0, lz_up_log = 0, lz_up_pool = 0;
+    int lz_rounds = 0;
 };
+
+constexpr uint32_t kMissCap = 1u << 16;
 
 }  // namespace
 
@@ -98,9 +111,26 @@ struct trre_prog {
     BlobHeader hdr;
     std::mutex mu;
     std::map<int, DeviceState *> dev;
+    LazyDsa *lazy = nullptr;       // TRRE_EXEC_LAZY: the on-demand table builder, shared by all devices
+    std::mutex lazy_mu;
 };
 
 namespace {
+
+// TRRE_EXEC_LAZY programs keep their table builder: the flat NFT comes back out of the blob (so a broadcast blob
+// works on every rank without recompiling the expression)
+void attach_lazy(trre_prog *p) {
+    if (p->hdr.exec_kind != TRRE_EXEC_LAZY) return;
+    Nft g;
+    const NftFlat *nf = reinterpret_cast<const NftFlat *>(p->blob.data() + p->hdr.off_nft);
+    g.st.resize(p->hdr.nft_states);
+    for (uint32_t k = 0; k < p->hdr.nft_states; ++k) {
+        g.st[k].op = nf[k].op; g.st[k].val = nf[k].val; g.st[k].a = nf[k].a; g.st[k].b = nf[k].b;
+    }
+    g.start = p->hdr.nft_start;
+    g.has_init_join = p->hdr.flavor == TRRE_FLAVOR_DFT;
+    p->lazy = new LazyDsa(g, (int)p->hdr.flavor);
+}
 
 #define CUDA_TRY(expr)                                                                         \
     do {                                                                                       \
@@ -154,6 +184,18 @@ int plan_match(const BlobHeader &h, size_t warp_bytes, size_t budget, int sm_cou
     }
     mp->blocks = sm_count * (per_sm < 1 ? 1 : per_sm);
     return TRRE_OK;
+}
+
+const void *gram_kernel(uint32_t depth, bool small) {
+    switch (depth) {
+        case 1: return small ? (const void *)k_gram<1, true> : (const void *)k_gram<1, false>;
+        case 2: return small ? (const void *)k_gram<2, true> : (const void *)k_gram<2, false>;
+        case 3: return small ? (const void *)k_gram<3, true> : (const void *)k_gram<3, false>;
+        case 4: return small ? (const void *)k_gram<4, true> : (const void *)k_gram<4, false>;
+        case 5: return small ? (const void *)k_gram<5, true> : (const void *)k_gram<5, false>;
+        case 6: return small ? (const void *)k_gram<6, true> : (const void *)k_gram<6, false>;
+        default: return nullptr;
+    }
 }
 
 int get_state(const trre_prog *cp, int device, DeviceState **out) {
@@ -210,7 +252,8 @@ int get_state(const trre_prog *cp, int device, DeviceState **out) {
             d->swar.half[k] = lo < 0x80u ? 0x80808080u : 0u;
             d->swar.delta[k] = delta;
         }
-        if (const char *e = std::getenv("TRRE_SWAR_CTAS")) { int v = std::atoi(e); if (v >= 1 && v <= 8) d->swar_ctas = v; }
+        if (const char *e = std::getenv("TRRE_SWAR_CTAS")) { int v = std::atoi(e); if (v >= 1 && v <= 16) d->swar_ctas = v; }
+        if (const char *e = std::getenv("TRRE_SWAR_VARIANT")) { int v = std::atoi(e); if (v >= 0 && v <= 2) d->swar_variant = v; }
     }
     if (h.flags & PF_MATCHABLE) {
         int rc2 = plan_match(h, (size_t)kMatchWarps * kWarpSmem, 108 * 1024, d->sm_count, OP_INPLACE, &d->mp);
@@ -232,16 +275,15 @@ int get_state(const trre_prog *cp, int device, DeviceState **out) {
         g.uniform_len = h.gram_len;
         g.gflags = h.gram_flags;
         const uint32_t words = (h.gram_entries + 31) / 32;
-        g.bits_replicated = words <= 128 ? 1u : 0u;
+        d->gram_small = h.gram_entries <= kGramSmallEntries;
         g.gout_in_smem = h.gram_entries <= 4096 ? 1u : 0u;
         g.pool_in_smem = (h.gpool_bytes && h.gpool_bytes <= 4096) ? 1u : 0u;
-        d->gram_smem = 256 * 32 * 4 + (size_t)((words * (g.bits_replicated ? 32u : 1u) + 3) & ~3u) * 4 +
+        d->gram_smem = 256 * 32 * 4 + (d->gram_small ? (size_t)h.gram_entries * 128 : (size_t)((words + 3) & ~3u) * 4) +
                        (g.gout_in_smem ? (size_t)((h.gram_entries + 3) & ~3u) * 4 : 0) +
-                       (g.pool_in_smem ? ((h.gpool_bytes + 15) & ~15u) : 0) + (size_t)kGramWarps * kWarpSmem;
-        const void *fns[6] = {(const void *)k_gram<1>, (const void *)k_gram<2>, (const void *)k_gram<3>,
-                              (const void *)k_gram<4>, (const void *)k_gram<5>, (const void *)k_gram<6>};
-        if (h.gram_depth >= 1 && h.gram_depth <= 6 && d->gram_smem <= 220 * 1024) {
-            CUDA_TRY(cudaFuncSetAttribute(fns[h.gram_depth - 1], cudaFuncAttributeMaxDynamicSharedMemorySize, (int)d->gram_smem));
+                       (g.pool_in_smem ? ((h.gpool_bytes + 15) & ~15u) : 0) + (size_t)kGramWarps * kGramWarpSmem;
+        d->gram_fn = gram_kernel(h.gram_depth, d->gram_small);
+        if (d->gram_fn && d->gram_smem <= 220 * 1024) {
+            CUDA_TRY(cudaFuncSetAttribute(d->gram_fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)d->gram_smem));
         } else {
             g.entries = 0;
         }
@@ -264,10 +306,14 @@ int ensure_workspace(DeviceState *d, size_t n_chunks, size_t n_groups, bool back
         CUDA_TRY(cudaMalloc(&d->d_gsum, n_groups * sizeof(unsigned long long)));
         d->cap_groups = n_groups;
     }
-    if (backtrack && resident_threads > d->bt_threads) {
-        // per-thread DFS stack (the reference allows 65536 entries, trre_nft.c:36/551) and output buffer
-        uint32_t cap = 8192, ocap = 8192;
-        if (const char *e = std::getenv("TRRE_BT_STACK")) { long v = std::atol(e); if (v >= 64 && v <= 65536) cap = (uint32_t)v; }
+    // per-thread DFS stack and output buffer.  The reference's stack holds 65536 entries before "stack max capacity
+    // reached" (32 doubled while <= 100000, trre_nft.c:34-36, 548-556) and its output buffer grows without bound;
+    // almost no line needs that, so every resident thread gets 8192 / 8 KB first and a scan that overflows them is
+    // repeated (collect) with the reference's capacity on a small grid.
+    uint32_t cap = 8192, ocap = 8192;
+    if (const char *e = std::getenv("TRRE_BT_STACK")) { long v = std::atol(e); if (v >= 64 && v <= 65536) cap = (uint32_t)v; }
+    if (d->bt_tier) { cap = 65536; ocap = 1u << 20; }
+    if (backtrack && (resident_threads > d->bt_threads || cap != d->bt_cap || ocap != d->bt_ocap)) {
         if (d->bt_s) { cudaFree(d->bt_s); cudaFree(d->bt_i); cudaFree(d->bt_o); cudaFree(d->bt_obuf); }
         d->bt_s = nullptr; d->bt_threads = 0;
         CUDA_TRY(cudaMalloc(&d->bt_s, resident_threads * cap * sizeof(int32_t)));
@@ -280,9 +326,57 @@ int ensure_workspace(DeviceState *d, size_t n_chunks, size_t n_groups, bool back
 }
 
 template <int MODE>
-void launch_lines(bool backtrack, int grid, cudaStream_t st, const LineArgs &a) {
-    if (backtrack) k_lines<MODE, true><<<grid, kLineThreads, 0, st>>>(a);
-    else k_lines<MODE, false><<<grid, kLineThreads, 0, st>>>(a);
+void launch_lines(int exec, int grid, cudaStream_t st, const LineArgs &a) {
+    if (exec == EXEC_DFS) k_lines<MODE, EXEC_DFS><<<grid, kLineThreads, 0, st>>>(a);
+    else if (exec == EXEC_LAZY) k_lines<MODE, EXEC_LAZY><<<grid, kLineThreads, 0, st>>>(a);
+    else k_lines<MODE, EXEC_TABLE><<<grid, kLineThreads, 0, st>>>(a);
+}
+
+__global__ void k_fill64(uint64_t *p, size_t n, uint64_t v) {
+    for (size_t k = (size_t)blockIdx.x * blockDim.x + threadIdx.x; k < n; k += (size_t)gridDim.x * blockDim.x) p[k] = v;
+}
+
+// TRRE_EXEC_LAZY: bring this device's copy of the tables up to date with the host builder
+int lazy_sync(trre_prog *p, DeviceState *d, cudaStream_t st) {
+    std::lock_guard<std::mutex> lock(p->lazy_mu);
+    LazyDsa &L = *p->lazy;
+    const size_t n = L.n_states();
+    if (n > d->lz_cap_states) {                               // grow: everything is uploaded again
+        const size_t cap = std::max<size_t>(2 * n, 4096);
+        if (d->lz_rows) { cudaFree(d->lz_rows); cudaFree(d->lz_sinfo); cudaFree(d->lz_requested); }
+        d->lz_rows = nullptr; d->lz_cap_states = 0; d->lz_up_log = 0;
+        CUDA_TRY(cudaMalloc(&d->lz_rows, cap * 256 * sizeof(uint64_t)));
+        CUDA_TRY(cudaMalloc(&d->lz_sinfo, cap * sizeof(uint64_t)));
+        CUDA_TRY(cudaMalloc(&d->lz_requested, cap * sizeof(uint32_t)));
+        k_fill64<<<d->sm_count * 4, 256, 0, st>>>(d->lz_rows, cap * 256, pack64(LAZY_UNBUILT, 0));
+        CUDA_TRY(cudaMemsetAsync(d->lz_requested, 0, cap * sizeof(uint32_t), st));
+        d->lz_cap_states = cap;
+    }
+    if (!d->lz_miss) {
+        CUDA_TRY(cudaMalloc(&d->lz_miss, (1 + kMissCap) * sizeof(uint32_t)));
+        CUDA_TRY(cudaMallocHost(&d->h_lz_miss, (1 + kMissCap) * sizeof(uint32_t)));
+    }
+    const std::vector<uint8_t> &pool = L.pool();
+    if (pool.size() > d->lz_cap_pool) {
+        const size_t cap = std::max<size_t>(2 * pool.size(), 1 << 16);
+        if (d->lz_pool) cudaFree(d->lz_pool);
+        d->lz_pool = nullptr; d->lz_cap_pool = 0; d->lz_up_pool = 0;
+        CUDA_TRY(cudaMalloc(&d->lz_pool, cap));
+        d->lz_cap_pool = cap;
+    }
+    if (pool.size() > d->lz_up_pool) {
+        CUDA_TRY(cudaMemcpyAsync(d->lz_pool + d->lz_up_pool, pool.data() + d->lz_up_pool, pool.size() - d->lz_up_pool, cudaMemcpyHostToDevice, st));
+        d->lz_up_pool = pool.size();
+    }
+    CUDA_TRY(cudaMemcpyAsync(d->lz_sinfo, L.sinfo().data(), n * sizeof(uint64_t), cudaMemcpyHostToDevice, st));
+    const std::vector<uint32_t> &log = L.log();
+    for (size_t k = d->lz_up_log; k < log.size(); ++k) {
+        const size_t s = log[k];
+        CUDA_TRY(cudaMemcpyAsync(d->lz_rows + s * 256, L.rows().data() + s * 256, 256 * sizeof(uint64_t), cudaMemcpyHostToDevice, st));
+    }
+    d->lz_up_log = log.size();
+    CUDA_TRY(cudaStreamSynchronize(st));                      // the host vectors may move once the lock is dropped
+    return TRRE_OK;
 }
 
 enum { PH_SIZE = 0, PH_ALL = 1, PH_WRITE = 2 };    // count+scan | count+scan+write | write (counts already there)
@@ -295,6 +389,9 @@ LineArgs make_args(DeviceState *d, const uint8_t *d_in, size_t n, uint8_t *d_out
     a.n_groups = (a.n_chunks + kLineThreads - 1) / kLineThreads;
     a.bt_s = d->bt_s; a.bt_i = d->bt_i; a.bt_o = d->bt_o; a.bt_obuf = d->bt_obuf;
     a.bt_cap = d->bt_cap; a.bt_ocap = d->bt_ocap;
+    a.L.rows = d->lz_rows; a.L.sinfo = d->lz_sinfo; a.L.pool = d->lz_pool;
+    a.L.requested = d->lz_requested; a.L.miss_count = d->lz_miss; a.L.miss_list = d->lz_miss ? d->lz_miss + 1 : nullptr;
+    a.L.miss_cap = kMissCap; a.L.start_info = 0;
     return a;
 }
 
@@ -308,7 +405,19 @@ int launch_fast(const trre_prog *p, DeviceState *d, const uint8_t *d_in, size_t 
                 uint32_t *status, cudaStream_t st) {
     const BlobHeader &h = p->hdr;
     const bool aligned = ((reinterpret_cast<uintptr_t>(d_in) ^ reinterpret_cast<uintptr_t>(d_out)) & 15) == 0;
-    if (h.exec_kind == TRRE_EXEC_BYTEMAP && aligned && d->swar.n) {
+    if (h.exec_kind == TRRE_EXEC_BYTEMAP && aligned && d->swar.n && d->swar_variant) {
+        const size_t nvec = n / 16 + 1;
+        const int grid = d->swar_variant == 1 ? d->sm_count * d->swar_ctas : (int)((nvec + 1023) / 1024);
+#define SWAR_LAUNCH(K, NR) K<NR><<<grid, 256, 0, st>>>(d_in, d_out, n, d->swar, d->P.lut, status)
+        if (d->swar_variant == 1) {
+            switch (d->swar.n) { case 1: SWAR_LAUNCH(k_bytemap_swar_v1, 1); break; case 2: SWAR_LAUNCH(k_bytemap_swar_v1, 2); break;
+                                 case 3: SWAR_LAUNCH(k_bytemap_swar_v1, 3); break; default: SWAR_LAUNCH(k_bytemap_swar_v1, 4); break; }
+        } else {
+            switch (d->swar.n) { case 1: SWAR_LAUNCH(k_bytemap_swar_v2, 1); break; case 2: SWAR_LAUNCH(k_bytemap_swar_v2, 2); break;
+                                 case 3: SWAR_LAUNCH(k_bytemap_swar_v2, 3); break; default: SWAR_LAUNCH(k_bytemap_swar_v2, 4); break; }
+        }
+#undef SWAR_LAUNCH
+    } else if (h.exec_kind == TRRE_EXEC_BYTEMAP && aligned && d->swar.n) {
         const int grid = d->sm_count * d->swar_ctas;
         switch (d->swar.n) {
             case 1: k_bytemap_swar<1><<<grid, kSwarThreads, 0, st>>>(d_in, d_out, n, d->swar, d->P.lut, status); break;
@@ -325,14 +434,8 @@ int launch_fast(const trre_prog *p, DeviceState *d, const uint8_t *d_in, size_t 
         size_t blocks = std::min<size_t>((size_t)d->sm_count, (n_tiles + 16 * kGramWarps - 1) / (16 * kGramWarps));
         if (blocks < 1) blocks = 1;
         g.tiles_per_warp = (n_tiles + blocks * kGramWarps - 1) / (blocks * kGramWarps);
-        switch (p->hdr.gram_depth) {
-            case 1: k_gram<1><<<(int)blocks, kGramThreads, d->gram_smem, st>>>(g); break;
-            case 2: k_gram<2><<<(int)blocks, kGramThreads, d->gram_smem, st>>>(g); break;
-            case 3: k_gram<3><<<(int)blocks, kGramThreads, d->gram_smem, st>>>(g); break;
-            case 4: k_gram<4><<<(int)blocks, kGramThreads, d->gram_smem, st>>>(g); break;
-            case 5: k_gram<5><<<(int)blocks, kGramThreads, d->gram_smem, st>>>(g); break;
-            default: k_gram<6><<<(int)blocks, kGramThreads, d->gram_smem, st>>>(g); break;
-        }
+        void *kargs[] = {&g};
+        CUDA_TRY(cudaLaunchKernel(d->gram_fn, dim3((unsigned)blocks), dim3(kGramThreads), kargs, d->gram_smem, st));
     } else if ((d->P.flags & PF_MATCHABLE) && d->P.row0 && aligned && (reinterpret_cast<uintptr_t>(d_in) & 15) == 0 && !std::getenv("TRRE_NO_MATCH_KERNEL")) {
         MatchArgs m{};
         m.P = d->P; m.in = d_in; m.out = d_out; m.n = n; m.status = status;
@@ -348,7 +451,7 @@ int launch_fast(const trre_prog *p, DeviceState *d, const uint8_t *d_in, size_t 
     } else {
         LineArgs a = make_args(d, d_in, n, d_out, n, status);
         int grid = (int)std::min<size_t>(a.n_groups, (size_t)d->sm_count * 64);
-        k_lines<MODE_INPLACE, false><<<grid, kLineThreads, 0, st>>>(a);
+        k_lines<MODE_INPLACE, EXEC_TABLE><<<grid, kLineThreads, 0, st>>>(a);
     }
     CUDA_TRY(cudaGetLastError());
     return TRRE_OK;
@@ -358,16 +461,20 @@ int launch_fast(const trre_prog *p, DeviceState *d, const uint8_t *d_in, size_t 
 int launch_general(const trre_prog *p, DeviceState *d, const uint8_t *d_in, size_t n, uint8_t *d_out,
                    size_t out_cap, cudaStream_t st, int phase, int *launches) {
     const bool backtrack = p->hdr.exec_kind == TRRE_EXEC_BACKTRACK;
+    const bool lazy = p->hdr.exec_kind == TRRE_EXEC_LAZY;
+    const int exec = backtrack ? EXEC_DFS : lazy ? EXEC_LAZY : EXEC_TABLE;
+    if (lazy) { int rc0 = lazy_sync(const_cast<trre_prog *>(p), d, st); if (rc0 != TRRE_OK) return rc0; }
     const size_t n_chunks = (n + kChunk - 1) / kChunk;
     const size_t n_groups = (n_chunks + kLineThreads - 1) / kLineThreads;
     // persistent-style grid: the DFS executor's scratch is per resident thread
-    int grid = (int)std::min<size_t>(n_groups, backtrack ? (size_t)d->sm_count : (size_t)d->sm_count * 64);
+    int grid = (int)std::min<size_t>(n_groups, backtrack ? (d->bt_tier ? (size_t)8 : (size_t)d->sm_count) : (size_t)d->sm_count * 64);
     if (grid < 1) grid = 1;
     int rc = ensure_workspace(d, n_chunks, n_groups, backtrack, (size_t)grid * kLineThreads);
     if (rc != TRRE_OK) return rc;
     if (phase != PH_WRITE) d->counts_kind = 1;
     LineArgs a = make_args(d, d_in, n, d_out, out_cap, d->d_status);
-    const bool staged = !backtrack && d->P.ctrans && !std::getenv("TRRE_NO_STAGED_LINES");
+    if (lazy) a.L.start_info = p->lazy->start_info();
+    const bool staged = !backtrack && !lazy && d->P.ctrans && !std::getenv("TRRE_NO_STAGED_LINES");
     StagedArgs sa{};
     size_t smem_count = 0, smem_write = 0;
     int grid_s = grid;
@@ -388,8 +495,40 @@ int launch_general(const trre_prog *p, DeviceState *d, const uint8_t *d_in, size
         grid_s = (int)std::min<size_t>(n_groups, (size_t)d->sm_count * 3);
         if (grid_s < 1) grid_s = 1;
         if (phase != PH_WRITE) k_lines_s<MODE_COUNT><<<grid_s, kLineThreads, smem_count, st>>>(sa);
+    } else if (lazy && phase != PH_WRITE) {
+        // count passes until the input meets no missing row: each pass reports the states whose rows it needed, the
+        // host builds them (and a few behind them), the device copy is refreshed.  trre_dft.c:1135-1175, batched.
+        trre_prog *mp = const_cast<trre_prog *>(p);
+        for (int round = 0;; ++round) {
+            CUDA_TRY(cudaMemsetAsync(d->lz_miss, 0, sizeof(uint32_t), st));
+            launch_lines<MODE_COUNT>(exec, grid, st, a);
+            *launches += 1;
+            CUDA_TRY(cudaGetLastError());
+            CUDA_TRY(cudaMemcpyAsync(d->h_status, d->d_status, sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
+            CUDA_TRY(cudaMemcpyAsync(d->h_lz_miss, d->lz_miss, sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
+            CUDA_TRY(cudaStreamSynchronize(st));
+            if (!(*d->h_status & ST_MISS)) break;
+            const uint32_t cnt = std::min<uint32_t>(d->h_lz_miss[0], kMissCap);
+            CUDA_TRY(cudaMemcpy(d->h_lz_miss + 1, d->lz_miss + 1, cnt * sizeof(uint32_t), cudaMemcpyDeviceToHost));
+            try {
+                std::lock_guard<std::mutex> lock(mp->lazy_mu);
+                mp->lazy->build(d->h_lz_miss + 1, cnt, 256);
+            } catch (const PatternError &pe) {
+                g_last_error = pe.text;
+                return pe.code;
+            } catch (const std::bad_alloc &) {
+                g_last_error = "error: out of memory while building tables on demand\n";
+                return TRRE_E_UNSUPPORTED;
+            }
+            int rc2 = lazy_sync(mp, d, st);
+            if (rc2 != TRRE_OK) return rc2;
+            a.L.rows = d->lz_rows; a.L.sinfo = d->lz_sinfo; a.L.pool = d->lz_pool; a.L.requested = d->lz_requested;
+            CUDA_TRY(cudaMemsetAsync(d->d_status, 0, sizeof(uint32_t), st));
+            d->lz_rounds = round + 1;
+        }
+        *launches -= 1;                                       // the last pass is the one counted below
     } else if (phase != PH_WRITE) {
-        launch_lines<MODE_COUNT>(backtrack, grid, st, a);
+        launch_lines<MODE_COUNT>(exec, grid, st, a);
     }
     if (phase != PH_WRITE) {
         k_scan_groups<<<1, kScanThreads, 0, st>>>(d->d_gsum, n_groups, d->d_total);
@@ -397,7 +536,7 @@ int launch_general(const trre_prog *p, DeviceState *d, const uint8_t *d_in, size
     }
     if (phase != PH_SIZE) {
         if (staged) k_lines_s<MODE_WRITE><<<std::min(grid_s, d->sm_count * 2), kLineThreads, smem_write, st>>>(sa);
-        else launch_lines<MODE_WRITE>(backtrack, grid, st, a);
+        else launch_lines<MODE_WRITE>(exec, grid, st, a);
         *launches += 1;
     }
     CUDA_TRY(cudaGetLastError());
@@ -522,7 +661,11 @@ int enqueue_scan(const trre_prog *p, DeviceState *d, const uint8_t *d_in, size_t
 
 int status_to_rc(uint32_t s) {
     if (s & (ST_DIVERGE | ST_STACK)) { g_last_error = "error: stack max capacity reached\n"; return TRRE_E_STACK; }
-    if (s & ST_OBUF) { g_last_error = "error: per-attempt output exceeds the DFS executor's buffer\n"; return TRRE_E_UNSUPPORTED; }
+    if (s & ST_OBUF) { g_last_error = "error: one match attempt produced more than 1 MiB of output (limit of the GPU DFS executor, not of trre)\n"; return TRRE_E_UNSUPPORTED; }
+    if (s & ST_RUNAWAY) {
+        g_last_error = "error: the input leads into an epsilon cycle of the transducer (trre_dft recurses for ever there)\n";
+        return TRRE_E_UNSUPPORTED;
+    }
     if (s & ST_NOSPACE) { g_last_error = "output buffer too small"; return TRRE_E_NOSPACE; }
     return TRRE_OK;
 }
@@ -540,6 +683,20 @@ int collect(const trre_prog *p, DeviceState *d, cudaStream_t st, size_t *out_n) 
         int rc = clear_status(d, st);
         if (rc != TRRE_OK) return rc;
         d->pend_fast = false;
+        d->status_dirty = true;
+        rc = launch_general(p, d, d->pend_in, d->pend_n, d->pend_out, d->pend_cap, st, d->pend_phase, &d->launches);
+        if (rc != TRRE_OK) return rc;
+        CUDA_TRY(cudaMemcpyAsync(d->h_status, d->d_status, sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
+        CUDA_TRY(cudaMemcpyAsync(d->h_total, d->d_total, sizeof(unsigned long long), cudaMemcpyDeviceToHost, st));
+        CUDA_TRY(cudaStreamSynchronize(st));
+        s = *d->h_status;
+        total = (size_t)*d->h_total;
+    }
+    if ((s & (ST_STACK | ST_OBUF)) && p->hdr.exec_kind == TRRE_EXEC_BACKTRACK && d->bt_tier == 0) {
+        // the small per-thread DFS stacks overflowed: once more with the reference's capacity (see ensure_workspace)
+        d->bt_tier = 1;
+        int rc = clear_status(d, st);
+        if (rc != TRRE_OK) return rc;
         d->status_dirty = true;
         rc = launch_general(p, d, d->pend_in, d->pend_n, d->pend_out, d->pend_cap, st, d->pend_phase, &d->launches);
         if (rc != TRRE_OK) return rc;
@@ -714,6 +871,7 @@ int trre_compile(const char *expr, int flavor, trre_prog **out, char *err, size_
         trre_prog *p = new trre_prog();
         p->blob = std::move(blob);
         std::memcpy(&p->hdr, p->blob.data(), sizeof(BlobHeader));
+        attach_lazy(p);
         *out = p;
         if (err && errcap) err[0] = 0;
         return TRRE_OK;
@@ -734,7 +892,39 @@ int trre_prog_from_blob(const void *blob, size_t nbytes, trre_prog **out, char *
     trre_prog *p = new trre_prog();
     p->blob.assign(static_cast<const uint8_t *>(blob), static_cast<const uint8_t *>(blob) + nbytes);
     std::memcpy(&p->hdr, p->blob.data(), sizeof(BlobHeader));
+    try {
+        attach_lazy(p);
+    } catch (const PatternError &e) {
+        set_err(err, errcap, e.text);
+        delete p;
+        return e.code;
+    }
     *out = p;
+    return TRRE_OK;
+}
+
+int trre_lazy_build(trre_prog *p, const uint32_t *states, size_t n, uint32_t extra) {
+    if (!p || !p->lazy || (n && !states)) return TRRE_E_ARG;
+    try {
+        std::lock_guard<std::mutex> lock(p->lazy_mu);
+        for (size_t k = 0; k < n; ++k)
+            if (states[k] >= p->lazy->n_states()) return TRRE_E_ARG;
+        p->lazy->build(states, n, extra);
+    } catch (const PatternError &e) {
+        g_last_error = e.text;
+        return e.code;
+    }
+    return TRRE_OK;
+}
+
+int trre_lazy_view(const trre_prog *p, uint32_t *n_states, const uint64_t **rows, const uint64_t **sinfo,
+                   const uint8_t **pool, size_t *pool_bytes) {
+    if (!p || !p->lazy) return TRRE_E_ARG;
+    if (n_states) *n_states = p->lazy->n_states();
+    if (rows) *rows = p->lazy->rows().data();
+    if (sinfo) *sinfo = p->lazy->sinfo().data();
+    if (pool) *pool = p->lazy->pool().data();
+    if (pool_bytes) *pool_bytes = p->lazy->pool().size();
     return TRRE_OK;
 }
 
@@ -749,6 +939,9 @@ void trre_prog_free(trre_prog *p) {
         if (d->d_slot_total) { cudaFree(d->d_slot_total); cudaFreeHost(d->h_slot_total); }
         if (d->buf_in) cudaFree(d->buf_in);
         if (d->buf_out) cudaFree(d->buf_out);
+        if (d->lz_rows) { cudaFree(d->lz_rows); cudaFree(d->lz_sinfo); cudaFree(d->lz_requested); }
+        if (d->lz_pool) cudaFree(d->lz_pool);
+        if (d->lz_miss) { cudaFree(d->lz_miss); cudaFreeHost(d->h_lz_miss); }
         for (int k = 0; k < kSlots; ++k) {
             if (d->slot_in[k]) cudaFree(d->slot_in[k]);
             if (d->slot_out[k]) cudaFree(d->slot_out[k]);
@@ -758,6 +951,7 @@ void trre_prog_free(trre_prog *p) {
         }
         delete d;
     }
+    delete p->lazy;
     delete p;
 }
 

@@ -6,7 +6,8 @@
 // acyclic program reads at most D = max_depth bytes, so its outcome is a function of the D byte CLASSES at the position -
 // n_classes^D combinations (cat:dog 4^3, (cat:dog|dog:cat) 7^3, the 10 000-word dictionary 27^4 = 531 441).  The device
 // keeps
-//     gbits  1 bit per combination: the attempt matches          (shared memory; 32x bank-replicated when small)
+//     gbits  1 bit per combination: the attempt matches          (shared memory; up to 512 combinations: one word per
+//                                                                  combination and lane, conflict free)
 //     gout   u32 per combination: what the match prints          (shared memory when small, else L2)
 // and a tile (512 bytes per warp, 16 positions per lane, as k_match) becomes straight-line code:
 //   A  16-byte vector load per lane (next tile prefetched); the D-1 bytes past a lane's end come from its neighbour
@@ -15,8 +16,8 @@
 //   C  index of the D-gram at each position by Horner steps over the classes (IMAD), one bitmap lookup -> candidate
 //      mask.  With matches of one common length (every BASELINE config) their lengths need no lookup at all.
 //   D  chain resolution (resolve_chain, shared with k_match): which candidates start outside an earlier match
-//   E  the real matches - a few per cent of the positions - are dealt round the warp; each fetches its output from
-//      gout (the bytes themselves when they fit a word) and overwrites its span of the staged output tile
+//   E  the real matches - a few per cent of the positions - fetch their output from gout (the bytes themselves when
+//      they fit a word) and overwrite their span of the staged output tile
 //   F  16-byte vector store per lane
 // Scan-driver semantics, warm-up from the last '\n' before a warp's span and ST_IRREGULAR handling are k_match's
 // (trre_nft.c:778-789 on a regular buffer: an attempt at every position not covered by an earlier match).
@@ -30,6 +31,8 @@ namespace trre {
 constexpr int kGramThreads = 1024;
 constexpr int kGramWarps = kGramThreads / 32;
 constexpr int kGramMaxDepth = 6;
+constexpr int kGramWarpSmem = 544 + 544;             // s_in (+halo), s_out (+halo)
+constexpr uint32_t kGramSmallEntries = 512;          // up to here: one u32 per combination and lane (conflict free)
 
 enum : uint32_t {
     GRAM_DIRECT = 1u,       // gout holds the output bytes themselves (every match prints <= 4 bytes, one common length)
@@ -50,18 +53,18 @@ struct GramArgs {
     uint32_t entries;            // n_classes ^ D
     uint32_t uniform_len;        // > 0: every match consumes exactly this many bytes
     uint32_t gflags;
-    uint32_t bits_replicated;    // 1: gbits sits 32x replicated in shared memory (bank = lane)
     uint32_t gout_in_smem;
     uint32_t pool_in_smem;
 };
 
 struct GramTables {
-    const uint32_t *cls_lane;    // shared: class of byte c at cls_lane[c * 32]  (already offset by the lane)
-    const uint32_t *cls_any;     // shared: same table, lane 0's column base (for lookups where banks do not matter)
-    const uint32_t *bits;        // shared: word w of the bitmap at bits[w * bstride]  (offset by the lane when replicated)
-    uint32_t bstride;
+    const uint8_t *cls_b;        // shared: class of byte c for lane l at byte offset c * 128 + l * 4 (32 KB, bank = lane)
+    const uint8_t *hit_b;        // SMALL: u32 per combination and lane at idx * 128 + l * 4, bit 31 = the attempt matches
+    const uint32_t *bits;        // !SMALL: bitmap, bit (31 - idx % 32) of word idx / 32 (reversed: a left shift by idx
+                                 // brings the bit to position 31)
     const uint32_t *gout;        // shared or global
     const uint8_t *pool;         // shared or global
+    uint32_t lane4;              // lane * 4
 };
 
 // index of the D-gram starting at tile position p, from the staged bytes (any lane, any position)
@@ -69,13 +72,22 @@ template <int D>
 __device__ __forceinline__ uint32_t gram_index_at(const GramTables &T, const uint8_t *s_in, uint32_t p, uint32_t ncls) {
     uint32_t idx = 0;
 #pragma unroll
-    for (int i = D - 1; i >= 0; --i) idx = idx * ncls + T.cls_lane[(uint32_t)s_in[p + i] << 5];
+    for (int i = D - 1; i >= 0; --i)
+        idx = idx * ncls + *reinterpret_cast<const uint32_t *>(T.cls_b + (((uint32_t)s_in[p + i] << 7) | T.lane4));
     return idx;
 }
 
-template <int D, bool STORE>
+// class of byte k (0..3) of word w: one shift, one and-or (the lane's column is OR-ed in: the fields do not overlap),
+// one conflict-free shared-memory load
+template <int K>
+__device__ __forceinline__ uint32_t class_of(const GramTables &T, uint32_t w) {
+    const uint32_t sh = K == 0 ? (w << 7) : (w >> (8 * K - 7));
+    return *reinterpret_cast<const uint32_t *>(T.cls_b + ((sh & 0x7F80u) | T.lane4));
+}
+
+template <int D, bool SMALL, bool STORE>
 __device__ __forceinline__ void gram_tile(const GramArgs &a, const GramTables &T, uint8_t *s_in, uint8_t *s_out,
-                                          uint16_t *s_list, uint32_t *s_count, size_t base, uint4 x, uint4 x_next,
+                                          size_t base, bool full, uint4 x, uint4 x_next,
                                           uint32_t lane, uint32_t first_valid, uint32_t &carry_e, uint4 &carry_halo,
                                           uint32_t &nul_acc) {
     // ---- A: stage the tile (input and default output = raw copy); lane 0 of the next tile is the halo ---------------
@@ -84,26 +96,32 @@ __device__ __forceinline__ void gram_tile(const GramArgs &a, const GramTables &T
     if (lane == 0) {
         *reinterpret_cast<uint4 *>(s_in + kTile) = x_next;
         *reinterpret_cast<uint4 *>(s_out + kTile) = x_next;
-        *s_count = 0;
     }
     nul_acc |= ((x.x - 0x01010101u) & ~x.x) | ((x.y - 0x01010101u) & ~x.y) | ((x.z - 0x01010101u) & ~x.z) | ((x.w - 0x01010101u) & ~x.w);
     // the D-1 bytes after this lane's 16: the neighbour's first words (lane 31: the next tile's)
-    uint32_t h0 = __shfl_down_sync(0xFFFFFFFFu, x.x, 1), h1 = __shfl_down_sync(0xFFFFFFFFu, x.y, 1);
-    const uint32_t n0 = __shfl_sync(0xFFFFFFFFu, x_next.x, 0), n1 = __shfl_sync(0xFFFFFFFFu, x_next.y, 0);
-    if (lane == 31) { h0 = n0; h1 = n1; }
+    uint32_t h0 = __shfl_down_sync(0xFFFFFFFFu, x.x, 1), h1 = 0;
+    const uint32_t n0 = __shfl_sync(0xFFFFFFFFu, x_next.x, 0);
+    if (lane == 31) h0 = n0;
+    if (D > 5) {
+        h1 = __shfl_down_sync(0xFFFFFFFFu, x.y, 1);
+        const uint32_t n1 = __shfl_sync(0xFFFFFFFFu, x_next.y, 0);
+        if (lane == 31) h1 = n1;
+    }
 
     // ---- B: byte classes, conflict free (bank = lane) ------------------------------------------------------------------
     const uint32_t ncls = a.n_classes;
     uint32_t cls[16 + kGramMaxDepth - 1];
-    {
-        const uint32_t w[6] = {x.x, x.y, x.z, x.w, h0, h1};
-#pragma unroll
-        for (int t = 0; t < 16 + D - 1; ++t) {
-            const uint32_t c = (w[t >> 2] >> ((t & 3) * 8)) & 0xFFu;
-            cls[t] = T.cls_lane[c << 5];
-        }
-    }
-    // ---- C: D-gram index per position (Horner over the classes), one bitmap lookup each -> candidate mask -----------
+    cls[0] = class_of<0>(T, x.x);  cls[1] = class_of<1>(T, x.x);  cls[2] = class_of<2>(T, x.x);  cls[3] = class_of<3>(T, x.x);
+    cls[4] = class_of<0>(T, x.y);  cls[5] = class_of<1>(T, x.y);  cls[6] = class_of<2>(T, x.y);  cls[7] = class_of<3>(T, x.y);
+    cls[8] = class_of<0>(T, x.z);  cls[9] = class_of<1>(T, x.z);  cls[10] = class_of<2>(T, x.z); cls[11] = class_of<3>(T, x.z);
+    cls[12] = class_of<0>(T, x.w); cls[13] = class_of<1>(T, x.w); cls[14] = class_of<2>(T, x.w); cls[15] = class_of<3>(T, x.w);
+    if (D >= 2) cls[16] = class_of<0>(T, h0);
+    if (D >= 3) cls[17] = class_of<1>(T, h0);
+    if (D >= 4) cls[18] = class_of<2>(T, h0);
+    if (D >= 5) cls[19] = class_of<3>(T, h0);
+    if (D >= 6) cls[20] = class_of<0>(T, h1);
+    // ---- C: D-gram index per position (Horner over the classes), one lookup each -> candidate mask --------------------
+    // positions are taken from 15 down to 0 and the hit bit enters the mask through a funnel shift: 1 instruction
     uint32_t cand = 0;
     {
         const uint32_t n2 = ncls * ncls, n4 = n2 * n2;
@@ -113,7 +131,7 @@ __device__ __forceinline__ void gram_tile(const GramArgs &a, const GramTables &T
             for (int t = 0; t < 16 + D - 2; ++t) q[t] = cls[t] + ncls * cls[t + 1];
         }
 #pragma unroll
-        for (int j = 0; j < 16; ++j) {
+        for (int j = 15; j >= 0; --j) {
             uint32_t idx;
             if (D == 1) idx = cls[j];
             else if (D == 2) idx = cls[j] + ncls * cls[j + 1];
@@ -121,8 +139,10 @@ __device__ __forceinline__ void gram_tile(const GramArgs &a, const GramTables &T
             else if (D == 4) idx = q[j] + n2 * q[j + 2];
             else if (D == 5) idx = q[j] + n2 * q[j + 2] + n4 * cls[j + 4];
             else idx = q[j] + n2 * q[j + 2] + n4 * q[j + 4];
-            const uint32_t wd = T.bits[(idx >> 5) * T.bstride];
-            cand |= ((wd >> (idx & 31u)) & 1u) << j;
+            uint32_t hit;                                           // bit 31 = the attempt at position j matches
+            if (SMALL) hit = *reinterpret_cast<const uint32_t *>(T.hit_b + ((idx << 7) | T.lane4));
+            else hit = T.bits[idx >> 5] << (idx & 31u);
+            cand = __funnelshift_l(hit, cand, 1);
         }
     }
     {
@@ -147,24 +167,19 @@ __device__ __forceinline__ void gram_tile(const GramArgs &a, const GramTables &T
     }
     // ---- D ---------------------------------------------------------------------------------------------------------------
     resolve_chain(f, cand, lane, carry_e);
-    uint32_t real = f.real;
 
-    // ---- E: real matches overwrite their span of the output tile; dealt round the warp ---------------------------------
+    // ---- E: every real match overwrites its span of the output tile, written by the lane it starts in (matches are a few
+    // per cent of the positions: compacting them across the warp costs more than the divergence it removes) ----------
     if (lane == 0 && carry_e) {
         const uint32_t h[4] = {carry_halo.x, carry_halo.y, carry_halo.z, carry_halo.w};
         for (uint32_t k = 0; k < carry_e; ++k) s_out[k] = (uint8_t)(h[k >> 2] >> ((k & 3) * 8));
     }
-    if (__any_sync(0xFFFFFFFFu, real != 0)) {
-        uint32_t slot = real ? atomicAdd(s_count, (uint32_t)__popc(real)) : 0u;
+    {
+        uint32_t real = f.real;
         while (real) {
             const uint32_t j = __ffs(real) - 1;
             real &= real - 1;
-            s_list[slot++] = (uint16_t)(lane * 16 + j);
-        }
-        __syncwarp();
-        const uint32_t total = *s_count;
-        for (uint32_t qi = lane; qi < total; qi += 32) {
-            const uint32_t p = s_list[qi];
+            const uint32_t p = lane * 16 + j;
             const uint32_t g = T.gout[gram_index_at<D>(T, s_in, p, ncls)];
             if (a.gflags & GRAM_DIRECT) {
                 const uint32_t m = a.uniform_len;
@@ -180,7 +195,7 @@ __device__ __forceinline__ void gram_tile(const GramArgs &a, const GramTables &T
     if (STORE) {
         const size_t my = base + (size_t)lane * 16;
         const uint4 y = *reinterpret_cast<const uint4 *>(s_out + lane * 16);
-        if (my + 16 <= a.n) {
+        if (full || my + 16 <= a.n) {
             *reinterpret_cast<uint4 *>(a.out + my) = y;
         } else if (my < a.n) {
             const uint32_t w[4] = {y.x, y.y, y.z, y.w};
@@ -192,28 +207,31 @@ __device__ __forceinline__ void gram_tile(const GramArgs &a, const GramTables &T
     __syncwarp();
 }
 
-template <int D>
+template <int D, bool SMALL>
 __global__ void __launch_bounds__(kGramThreads, 1)
 k_gram(GramArgs a) {
     extern __shared__ __align__(16) uint8_t smem[];
     const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    // layout: [class table 32 KB] [bitmap (x32 when replicated)] [gout]? [pool]? [per warp: s_in, s_out, list, counter]
+    // layout: [class table 32 KB] [SMALL: hit words x32 | bitmap] [gout]? [pool]? [per warp: s_in, s_out]
     uint8_t *cur = smem;
     uint32_t *cls_s = reinterpret_cast<uint32_t *>(cur); cur += 256 * 32 * 4;
     uint32_t *bits_s = reinterpret_cast<uint32_t *>(cur);
     const uint32_t words = (a.entries + 31) / 32;
-    cur += (size_t)((words * (a.bits_replicated ? 32u : 1u) + 3) & ~3u) * 4;
+    cur += SMALL ? (size_t)a.entries * 128 : (size_t)((words + 3) & ~3u) * 4;
     uint32_t *gout_s = nullptr;
     if (a.gout_in_smem) { gout_s = reinterpret_cast<uint32_t *>(cur); cur += (size_t)((a.entries + 3) & ~3u) * 4; }
     uint8_t *pool_s = nullptr;
     if (a.pool_in_smem) { pool_s = cur; cur += (a.gpool_bytes + 15) & ~15u; }
-    uint8_t *warp_base = cur + warp * kWarpSmem;
+    uint8_t *warp_base = cur + warp * kGramWarpSmem;
 
     for (uint32_t k = threadIdx.x; k < 256u * 32u; k += blockDim.x) cls_s[k] = __ldg(a.classmap + (k >> 5));
-    if (a.bits_replicated) {
-        for (uint32_t k = threadIdx.x; k < words * 32u; k += blockDim.x) bits_s[k] = __ldg(a.gbits + (k >> 5));
+    if (SMALL) {
+        for (uint32_t k = threadIdx.x; k < a.entries * 32u; k += blockDim.x) {
+            const uint32_t e = k >> 5;
+            bits_s[k] = ((__ldg(a.gbits + (e >> 5)) >> (e & 31u)) & 1u) << 31;
+        }
     } else {
-        for (uint32_t k = threadIdx.x; k < words; k += blockDim.x) bits_s[k] = __ldg(a.gbits + k);
+        for (uint32_t k = threadIdx.x; k < words; k += blockDim.x) bits_s[k] = __brev(__ldg(a.gbits + k));
     }
     if (gout_s)
         for (uint32_t k = threadIdx.x; k < a.entries; k += blockDim.x) gout_s[k] = __ldg(a.gout + k);
@@ -222,16 +240,14 @@ k_gram(GramArgs a) {
     __syncthreads();
 
     GramTables T;
-    T.cls_lane = cls_s + lane;
-    T.cls_any = cls_s;
-    T.bits = a.bits_replicated ? bits_s + lane : bits_s;
-    T.bstride = a.bits_replicated ? 32u : 1u;
+    T.cls_b = reinterpret_cast<const uint8_t *>(cls_s);
+    T.hit_b = reinterpret_cast<const uint8_t *>(bits_s);
+    T.bits = bits_s;
     T.gout = gout_s ? gout_s : a.gout;
     T.pool = pool_s ? pool_s : a.gpool;
+    T.lane4 = lane * 4;
 
     uint8_t *s_in = warp_base, *s_out = warp_base + 544;
-    uint16_t *s_list = reinterpret_cast<uint16_t *>(warp_base + 1088);
-    uint32_t *s_count = reinterpret_cast<uint32_t *>(warp_base + 1088 + 1024);
 
     const size_t n = a.n;
     const size_t n_tiles = (n + kTile - 1) / kTile;
@@ -273,9 +289,11 @@ k_gram(GramArgs a) {
         uint4 x = load_padded(a.in, base + lane * 16, n);
         for (size_t t = tw; t < t1; ++t) {
             base = t * (size_t)kTile;
-            const uint4 x_next = load_padded(a.in, base + kTile + lane * 16, n);     // prefetch; its lane 0 is this tile's halo
-            if (t < t0) gram_tile<D, false>(a, T, s_in, s_out, s_list, s_count, base, x, x_next, lane, first_valid, carry_e, carry_halo, nul_acc);
-            else        gram_tile<D, true>(a, T, s_in, s_out, s_list, s_count, base, x, x_next, lane, first_valid, carry_e, carry_halo, nul_acc);
+            // prefetch; its lane 0 is this tile's halo.  Tiles whose successor lies inside the buffer skip every bounds check
+            const bool full = base + 2 * (size_t)kTile <= n;
+            const uint4 x_next = full ? ldg_vec(a.in + base + kTile + lane * 16) : load_padded(a.in, base + kTile + lane * 16, n);
+            if (t < t0) gram_tile<D, SMALL, false>(a, T, s_in, s_out, base, full, x, x_next, lane, first_valid, carry_e, carry_halo, nul_acc);
+            else        gram_tile<D, SMALL, true>(a, T, s_in, s_out, base, full, x, x_next, lane, first_valid, carry_e, carry_halo, nul_acc);
             first_valid = 0;
             x = x_next;
         }

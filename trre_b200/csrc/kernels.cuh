@@ -258,6 +258,77 @@ k_bytemap_swar(const uint8_t *__restrict__ in, uint8_t *__restrict__ out, size_t
     }
 }
 
+// Experimental launch shapes of the same map (TRRE_SWAR_VARIANT=1/2), kept selectable until one wins on hardware:
+//  1: no register double buffering, 32 registers, up to 8 x 256 threads per SM (more loads in flight through warps)
+//  2: one CTA per 16 KB block of the buffer, 4 vectors per thread, hardware block scheduling instead of a sweep
+template <int NR>
+__global__ void __launch_bounds__(256, 8)
+k_bytemap_swar_v1(const uint8_t *__restrict__ in, uint8_t *__restrict__ out, size_t n, const SwarMap M,
+                  const uint8_t *__restrict__ lut, uint32_t *__restrict__ status) {
+    uint32_t nul = 0;
+    size_t head = ((16 - (reinterpret_cast<uintptr_t>(in) & 15)) & 15);
+    if (head > n) head = n;
+    const size_t nvec = (n - head) / 16;
+    const uint4 *vin = reinterpret_cast<const uint4 *>(in + head);
+    uint4 *vout = reinterpret_cast<uint4 *>(out + head);
+    const size_t stride = (size_t)gridDim.x * blockDim.x;
+    size_t v = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    for (; v + 3 * stride < nvec; v += 4 * stride) {
+        uint4 x[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) x[u] = ld_stream(vin + v + u * stride);
+#pragma unroll
+        for (int u = 0; u < 4; ++u) st_stream(vout + v + u * stride, swar_vec<NR>(x[u], M, nul));
+    }
+    for (; v < nvec; v += stride) {
+        uint4 x = ld_stream(vin + v);
+        st_stream(vout + v, swar_vec<NR>(x, M, nul));
+    }
+    nul &= 0x80808080u;
+    if (blockIdx.x == 0 && threadIdx.x == 0) {
+        for (size_t k = 0; k < head; ++k) { uint8_t c = in[k]; if (!c) nul = 1; out[k] = lut[c]; }
+        for (size_t k = head + nvec * 16; k < n; ++k) { uint8_t c = in[k]; if (!c) nul = 1; out[k] = lut[c]; }
+        if (n && in[n - 1] != '\n') nul = 1;
+    }
+    if (__any_sync(0xFFFFFFFFu, nul != 0)) {
+        if ((threadIdx.x & 31) == 0) atomicOr(status, ST_IRREGULAR);
+    }
+}
+
+template <int NR>
+__global__ void __launch_bounds__(256, 8)
+k_bytemap_swar_v2(const uint8_t *__restrict__ in, uint8_t *__restrict__ out, size_t n, const SwarMap M,
+                  const uint8_t *__restrict__ lut, uint32_t *__restrict__ status) {
+    uint32_t nul = 0;
+    size_t head = ((16 - (reinterpret_cast<uintptr_t>(in) & 15)) & 15);
+    if (head > n) head = n;
+    const size_t nvec = (n - head) / 16;
+    const uint4 *vin = reinterpret_cast<const uint4 *>(in + head);
+    uint4 *vout = reinterpret_cast<uint4 *>(out + head);
+    const size_t v0 = (size_t)blockIdx.x * 1024 + threadIdx.x;
+    if (v0 + 768 < nvec) {
+        uint4 x[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) x[u] = ld_stream(vin + v0 + u * 256);
+#pragma unroll
+        for (int u = 0; u < 4; ++u) st_stream(vout + v0 + u * 256, swar_vec<NR>(x[u], M, nul));
+    } else {
+        for (size_t v = v0; v < nvec && v < (size_t)(blockIdx.x + 1) * 1024; v += 256) {
+            uint4 x = ld_stream(vin + v);
+            st_stream(vout + v, swar_vec<NR>(x, M, nul));
+        }
+    }
+    nul &= 0x80808080u;
+    if (blockIdx.x == 0 && threadIdx.x == 0) {
+        for (size_t k = 0; k < head; ++k) { uint8_t c = in[k]; if (!c) nul = 1; out[k] = lut[c]; }
+        for (size_t k = head + nvec * 16; k < n; ++k) { uint8_t c = in[k]; if (!c) nul = 1; out[k] = lut[c]; }
+        if (n && in[n - 1] != '\n') nul = 1;
+    }
+    if (__any_sync(0xFFFFFFFFu, nul != 0)) {
+        if ((threadIdx.x & 31) == 0) atomicOr(status, ST_IRREGULAR);
+    }
+}
+
 // ------------------------------------------------------------------------------------------------
 // k_lines
 // ------------------------------------------------------------------------------------------------
@@ -278,21 +349,26 @@ struct LineArgs {
     // DFS executor scratch, indexed by resident thread
     int32_t *bt_s; uint32_t *bt_i; uint32_t *bt_o; uint8_t *bt_obuf;
     uint32_t bt_cap, bt_ocap;
+    LazyDev L;                   // EXEC_LAZY
 };
+
+enum { EXEC_TABLE = 0, EXEC_DFS = 1, EXEC_LAZY = 2 };   // which per-attempt executor k_lines runs
 
 // The per-record loop of the reference's scan drivers (trre_nft.c:778-789 / trre_dft.c:1275-1285)
 // for the record whose payload starts at `p`; `lim` = end of all payload bytes of the buffer (n, or
 // n-1 when the buffer does not end in '\n': getline's last record loses its last byte).
 // Returns the position just past the record.
-template <bool BACKTRACK>
-__device__ __forceinline__ size_t run_record(const DevProg &P, const BtScratch &B, const uint8_t *__restrict__ in,
+template <int EXEC>
+__device__ __forceinline__ size_t run_record(const DevProg &P, const BtScratch &B, const LazyDev &L, const uint8_t *__restrict__ in,
                                              size_t p, size_t lim, size_t n, Sink &o, uint32_t &status) {
     for (;;) {
         bool at_end = true;
         uint8_t c = 0;
         if (p < lim) { c = __ldg(in + p); at_end = (c == 0 || c == '\n'); }
-        long k = BACKTRACK ? attempt_backtrack(P, B, in, p, lim, o, status)
-                           : attempt_table(P, in, p, lim, o, status);
+        long k = EXEC == EXEC_DFS    ? attempt_backtrack(P, B, in, p, lim, o, status)
+                 : EXEC == EXEC_LAZY ? attempt_lazy(L, in, p, lim, o, status)
+                                     : attempt_table(P, in, p, lim, o, status);
+        if (EXEC == EXEC_LAZY && k == -2) break;          // a row is missing: this pass is void, leave the record
         if (at_end) break;                                // that was the attempt on the empty tail
         if (k > 0) p += (size_t)k;
         else { o.put(c); ++p; }                           // no match or empty match: copy one raw byte
@@ -303,7 +379,7 @@ __device__ __forceinline__ size_t run_record(const DevProg &P, const BtScratch &
     return p + 1;
 }
 
-template <int MODE, bool BACKTRACK>
+template <int MODE, int EXEC>
 __global__ void __launch_bounds__(kLineThreads)
 k_lines(LineArgs a) {
     __shared__ unsigned long long warp_sums[kLineThreads / 32];
@@ -318,7 +394,7 @@ k_lines(LineArgs a) {
         return;
     }
     BtScratch B;
-    if (BACKTRACK) {
+    if (EXEC == EXEC_DFS) {
         size_t slot = (size_t)blockIdx.x * kLineThreads + threadIdx.x;
         B.stk_s = a.bt_s + slot * a.bt_cap; B.stk_i = a.bt_i + slot * a.bt_cap; B.stk_o = a.bt_o + slot * a.bt_cap;
         B.obuf = a.bt_obuf + slot * a.bt_ocap; B.cap = a.bt_cap; B.ocap = a.bt_ocap;
@@ -361,7 +437,7 @@ k_lines(LineArgs a) {
             while (p < cend) {                            // p < n here: a record starts at p
                 if (MODE == MODE_INPLACE) o.n = p;
                 size_t before = o.n;
-                p = run_record<BACKTRACK>(a.P, B, in, p, lim, n, o, status);
+                p = run_record<EXEC>(a.P, B, a.L, in, p, lim, n, o, status);
                 produced += o.n - before;
                 if (MODE == MODE_INPLACE && o.n != p) status |= ST_IRREGULAR;   // a NUL cut the line short
             }
