@@ -18,11 +18,11 @@ cli: bin/trre bin/trre_dft
 
 bin/trre: $(CSRC)/cli_main.cpp $(LIB)
 	@mkdir -p bin
-	g++ -O2 -std=c++17 -Wall -Wextra -DTRRE_CLI_FLAVOR=0 $< -o $@ -Ltrre_b200/lib -ltrre_b200 -Wl,-rpath,'$$ORIGIN/../trre_b200/lib'
+	g++ -O2 -std=c++17 -pthread -Wall -Wextra -DTRRE_CLI_FLAVOR=0 $< -o $@ -Ltrre_b200/lib -ltrre_b200 -Wl,-rpath,'$$ORIGIN/../trre_b200/lib'
 
 bin/trre_dft: $(CSRC)/cli_main.cpp $(LIB)
 	@mkdir -p bin
-	g++ -O2 -std=c++17 -Wall -Wextra -DTRRE_CLI_FLAVOR=1 $< -o $@ -Ltrre_b200/lib -ltrre_b200 -Wl,-rpath,'$$ORIGIN/../trre_b200/lib'
+	g++ -O2 -std=c++17 -pthread -Wall -Wextra -DTRRE_CLI_FLAVOR=1 $< -o $@ -Ltrre_b200/lib -ltrre_b200 -Wl,-rpath,'$$ORIGIN/../trre_b200/lib'
 
 oracle:
 	$(MAKE) -s -C oracle

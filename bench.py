@@ -1,7 +1,7 @@
 #!/usr/bin/env python
 """bench.py - headline measurement of the trre scan path on B200 (BASELINE.json metric).
 
-  python bench.py [--gpus N] [--steps K] [--warmup W] [--workload cfg2|cfg1|cfg3|cfg4|cfg5] [--impl reference]
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--workload cfg2|cfg1|cfg3|cfg4|cfg5|...] [--impl reference]
 
 A "step" is one pass of the hot path over one batch of synthetic input: at N=1 the workload is
 BASELINE.json configs[1] - '[a:A-z:Z]' uppercase over 1 GiB synthetic ASCII, DFT flavour (trre_dft
@@ -9,14 +9,20 @@ semantics).  N>1 (torchrun, one rank per GPU): the compiled program is broadcast
 rank scans its own line-aligned 1 GiB shard (weak scaling), output sizes are all-gathered.
 
   value    input GB/s, inputs resident in HBM, CUDA-event timed on the launching stream, max over ranks
-  e2e      same metric through the C ABI with HOST (pinned) buffers: H2D + kernels + D2H inside the clock
+  e2e      same metric through the C ABI with HOST (pinned) buffers: H2D + kernels + D2H inside the clock,
+           next to the PCIe copy rates measured in the same process (its roofline)
   roofline dominant kernel vs the measured HBM copy bandwidth (MEASURED_PEAKS.json)
   cpu_baseline  the reference binary (oracle/_ref/trre_dft, 1 thread - it is single threaded) on a
            bounded sample of the same workload, same box
+  others   measured after the headline, same process: the other BASELINE configs (1 GiB slices and their
+           stated sizes), each verified against the SHA-256 of the real reference's stdout
+           (tests/golden/config_hashes.json); at N>1 also Caesar 8 GiB per GPU and the 64 GiB dictionary split
+           over the ranks (strong scaling) with the program broadcast and the size all-gather inside the clock
 
 --impl reference times the reference's own CPU implementation (oracle/_ref) on the same config.
 """
 import argparse
+import hashlib
 import json
 import os
 import subprocess
@@ -70,6 +76,20 @@ DESCR = {
     "del": "'a:' (delete every a; NOT length preserving: count + scan + write path) over 1 GiB synthetic ASCII, NFT flavour",
 }
 METRIC = "input GB/s (scan mode)"
+KERNELS = {0: "k_lines_s<count> + k_scan_groups + k_lines_s<write>", 1: "k_bytemap", 2: "k_match",
+           3: "k_bmv_count + k_scan_groups + k_bmv_write", 4: "k_match<count> + k_scan_groups + k_match<write>",
+           5: "k_lines<inplace>"}
+
+
+def short_pattern(pattern):
+    return pattern if len(pattern) < 200 else pattern[:60] + "...(%d bytes)" % len(pattern)
+
+
+def config_of(name, spec, n_gpus):
+    """The `config` object - the SAME in both arms (the driver compares them)."""
+    pattern, flavor, nbytes = spec[0], spec[1], spec[2]
+    return {"workload": DESCR[name], "pattern": short_pattern(pattern), "flavor": "dft" if flavor else "nft",
+            "bytes_per_gpu": nbytes, "n_gpus": n_gpus}
 
 
 def measured_hbm_peak():
@@ -79,6 +99,14 @@ def measured_hbm_peak():
             return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json, copy read+write)"
     except Exception:
         return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+def config_hashes():
+    try:
+        with open(os.path.join(ROOT, "tests", "golden", "config_hashes.json")) as f:
+            return json.load(f)["configs"]
+    except Exception:
+        return {}
 
 
 class ClockSampler:
@@ -92,15 +120,7 @@ class ClockSampler:
             import pynvml
             pynvml.nvmlInit()
             self.nv = pynvml
-            # NVML indexes physical GPUs; honour CUDA_VISIBLE_DEVICES when it is a plain index list
-            vis = os.environ.get("CUDA_VISIBLE_DEVICES")
-            phys = index
-            if vis:
-                try:
-                    phys = int(vis.split(",")[index])
-                except Exception:
-                    phys = index
-            self.h = pynvml.nvmlDeviceGetHandleByIndex(phys)
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(physical_index(index))
             self.max_sm = pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM)
         except Exception:
             self.nv = None
@@ -158,26 +178,55 @@ class ClockSampler:
                 "reasons": sorted(k for k, bit in names.items() if allr & bit), "samples": len(sm)}
 
 
-def make_text(T, spec, nbytes):
-    """One tile of the synthetic corpus, replicated to nbytes; ends on a line boundary."""
-    pattern, flavor, _, words, p_hit, lower, seed, _ = spec
-    tile_n = min(TILE, nbytes)
-    tile = T.synth_text(seed, tile_n, words, p_hit, lower)
-    return tile
+def physical_index(index):
+    """NVML indexes physical GPUs; honour CUDA_VISIBLE_DEVICES when it is a plain index list."""
+    vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+    if vis:
+        try:
+            return int(vis.split(",")[index])
+        except Exception:
+            pass
+    return index
 
 
-def run_reference(args, spec):
+def bind_to_gpu_numa_node(index):
+    """Pin this rank to the CPU cores next to its GPU (NVML affinity mask) BEFORE any pinned buffer is allocated:
+    first touch then places the staging memory on the GPU's own NUMA node.  With 8 ranks pushing 1 GiB each way this is
+    the difference between every copy crossing the socket link and none."""
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        h = pynvml.nvmlDeviceGetHandleByIndex(physical_index(index))
+        ncpu = os.cpu_count() or 1
+        words = pynvml.nvmlDeviceGetCpuAffinity(h, (ncpu + 63) // 64)
+        cpus = {64 * w + b for w, m in enumerate(words) for b in range(64) if (m >> b) & 1}
+        cpus &= os.sched_getaffinity(0)
+        if cpus:
+            os.sched_setaffinity(0, cpus)
+            return {"cpus": "%d-%d (%d)" % (min(cpus), max(cpus), len(cpus))}
+    except Exception as e:
+        return {"cpus": None, "error": str(e)[:80]}
+    return {"cpus": None}
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# --impl reference
+# ---------------------------------------------------------------------------------------------------------------------
+
+def run_reference(args, name, spec):
     """--impl reference: the UNMODIFIED reference binary (oracle/_ref, built from /root/reference by
-    oracle/Makefile), single threaded because it is, on a bounded sample per step."""
+    oracle/Makefile), single threaded because it is, on a bounded sample per step.  The corpus comes from the oracle
+    library's own generator: this arm never maps the product's library."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return 0
-    import trre_b200 as T
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    from oracle_util import oracle_run, oracle_synth_text
     pattern, flavor, nbytes, words, p_hit, lower, seed, refbin = spec
     exe = os.path.join(ROOT, "oracle", "_ref", refbin)
     kind = "reference"
     sample_n = min(nbytes, 64 * MiB)
-    text = bytes(T.synth_text(seed, sample_n, words, p_hit, lower))
+    text = bytes(oracle_synth_text(seed, sample_n, words, p_hit, lower))
     shm = "/dev/shm" if os.path.isdir("/dev/shm") else tempfile.gettempdir()
     path = os.path.join(shm, "trre_bench_ref_%d.txt" % os.getpid())
     with open(path, "wb") as f:
@@ -191,8 +240,6 @@ def run_reference(args, spec):
                 return time.perf_counter() - t0
         else:
             kind = "port"
-            sys.path.insert(0, os.path.join(ROOT, "tests"))
-            from oracle_util import oracle_run
 
             def one():
                 t0 = time.perf_counter()
@@ -209,8 +256,10 @@ def run_reference(args, spec):
         "impl": "reference", "metric": METRIC, "value": gbs, "unit": "GB/s", "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * total / args.steps,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8", "data": "synthetic",
-        "config": {"workload": DESCR[args.workload], "pattern": pattern if len(pattern) < 200 else pattern[:60] + "...(%d bytes)" % len(pattern),
-                   "flavor": "dft" if flavor else "nft", "sample_bytes_per_step": sample_n},
+        "config": config_of(name, spec, args.gpus),
+        "config_detail": {"sample_bytes_per_step": sample_n,
+                          "note": "the reference is single threaded and its speed does not depend on the input size "
+                                  "(~50 MB/s): every step times a %d MiB sample of the same corpus" % (sample_n // MiB)},
         "cpu_baseline": {"value": gbs, "unit": "GB/s", "cores": 1, "kind": kind,
                          "sample": "%d MiB of the same synthetic corpus per step, file in /dev/shm, stdout to /dev/null; "
                                    "single threaded (the reference has no threads)" % (sample_n // MiB)},
@@ -255,6 +304,251 @@ def cpu_baseline(T, spec):
                       "oracle/_ref/%s is single threaded (host has %d cores)" % (sample_n // MiB, refbin, os.cpu_count() or 0)}
 
 
+# ---------------------------------------------------------------------------------------------------------------------
+# the B200 arm
+# ---------------------------------------------------------------------------------------------------------------------
+
+class Ctx:
+    """torch / distributed handles of this rank"""
+
+    def __init__(self, args):
+        import torch
+        import trre_b200 as T
+        self.torch, self.T = torch, T
+        self.world = int(os.environ.get("WORLD_SIZE", "1"))
+        self.rank = int(os.environ.get("RANK", "0"))
+        self.local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+        if not torch.cuda.is_available():
+            raise SystemExit("bench.py: no CUDA device - the trre_b200 scan path has no CPU fallback")
+        self.numa = bind_to_gpu_numa_node(self.local_rank)
+        torch.cuda.set_device(self.local_rank)
+        self.dev = torch.device("cuda", self.local_rank)
+        self.dist = None
+        if self.world > 1:
+            import torch.distributed as dist
+            dist.init_process_group("nccl", device_id=self.dev)
+            self.dist = dist
+        self.stream = torch.cuda.current_stream()
+        self.sp = self.stream.cuda_stream
+        self.hashes = config_hashes()
+
+    def barrier(self):
+        self.torch.cuda.synchronize()
+        if self.dist:
+            self.dist.barrier()
+        self.torch.cuda.synchronize()
+
+    def max_over_ranks(self, x):
+        t = self.torch.tensor([x], dtype=self.torch.float64, device=self.dev)
+        if self.dist:
+            self.dist.all_reduce(t, op=self.dist.ReduceOp.MAX)
+        return float(t.item())
+
+    def all_true(self, ok):
+        t = self.torch.tensor([1 if ok else 0], dtype=self.torch.int32, device=self.dev)
+        if self.dist:
+            self.dist.all_reduce(t, op=self.dist.ReduceOp.MIN)
+        return bool(t.item())
+
+    def broadcast_program(self, pattern, flavor):
+        """Compiled once on rank 0, the flat tables broadcast to every rank (ONE collective)."""
+        T, torch = self.T, self.torch
+        prog = blob = None
+        if self.rank == 0:
+            prog = T.compile(pattern, flavor)
+            blob = prog.blob()
+        self.d_blob = None
+        if self.dist:
+            size = torch.tensor([len(blob) if self.rank == 0 else 0], dtype=torch.int64, device=self.dev)
+            self.dist.broadcast(size, 0)
+            buf = torch.empty(int(size.item()), dtype=torch.uint8, device=self.dev)
+            if self.rank == 0:
+                buf.copy_(torch.frombuffer(bytearray(blob), dtype=torch.uint8))
+            self.dist.broadcast(buf, 0)
+            if self.rank != 0:
+                prog = T.from_blob(bytes(buf.cpu().numpy().tobytes()))
+            self.d_blob = buf
+        return prog
+
+
+def measure(ctx, name, nbytes, steps, warmup, collectives=False, tile_rank=None, clocks=False):
+    """One workload, device resident: build the input from the rank's synthetic tile, time `steps` scans with CUDA
+    events on the launching stream, verify against the reference's hash.  Returns a dict; buffers are released."""
+    T, torch = ctx.T, ctx.torch
+    pattern, flavor, _, words, p_hit, lower, seed, refbin = WORKLOADS[name]
+    prog = ctx.broadcast_program(pattern, flavor)
+    info = prog.info
+    rank_tile = ctx.rank if tile_rank is None else tile_rank
+    tile_n = min(TILE, nbytes)
+    tile = T.synth_text(seed + rank_tile, tile_n, words, p_hit, lower)
+    reps = max(1, nbytes // tile_n)
+    n = tile_n * reps
+    d_tile = torch.frombuffer(tile, dtype=torch.uint8).to(ctx.dev)
+    d_in = d_tile.repeat(reps) if reps > 1 else d_tile
+    if reps > 1:
+        del d_tile
+    out_cap = n + 64 if info["length_preserving"] else 2 * n + 64      # expanding programs: room for 2x
+    d_out = torch.empty(out_cap, dtype=torch.uint8, device=ctx.dev)
+    sizes = torch.zeros(1, dtype=torch.int64, device=ctx.dev)
+    gathered = [torch.zeros_like(sizes) for _ in range(ctx.world)]
+
+    def step():
+        if collectives and ctx.dist:
+            ctx.dist.broadcast(ctx.d_blob, 0)                      # the compiled tables, rank 0 -> all (SURVEY s8d)
+        prog.scan_device(d_in.data_ptr(), n, d_out.data_ptr(), d_out.numel(), device=ctx.local_rank, stream=ctx.sp, sync=False)
+        if collectives and ctx.dist:
+            ctx.dist.all_gather(gathered, sizes)                   # output sizes -> global offsets
+
+    for _ in range(warmup):
+        step()
+    out_n = prog.scan_status(device=ctx.local_rank, stream=ctx.sp)
+    sizes.fill_(out_n)
+    launches_per_step = prog.launches(device=ctx.local_rank)
+    ctx.barrier()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    sampler = ClockSampler(ctx.local_rank) if clocks else None
+    if sampler:
+        sampler.__enter__()
+    ev0.record(ctx.stream)
+    for _ in range(steps):
+        step()
+    ev1.record(ctx.stream)
+    torch.cuda.synchronize()
+    if sampler:
+        sampler.__exit__()
+    ms = ev0.elapsed_time(ev1)
+    out_n = prog.scan_status(device=ctx.local_rank, stream=ctx.sp)
+    ctx.barrier()
+    ms_per_step = ctx.max_over_ranks(ms) / steps
+
+    coll = None
+    if collectives and ctx.dist:
+        # the two collectives on their own, same barrier-to-barrier discipline
+        def timed(fn, reps_=10):
+            ctx.barrier()
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record(ctx.stream)
+            for _ in range(reps_):
+                fn()
+            b.record(ctx.stream)
+            torch.cuda.synchronize()
+            return ctx.max_over_ranks(a.elapsed_time(b)) / reps_
+        coll = {"bcast_ms": timed(lambda: ctx.dist.broadcast(ctx.d_blob, 0)), "bcast_bytes": int(ctx.d_blob.numel()),
+                "allgather_ms": timed(lambda: ctx.dist.all_gather(gathered, sizes)), "inside_the_clock": True}
+
+    # ---- verification outside the clock: tile 0 against the SHA-256 of the REAL reference's stdout, the other tiles
+    # against tile 0 on the device (lines are independent => replicated tiles give replicated outputs)
+    verified, how = None, None
+    rec = None
+    for t in ctx.hashes.get(name, {}).get("tiles", []):
+        if t["rank"] == rank_tile and t["tile_bytes"] == tile_n:
+            rec = t
+    if rec is not None:
+        first = bytes(d_out[:rec["out_bytes"]].cpu().numpy().tobytes())
+        ok = hashlib.sha256(first).hexdigest() == rec["out_sha256"] and out_n == reps * rec["out_bytes"]
+        for r in range(1, reps):
+            ok = ok and bool(torch.equal(d_out[:rec["out_bytes"]], d_out[r * rec["out_bytes"]:(r + 1) * rec["out_bytes"]]))
+        verified, how = ok, "sha256 of the reference's stdout (tests/golden/config_hashes.json) for tile 0, tiles 1..%d equal tile 0" % (reps - 1)
+    elif info["exec_kind"] == T.EXEC_BYTEMAP:
+        lut = torch.frombuffer(bytearray(prog.bytemap()), dtype=torch.uint8).to(ctx.dev)
+        ok = out_n == n
+        for off in range(0, n, 256 * MiB):
+            want = lut[d_in[off:off + 256 * MiB].long()]
+            ok = ok and bool(torch.equal(want, d_out[off:off + 256 * MiB][: want.numel()]))
+            del want
+        verified, how = ok, "byte map applied by torch"
+    elif info["length_preserving"]:
+        ok = out_n == n
+        for r in range(1, reps):
+            ok = ok and bool(torch.equal(d_out[:tile_n], d_out[r * tile_n:(r + 1) * tile_n]))
+        verified, how = ok, "replicated tiles equal (no reference hash for this workload)"
+    verified_all = ctx.all_true(verified is not False)
+    res = {"prog": prog, "info": info, "n": n, "out_n": out_n, "ms_per_step": ms_per_step, "launches_per_step": launches_per_step,
+           "verified": (verified_all if verified is not None else None), "verified_how": how, "collectives": coll,
+           "clocks": sampler.summary() if sampler else None, "d_in": d_in, "d_out": d_out, "tile": tile, "tile_n": tile_n, "reps": reps}
+    return res
+
+
+def summarize(ctx, name, r, total_bytes):
+    peak, _ = measured_hbm_peak()
+    secs = r["ms_per_step"] * 1e-3
+    algo = float(r["n"] + r["out_n"])
+    return {"workload": name, "pattern": short_pattern(WORKLOADS[name][0]), "bytes_total": total_bytes, "bytes_per_gpu": r["n"],
+            "value": total_bytes / secs / 1e9, "unit": "GB/s", "ms_per_step": r["ms_per_step"],
+            "roofline_frac": algo / secs / 1e9 / peak, "exec": KERNELS[r["info"]["fast_path"]],
+            "launches_per_step": r["launches_per_step"], "verified": r["verified"], "verified_how": r["verified_how"]}
+
+
+def pcie_rates(ctx, n):
+    """Pinned cudaMemcpyAsync of the same size, same process: each direction alone and both at once (the e2e path
+    moves every byte once in each direction, concurrently: the bidirectional figure is its roofline)."""
+    torch = ctx.torch
+    n = min(n, 1 * GiB)
+    h_a = torch.empty(n, dtype=torch.uint8, pin_memory=True)
+    h_b = torch.empty(n, dtype=torch.uint8, pin_memory=True)
+    d_a = torch.empty(n, dtype=torch.uint8, device=ctx.dev)
+    d_b = torch.empty(n, dtype=torch.uint8, device=ctx.dev)
+    s1, s2 = torch.cuda.Stream(), torch.cuda.Stream()
+
+    def run(h2d, d2h, reps=3):
+        ctx.barrier()
+        t0 = time.perf_counter()
+        for _ in range(reps):
+            if h2d:
+                with torch.cuda.stream(s1):
+                    d_a.copy_(h_a, non_blocking=True)
+            if d2h:
+                with torch.cuda.stream(s2):
+                    h_b.copy_(d_b, non_blocking=True)
+        torch.cuda.synchronize()
+        dt = ctx.max_over_ranks(time.perf_counter() - t0)
+        return ctx.world * n * reps / dt / 1e9
+    run(True, True, 1)
+    res = {"h2d_gbs": run(True, False), "d2h_gbs": run(False, True), "bidir_gbs_per_direction": run(True, True),
+           "bytes": n, "note": "aggregate over %d GPU(s), pinned host memory, same process" % ctx.world}
+    del h_a, h_b, d_a, d_b
+    return res
+
+
+def end_to_end(ctx, prog, tile, tile_n, reps, n, out_cap, e2e_steps):
+    """Through the C ABI with HOST buffers (H2D + kernels + D2H inside the clock)."""
+    torch = ctx.torch
+    h_tile = torch.frombuffer(tile, dtype=torch.uint8)
+    h_in = torch.empty(n, dtype=torch.uint8, pin_memory=True)
+    for r in range(reps):
+        h_in[r * tile_n:(r + 1) * tile_n].copy_(h_tile)
+    h_out = torch.empty(out_cap, dtype=torch.uint8, pin_memory=True)
+    prog.scan_into(h_in.data_ptr(), n, h_out.data_ptr(), h_out.numel(), device=ctx.local_rank)   # warm-up
+    sweep = {}
+    best_mb, best = None, 0.0
+    for mb in (8, 16, 32, 64):
+        os.environ["TRRE_CHUNK_MB"] = str(mb)
+        prog.scan_into(h_in.data_ptr(), n, h_out.data_ptr(), h_out.numel(), device=ctx.local_rank)
+        ctx.barrier()
+        t0 = time.perf_counter()
+        prog.scan_into(h_in.data_ptr(), n, h_out.data_ptr(), h_out.numel(), device=ctx.local_rank)
+        torch.cuda.synchronize()
+        v = ctx.world * n / ctx.max_over_ranks(time.perf_counter() - t0) / 1e9
+        sweep[str(mb)] = round(v, 2)
+        if v > best:
+            best, best_mb = v, mb
+    os.environ["TRRE_CHUNK_MB"] = str(best_mb)
+    ctx.barrier()
+    t0 = time.perf_counter()
+    for _ in range(e2e_steps):
+        got = prog.scan_into(h_in.data_ptr(), n, h_out.data_ptr(), h_out.numel(), device=ctx.local_rank)
+    torch.cuda.synchronize()
+    dt = ctx.max_over_ranks(time.perf_counter() - t0)
+    first_ok = None
+    rec = [t for t in ctx.hashes.get("cfg2", {}).get("tiles", []) if t["rank"] == ctx.rank]
+    del h_in
+    res = {"value": ctx.world * n * e2e_steps / dt / 1e9, "unit": "GB/s", "h2d_bytes_per_step": ctx.world * n,
+           "d2h_bytes_per_step": ctx.world * got, "steps": e2e_steps, "chunk_mb": best_mb, "chunk_sweep_gbs": sweep,
+           "slots": 3, "numa": ctx.numa}
+    res["_h_out"] = h_out
+    return res
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -265,100 +559,34 @@ def main():
     ap.add_argument("--bytes", type=int, default=0, help="override bytes per GPU (for quick checks)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--e2e-steps", type=int, default=5)
+    ap.add_argument("--no-others", action="store_true", help="skip the other BASELINE configs after the headline")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
-    spec = list(WORKLOADS[args.workload])
+    name = args.workload
+    spec = list(WORKLOADS[name])
     if args.bytes:
         spec[2] = args.bytes
     spec = tuple(spec)
     if args.impl == "reference":
-        return run_reference(args, spec)
+        return run_reference(args, name, spec)
 
-    import torch
-    import trre_b200 as T
-
-    world = int(os.environ.get("WORLD_SIZE", "1"))
-    rank = int(os.environ.get("RANK", "0"))
-    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
-    if not torch.cuda.is_available():
-        raise SystemExit("bench.py: no CUDA device - the trre_b200 scan path has no CPU fallback")
-    torch.cuda.set_device(local_rank)
-    dev = torch.device("cuda", local_rank)
-    dist = None
-    if world > 1:
-        import torch.distributed as dist
-        dist.init_process_group("nccl", device_id=dev)
-
+    ctx = Ctx(args)
+    T, torch = ctx.T, ctx.torch
+    world, rank = ctx.world, ctx.rank
     pattern, flavor, nbytes, words, p_hit, lower, seed, refbin = spec
 
-    # ---- program: compiled once on rank 0, the flat tables broadcast to every rank -----------------
-    if rank == 0:
-        prog = T.compile(pattern, flavor)
-        blob = prog.blob()
+    # ---- headline: device-resident timing ------------------------------------------------------------------------------
+    r = measure(ctx, name, nbytes, args.steps, args.warmup, clocks=True)
+    prog, info, n, out_n, ms_per_step = r["prog"], r["info"], r["n"], r["out_n"], r["ms_per_step"]
+    value = world * n / (ms_per_step * 1e-3) / 1e9
+    sizes_t = torch.tensor([out_n], dtype=torch.int64, device=ctx.dev)
     if world > 1:
-        size = torch.tensor([len(blob) if rank == 0 else 0], dtype=torch.int64, device=dev)
-        dist.broadcast(size, 0)
-        buf = torch.empty(int(size.item()), dtype=torch.uint8, device=dev)
-        if rank == 0:
-            buf.copy_(torch.frombuffer(bytearray(blob), dtype=torch.uint8))
-        dist.broadcast(buf, 0)
-        if rank != 0:
-            prog = T.from_blob(bytes(buf.cpu().numpy().tobytes()))
-    info = prog.info
-
-    # ---- input: one synthetic tile per rank, replicated in HBM to the shard size ----------------------
-    tile = make_text(T, (pattern, flavor, nbytes, words, p_hit, lower, seed + rank, refbin), nbytes)
-    tile_n = len(tile)
-    reps = max(1, nbytes // tile_n)
-    n = tile_n * reps
-    h_tile = torch.frombuffer(tile, dtype=torch.uint8)
-    d_in = torch.empty(n, dtype=torch.uint8, device=dev)
-    d_tile = h_tile.to(dev)
-    for r in range(reps):
-        d_in[r * tile_n:(r + 1) * tile_n].copy_(d_tile)
-    del d_tile
-    out_cap = n + 64 if info["length_preserving"] else 2 * n + 64      # expanding programs: room for 2x
-    d_out = torch.empty(out_cap, dtype=torch.uint8, device=dev)
-    stream = torch.cuda.current_stream()
-    sp = stream.cuda_stream
-
-    def step():
-        prog.scan_device(d_in.data_ptr(), n, d_out.data_ptr(), d_out.numel(), device=local_rank, stream=sp, sync=False)
-
-    def barrier():
-        torch.cuda.synchronize()
-        if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize()
-
-    # ---- device-resident timing -------------------------------------------------------------------------
-    for _ in range(args.warmup):
-        step()
-    out_n = prog.scan_status(device=local_rank, stream=sp)
-    launches_per_step = prog.launches(device=local_rank)
-    barrier()
-    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    with ClockSampler(local_rank) as clocks:
-        ev0.record(stream)
-        for _ in range(args.steps):
-            step()
-        ev1.record(stream)
-        torch.cuda.synchronize()
-    ms = ev0.elapsed_time(ev1)
-    out_n = prog.scan_status(device=local_rank, stream=sp)
-    barrier()
-    t = torch.tensor([ms], dtype=torch.float64, device=dev)
-    sizes = torch.tensor([out_n], dtype=torch.int64, device=dev)
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        gathered = [torch.zeros_like(sizes) for _ in range(world)]
-        dist.all_gather(gathered, sizes)          # exclusive prefix of these = global output offsets
+        gathered = [torch.zeros_like(sizes_t) for _ in range(world)]
+        ctx.dist.all_gather(gathered, sizes_t)          # exclusive prefix of these = global output offsets
         sizes_all = [int(g.item()) for g in gathered]
     else:
         sizes_all = [out_n]
-    ms_max = float(t.item())
-    ms_per_step = ms_max / args.steps
-    value = world * n / (ms_per_step * 1e-3) / 1e9
+    d_in, d_out = r["d_in"], r["d_out"]
 
     # ---- calibration outside the clock: a plain device copy of the SAME size (the roofline denominator in
     # MEASURED_PEAKS.json was taken on 2 GiB buffers; fixed launch cost weighs more on 1 GiB)
@@ -368,142 +596,162 @@ def main():
             d_out[:n].copy_(d_in)
         torch.cuda.synchronize()
         c0, c1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        c0.record(stream)
+        c0.record(ctx.stream)
         for _ in range(10):
             d_out[:n].copy_(d_in)
-        c1.record(stream)
+        c1.record(ctx.stream)
         torch.cuda.synchronize()
         copy_gbs = 2.0 * n * 10 / (c0.elapsed_time(c1) * 1e-3) / 1e9
-        step()                      # restore d_out
-        prog.scan_status(device=local_rank, stream=sp)
+        prog.scan_device(d_in.data_ptr(), n, d_out.data_ptr(), d_out.numel(), device=ctx.local_rank, stream=ctx.sp, sync=True)   # restore d_out
     except Exception:
         pass
-
-    # ---- verification outside the clock (size independent): compare with the byte map applied by torch ---
-    verified = None
-    if info["exec_kind"] == T.EXEC_BYTEMAP:
-        lut = torch.frombuffer(bytearray(prog.bytemap()), dtype=torch.uint8).to(dev)
-        chunk = 256 * MiB
-        ok = out_n == n
-        for off in range(0, n, chunk):
-            want = lut[d_in[off:off + chunk].long()]
-            ok = ok and bool(torch.equal(want, d_out[off:off + chunk][: want.numel()]))
-            del want
-        verified = ok
-    elif info["length_preserving"]:
-        # replicated tiles must give replicated outputs (lines are independent)
-        ok = out_n == n
-        for r in range(1, reps):
-            ok = ok and bool(torch.equal(d_out[:tile_n], d_out[r * tile_n:(r + 1) * tile_n]))
-        verified = ok
 
     # ---- N > 1: the final gather of the output shards to rank 0 over NVLink, timed on its own (it is
     # NVLink-bound, 7 x shard / ~770 GB/s into one GPU, and would hide the scan if it sat inside the clock)
     gather = None
     if world > 1:
+        dist = ctx.dist
         offs = [0]
         for sz in sizes_all[:-1]:
             offs.append(offs[-1] + sz)
         total_out = offs[-1] + sizes_all[-1]
-        full = torch.empty(total_out if rank == 0 else 1, dtype=torch.uint8, device=dev)
+        full = torch.empty(total_out if rank == 0 else 1, dtype=torch.uint8, device=ctx.dev)
 
         def do_gather():
             ops = []
             if rank == 0:
                 full[:out_n].copy_(d_out[:out_n])
-                for r in range(1, world):
-                    ops.append(dist.P2POp(dist.irecv, full[offs[r]:offs[r] + sizes_all[r]], r))
+                for q in range(1, world):
+                    ops.append(dist.P2POp(dist.irecv, full[offs[q]:offs[q] + sizes_all[q]], q))
             else:
                 ops.append(dist.P2POp(dist.isend, d_out[:out_n], 0))
             for w in dist.batch_isend_irecv(ops):
                 w.wait()
 
         do_gather()                                   # warm-up (NCCL channel setup)
-        barrier()
+        ctx.barrier()
         g0, g1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        g0.record(stream)
+        g0.record(ctx.stream)
         do_gather()
-        g1.record(stream)
+        g1.record(ctx.stream)
         torch.cuda.synchronize()
-        gt = torch.tensor([g0.elapsed_time(g1)], dtype=torch.float64, device=dev)
-        dist.all_reduce(gt, op=dist.ReduceOp.MAX)
-        gms = float(gt.item())
+        gms = ctx.max_over_ranks(g0.elapsed_time(g1))
         moved = total_out - sizes_all[0]
         gather = {"ms": gms, "bytes_into_rank0": moved, "GB/s_into_rank0": moved / (gms * 1e-3) / 1e9,
                   "note": "NCCL point-to-point over NVLink 5 / NVSwitch, not part of value; measured peer-copy reference 770 GB/s"}
-        if rank == 0 and info["fast_path"] == 1:
-            lut_g = torch.frombuffer(bytearray(prog.bytemap()), dtype=torch.uint8).to(dev)
-            gather["first_shard_verified"] = bool(torch.equal(full[:out_n], lut_g[d_in.long()][:out_n]))
-            del lut_g
+        if rank == 0:
+            # every shard of the gathered buffer against the reference's hash of that rank's tile
+            ok = True
+            for q in range(world):
+                recs = [t for t in ctx.hashes.get(name, {}).get("tiles", []) if t["rank"] == q and t["tile_bytes"] == r["tile_n"]]
+                if not recs:
+                    ok = None
+                    break
+                shard = bytes(full[offs[q]:offs[q] + recs[0]["out_bytes"]].cpu().numpy().tobytes())
+                ok = ok and hashlib.sha256(shard).hexdigest() == recs[0]["out_sha256"]
+            gather["every_shard_matches_reference_sha256"] = ok
         del full
 
     # ---- end to end through the C ABI with host buffers (H2D + kernels + D2H inside the clock) -------------
     e2e = None
     if args.e2e_steps > 0:
-        h_in = torch.empty(n, dtype=torch.uint8, pin_memory=True)
-        for r in range(reps):
-            h_in[r * tile_n:(r + 1) * tile_n].copy_(h_tile)
-        h_out = torch.empty(out_cap, dtype=torch.uint8, pin_memory=True)
-        prog.scan_into(h_in.data_ptr(), n, h_out.data_ptr(), h_out.numel(), device=local_rank)   # warm-up
-        barrier()
-        t0 = time.perf_counter()
-        for _ in range(args.e2e_steps):
-            got = prog.scan_into(h_in.data_ptr(), n, h_out.data_ptr(), h_out.numel(), device=local_rank)
-        torch.cuda.synchronize()
-        dt = time.perf_counter() - t0
-        tt = torch.tensor([dt], dtype=torch.float64, device=dev)
-        if world > 1:
-            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
-        dt = float(tt.item())
-        e2e = {"value": world * n * args.e2e_steps / dt / 1e9, "unit": "GB/s",
-               "h2d_bytes_per_step": world * n, "d2h_bytes_per_step": world * got, "steps": args.e2e_steps}
-        del h_in, h_out
+        out_cap = d_out.numel()
+        del d_in, d_out
+        r["d_in"] = r["d_out"] = None
+        torch.cuda.empty_cache()
+        e2e = end_to_end(ctx, prog, r["tile"], r["tile_n"], r["reps"], n, out_cap, args.e2e_steps)
+        h_out = e2e.pop("_h_out")
+        recs = [t for t in ctx.hashes.get(name, {}).get("tiles", []) if t["rank"] == rank and t["tile_bytes"] == r["tile_n"]]
+        if recs:
+            ok = hashlib.sha256(bytes(h_out[:recs[0]["out_bytes"]].numpy().tobytes())).hexdigest() == recs[0]["out_sha256"]
+            e2e["verified"] = ctx.all_true(ok)
+        del h_out
+        pc = pcie_rates(ctx, n)
+        e2e["pcie"] = pc
+        e2e["frac_of_pcie"] = e2e["value"] / pc["bidir_gbs_per_direction"] if pc["bidir_gbs_per_direction"] else None
+        e2e["frac_of_pcie_note"] = "e2e input GB/s / measured bidirectional pinned-copy GB/s per direction (every byte crosses once each way)"
+    else:
+        del d_in, d_out
+        r["d_in"] = r["d_out"] = None
+    r["tile"] = None
+    torch.cuda.empty_cache()
+
+    # ---- the other BASELINE configs, same process, after the headline ---------------------------------------------------
+    others = None
+    if not args.no_others and name == "cfg2" and not args.bytes:
+        others = {}
+        plan = [("cfg1", 1_000_000, False), ("cfg1_1GiB", 1 * GiB, False), ("cfg3_1GiB", 1 * GiB, False), ("cfg4_1GiB", 1 * GiB, False),
+                ("cfg5_1GiB", 1 * GiB, False)]
+        if world == 1:
+            plan += [("cfg3", 8 * GiB, False), ("cfg5_64GiB", 64 * GiB, False)]
+        else:
+            plan += [("cfg4", 8 * GiB, True), ("cfg5_64GiB_split", 64 * GiB // world, True)]
+        free = torch.cuda.mem_get_info()[0]
+        for label, per_gpu, coll in plan:
+            wl = label.split("_")[0]
+            if 2 * per_gpu + (1 << 30) > free:
+                others[label] = {"skipped": "needs %d GiB of HBM" % ((2 * per_gpu) >> 30)}
+                continue
+            try:
+                steps = 10 if per_gpu <= 8 * GiB else 3
+                m = measure(ctx, wl, per_gpu, steps, 3, collectives=coll)
+                s = summarize(ctx, wl, m, world * m["n"])
+                if coll:
+                    s["collectives"] = m["collectives"]
+                    s["scaling"] = "strong (64 GiB split over the ranks)" if "split" in label else "weak"
+                others[label] = s
+                del m
+            except Exception as e:                      # a failing extra must not take the headline with it
+                others[label] = {"error": str(e)[:200]}
+            torch.cuda.empty_cache()
 
     if rank != 0:
         if world > 1:
-            dist.destroy_process_group()
+            ctx.dist.destroy_process_group()
         return 0
 
     peak, peak_src = measured_hbm_peak()
     algo_bytes = float(n + out_n)            # 1 B read per input byte + 1 B written per output byte
     achieved = algo_bytes / (ms_per_step * 1e-3) / 1e9
-    traffic = None
-    prof = os.path.join(ROOT, "profiles", "traffic_%s.json" % args.workload)
+    traffic, traffic_src = None, None
+    prof = os.path.join(ROOT, "profiles", "traffic_%s.json" % name)
     if os.path.exists(prof):
         try:
             with open(prof) as f:
-                traffic = json.load(f).get("dram_bytes_per_launch")
+                tj = json.load(f)
+            traffic = tj.get("dram_bytes_per_launch")
+            traffic_src = tj.get("source", "ncu --set full capture committed under profiles/ (not measured in this run)")
         except Exception:
             pass
-    kernel = {0: "k_lines_s<count> + k_scan_groups + k_lines_s<write>" if info["exec_kind"] != T.EXEC_BACKTRACK
-                 else "k_lines<dfs> count + k_scan_groups + k_lines<dfs> write",
-              1: "k_bytemap", 2: "k_match", 3: "k_bmv_count + k_scan_groups + k_bmv_write",
-              4: "k_match<count> + k_scan_groups + k_match<write>", 5: "k_lines<inplace>"}[info["fast_path"]]
+    kernel = KERNELS[info["fast_path"]] if info["exec_kind"] != T.EXEC_BACKTRACK else "k_lines<dfs> count + k_scan_groups + k_lines<dfs> write"
+    if info["exec_kind"] == T.EXEC_BYTEMAP:
+        kernel = "k_bytemap_swar" if os.environ.get("TRRE_NO_SWAR") is None else "k_bytemap"
     line = {
         "metric": METRIC, "value": value, "unit": "GB/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "u8", "data": "synthetic",
-        "config": {"workload": DESCR[args.workload], "pattern": pattern if len(pattern) < 200 else pattern[:60] + "...(%d bytes)" % len(pattern),
-                   "flavor": "dft" if flavor else "nft", "bytes_per_gpu": n, "exec": kernel, "dsa_states": info["dsa_states"], "nft_states": info["nft_states"],
-                   "l2": "input %d MiB per step exceeds the 126 MB L2; no flush needed" % (n // MiB),
-                   "parallelism": "lines sharded over %d GPU(s), program blob broadcast, sizes all-gathered" % world},
-        "clocks": clocks.summary(),
+        "config": config_of(name, (pattern, flavor, n), world),
+        "config_detail": {"exec": kernel, "dsa_states": info["dsa_states"], "nft_states": info["nft_states"],
+                          "l2": "input %d MiB per step exceeds the 126 MB L2; no flush needed" % (n // MiB),
+                          "parallelism": "lines sharded over %d GPU(s), program blob broadcast, sizes all-gathered" % world},
+        "clocks": r["clocks"],
         "e2e": e2e,
-        "gpu_launches": launches_per_step * args.steps,
+        "gpu_launches": r["launches_per_step"] * args.steps,
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                     "traffic": traffic, "kernel": kernel, "peak_source": peak_src,
+                     "traffic": traffic, "traffic_source": traffic_src, "kernel": kernel, "peak_source": peak_src,
                      "algorithmic_bytes_per_launch": algo_bytes,
                      "input_read_frac_of_peak": value / world / peak,
                      "torch_copy_same_size_gbs": copy_gbs},
-        "verified": verified,
+        "verified": r["verified"], "verified_how": r["verified_how"],
         "output_bytes_per_rank": sizes_all,
         "gather": gather,
+        "others": others,
     }
     if world == 1 and not args.no_cpu_baseline:
         line["cpu_baseline"] = cpu_baseline(T, spec)
     print(json.dumps(line))
     if world > 1:
-        dist.destroy_process_group()
+        ctx.dist.destroy_process_group()
     return 0
 
 

@@ -169,6 +169,11 @@ int  trre_match_host(const trre_prog *p, int scan, int all,
 int  trre_synth_text(uint64_t seed, uint8_t *buf, size_t n,
                      const char *words, double p_hit, int lowercase_only);
 
+/* Page-locked host memory for trre_scan_into: with it the H2D / D2H copies of the chunk pipeline are truly asynchronous
+ * (pageable memory is staged by the driver).  NULL when there is no usable CUDA device. */
+void       *trre_host_alloc(size_t nbytes);
+void        trre_host_free(void *p);
+
 void        trre_free(void *p);
 const char *trre_last_error(void);
 const char *trre_version(void);

@@ -845,3 +845,60 @@ int trre_oracle_run(const char *expr, int flavor, int mode, int all,
 void trre_oracle_free(void *p) { free(p); }
 size_t trre_oracle_last_nstates(void) { return g_last_nstates; }
 size_t trre_oracle_last_dstates(void) { return g_last_dstates; }
+
+/* ---- synthetic corpus (BASELINE.md s3 / SURVEY.md s8d) ----------------------------------------------------------
+ * Second, independent implementation of the generator the product exports as trre_synth_text(): bench.py's
+ * --impl reference arm builds its input with this one so that it never maps the product's library, and
+ * tests/test_bench_contract.py checks the two byte for byte.  splitmix64 stream: line target 40 + r % 81; per token
+ * one draw r (low 32 bits < p_hit * 2^32: hit word number (r >> 32) % n_words; else 1 + (r >> 32) % maxtok random
+ * characters, 12 bits each from two further draws); single spaces; the buffer's last byte is '\n'. */
+static uint64_t corpus_next(uint64_t *x) {
+    uint64_t z = (*x += 0x9E3779B97F4A7C15ull);
+    z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
+    z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
+    return z ^ (z >> 31);
+}
+
+int trre_oracle_synth_text(uint64_t seed, uint8_t *buf, size_t n, const char *words, double p_hit, int lowercase_only) {
+    static const char mixed[] = "abcdefghijklmnopqrstuvwxyzABCDEFGHIJKLMNOPQRSTUVWXYZ0123456789.,;";
+    const char *alpha = mixed;                                /* its first 26 characters are the lowercase set */
+    const uint64_t nalpha = lowercase_only ? 26 : 65, maxtok = lowercase_only ? 8 : 10;
+    const char **hit = NULL;
+    size_t *hit_len = NULL, n_hits = 0, cap = 0;
+    if (!buf && n) return 1;
+    for (const char *w = words; w && *w;) {
+        const char *e = strchr(w, '\n');
+        size_t len = e ? (size_t)(e - w) : strlen(w);
+        if (len) {
+            if (n_hits == cap) {
+                cap = cap ? 2 * cap : 64;
+                hit = (const char **)realloc((void *)hit, cap * sizeof *hit);
+                hit_len = (size_t *)realloc(hit_len, cap * sizeof *hit_len);
+                if (!hit || !hit_len) return 1;
+            }
+            hit[n_hits] = w; hit_len[n_hits++] = len;
+        }
+        w += len + (e ? 1 : 0);
+    }
+    const uint64_t thresh = (p_hit <= 0 || !n_hits) ? 0 : (uint64_t)(p_hit * 4294967296.0);
+    uint64_t st = seed;
+    size_t pos = 0, line_len = 0, target = 40 + corpus_next(&st) % 81;
+    while (pos < n) {
+        const uint64_t r = corpus_next(&st);
+        if ((r & 0xFFFFFFFFull) < thresh) {
+            const size_t k = (size_t)((r >> 32) % n_hits);
+            for (size_t c = 0; c < hit_len[k] && pos < n; ++c, ++line_len) buf[pos++] = (uint8_t)hit[k][c];
+        } else {
+            const uint64_t len = 1 + (r >> 32) % maxtok, b0 = corpus_next(&st), b1 = corpus_next(&st);
+            for (uint64_t c = 0; c < len && pos < n; ++c, ++line_len)
+                buf[pos++] = (uint8_t)alpha[((c < 5 ? b0 >> (c * 12) : b1 >> ((c - 5) * 12)) & 0xFFF) % nalpha];
+        }
+        if (pos >= n) break;
+        if (line_len >= target) { buf[pos++] = '\n'; line_len = 0; target = 40 + corpus_next(&st) % 81; }
+        else { buf[pos++] = ' '; ++line_len; }
+    }
+    if (n) buf[n - 1] = '\n';
+    free((void *)hit);
+    free(hit_len);
+    return 0;
+}

@@ -42,6 +42,11 @@ void trre_oracle_free(void *p);
 size_t trre_oracle_last_nstates(void);
 size_t trre_oracle_last_dstates(void);
 
+/* The synthetic corpus of BASELINE.md s3, implemented a second time (the product exports trre_synth_text): what
+ * bench.py --impl reference feeds the reference binary, without loading the product's library.  `words`: hit list,
+ * '\n'-separated, or NULL. */
+int trre_oracle_synth_text(uint64_t seed, uint8_t *buf, size_t n, const char *words, double p_hit, int lowercase_only);
+
 #ifdef __cplusplus
 }
 #endif

@@ -32,6 +32,9 @@ def lib():
         L.trre_oracle_free.argtypes = [ctypes.c_void_p]
         L.trre_oracle_last_nstates.restype = ctypes.c_size_t
         L.trre_oracle_last_dstates.restype = ctypes.c_size_t
+        L.trre_oracle_synth_text.restype = ctypes.c_int
+        L.trre_oracle_synth_text.argtypes = [ctypes.c_uint64, ctypes.c_void_p, ctypes.c_size_t, ctypes.c_char_p,
+                                             ctypes.c_double, ctypes.c_int]
         _lib = L
     return _lib
 
@@ -48,6 +51,19 @@ def oracle_run(expr: bytes, data: bytes, flavor=NFT, mode=SCAN, all_=False):
     if out.value:
         L.trre_oracle_free(out)
     return rc, res, err.value.decode("latin1")
+
+
+def oracle_synth_text(seed, n, words=None, p_hit=0.0, lowercase_only=False) -> bytearray:
+    """The synthetic corpus from the oracle library's own generator - what bench.py's reference arm
+    uses, so that it never maps the product's library."""
+    buf = bytearray(n)
+    if n:
+        arr = (ctypes.c_ubyte * n).from_buffer(buf)
+        w = None if not words else "\n".join(words).encode("latin1")
+        rc = lib().trre_oracle_synth_text(seed, ctypes.addressof(arr), n, w, float(p_hit), int(lowercase_only))
+        del arr
+        assert rc == 0
+    return buf
 
 
 def have_ref():

@@ -44,6 +44,31 @@ def test_cli_file_argument(tmp_path):
     assert r.returncode == rc and r.stdout == want
 
 
+@pytest.mark.parametrize("flavor", [NFT, DFT])
+def test_cli_streams_inputs_larger_than_its_block_ring(flavor, monkeypatch):
+    """Scan mode is a stream (trre_nft.c:776-790): with 1 MiB blocks a 12 MiB pipe crosses the 3-block ring four times;
+    a 3 MiB line makes a block grow; the last record has no newline."""
+    monkeypatch.setenv("TRRE_CLI_BLOCK_MB", "1")
+    big = bytes(T.synth_text(0x72726507, 12 << 20, ["cat", "dog", "catdog"], 0.25))
+    long_line = big[:5 << 20].replace(b"\n", b" ", 40000) + b"x" * (3 << 20) + b"\ncat dog\n" + big[:700000] + b"cat"
+    for expr, data in (("(cat:dog|dog:cat)", big), ("[a:A-z:Z]", big), ("a:", big), ("cat:mouse", big[:4 << 20]),
+                       ("cat:dog", long_line), ("a+:x", big[:3 << 20])):
+        rc, want = expected(expr, data, flavor)
+        r = subprocess.run([BIN[flavor], expr], input=data, capture_output=True)
+        assert r.returncode == rc and r.stdout == want, (expr, flavor, len(r.stdout), len(want), r.stderr[:200])
+
+
+def test_cli_prints_what_precedes_a_failing_block(monkeypatch):
+    """A runtime error ("stack max capacity reached") ends the reference after it has printed the earlier lines; the
+    streaming CLI has printed the earlier blocks."""
+    monkeypatch.setenv("TRRE_CLI_BLOCK_MB", "1")
+    head = bytes(T.synth_text(9, 2 << 20)).replace(b"a", b"e")
+    data = head + b"a" * 70000 + b"\n"
+    r = subprocess.run([BIN[NFT], "(a:x)*b|a"], input=data, capture_output=True)
+    assert r.returncode == 1 and b"stack max capacity reached" in r.stderr
+    assert len(r.stdout) >= 1 << 20 and head.startswith(r.stdout)
+
+
 def test_cli_match_flags_stay_on_the_host():
     r = subprocess.run([BIN[NFT], "-ma", "(.:x)*.*"], input=b"aaa\n", capture_output=True)
     assert r.stdout == b"xxx\nxxa\nxaa\naaa\n"

@@ -1010,12 +1010,90 @@ bool blob_is_valid(const void *blob, size_t nbytes, std::string *why) {
     if (h.magic != 0x32425254u) return bad("bad magic");
     if (h.abi != TRRE_B200_ABI_VERSION) return bad("ABI version mismatch");
     if (h.total_bytes != nbytes) return bad("size mismatch");
-    uint64_t need_trans = (uint64_t)h.off_trans + (uint64_t)h.dsa_states * h.n_classes * 8;
-    uint64_t need_sinfo = (uint64_t)h.off_sinfo + (uint64_t)h.dsa_states * 8;
-    uint64_t need_nft = (uint64_t)h.off_nft + (uint64_t)h.nft_states * sizeof(NftFlat);
-    if (need_trans > nbytes || need_sinfo > nbytes || need_nft > nbytes ||
-        (uint64_t)h.off_pool + h.pool_bytes > nbytes || (uint64_t)h.off_startrow + 256 > nbytes)
+    if (h.flavor > 1 || h.exec_kind > TRRE_EXEC_LAZY) return bad("unknown flavor / executor");
+    if (h.n_classes < 1 || h.n_classes > 256) return bad("class count out of range");
+    // every section the header names must lie inside the blob (0 = absent for the optional ones)
+    auto inside = [&](uint64_t off, uint64_t bytes, bool optional) {
+        if (off == 0 && optional) return true;
+        return off >= sizeof(BlobHeader) && off + bytes <= nbytes;
+    };
+    const uint64_t cells = (uint64_t)h.dsa_states * h.n_classes;
+    if (!inside(h.off_classmap, 256, false) || !inside(h.off_lut, 256, false) || !inside(h.off_startrow, 256, false) ||
+        !inside(h.off_trans, cells * 8, cells == 0) || !inside(h.off_sinfo, (uint64_t)h.dsa_states * 8, h.dsa_states == 0) ||
+        !inside(h.off_pool, h.pool_bytes, h.pool_bytes == 0) || !inside(h.off_nft, (uint64_t)h.nft_states * sizeof(NftFlat), h.nft_states == 0) ||
+        !inside(h.off_pairlut, 65536 * 2, true) || !inside(h.off_row0, 1024, true) || !inside(h.off_ctrans, cells * 4, true) ||
+        !inside(h.off_vent, 1024, true) || !inside(h.off_vpairlen, 65536 * 2, true) || !inside(h.off_vpool, h.vpool_bytes, true) ||
+        !inside(h.off_eout, (cells + h.dsa_states) * 4, true))
         return bad("section out of range");
+    const uint8_t *b = static_cast<const uint8_t *>(blob);
+    // flags must agree with the sections they promise
+    if (h.exec_kind == TRRE_EXEC_BYTEMAP && !h.off_pairlut) return bad("byte map without its pair table");
+    if ((h.flags & PF_BYTEMAP_VAR) && !(h.off_vent && h.off_vpairlen)) return bad("variable byte map without its tables");
+    if ((h.flags & (PF_MATCHABLE | PF_MATCHABLE_VAR)) && !(h.off_row0 && h.off_ctrans)) return bad("match program without compact tables");
+    if ((h.exec_kind == TRRE_EXEC_TABLE) && h.dsa_states == 0) return bad("table program without states");
+    if (h.swar_n > 4) return bad("byte-map range count");
+    for (uint32_t k = 0; k < h.swar_n; ++k) {
+        const uint32_t lo = h.swar[k] & 0xFFu, hi = (h.swar[k] >> 8) & 0xFFu;
+        if (lo > hi || (lo < 0x80u) != (hi < 0x80u)) return bad("byte-map range");
+    }
+    if (h.flags & PF_GRAM) {
+        uint64_t e = 1;
+        if (h.gram_depth < 1 || h.gram_depth > 6) return bad("gram depth");
+        for (uint32_t i = 0; i < h.gram_depth; ++i) e *= h.n_classes;
+        if (e != h.gram_entries || e > 640u * 1024u) return bad("gram table size");
+        if (!inside(h.off_gbits, (e + 31) / 32 * 4, false) || !inside(h.off_gout, e * 4, false) ||
+            !inside(h.off_gpool, h.gpool_bytes, h.gpool_bytes == 0) || h.gram_len > 16)
+            return bad("gram section out of range");
+        if (!(h.gram_flags & GRAM_DIRECT_FLAG)) {
+            const uint32_t *go = reinterpret_cast<const uint32_t *>(b + h.off_gout);
+            for (uint64_t k = 0; k < e; ++k)
+                if ((uint64_t)(go[k] & 0xFFFFFu) + ((go[k] >> 20) & 0xFFu) > h.gpool_bytes && go[k]) return bad("gram output reference");
+        }
+    }
+    // table contents: every class < n_classes, every next state < dsa_states (or DEAD), every string inside the pool
+    const uint8_t *cm = b + h.off_classmap;
+    for (int c = 0; c < 256; ++c)
+        if (cm[c] >= h.n_classes) return bad("class map entry out of range");
+    auto ref_ok = [&](uint32_t hi) {
+        const uint32_t len = hi >> 24, off = hi & 0xFFFFFFu;
+        if (len == 255u) {
+            if ((uint64_t)off + 4 > h.pool_bytes) return false;
+            uint32_t l2;
+            std::memcpy(&l2, b + h.off_pool + off, 4);
+            return (uint64_t)off + 4 + l2 <= h.pool_bytes;
+        }
+        return (uint64_t)off + len <= h.pool_bytes;
+    };
+    if (cells) {
+        const uint64_t *tr = reinterpret_cast<const uint64_t *>(b + h.off_trans);
+        for (uint64_t k = 0; k < cells; ++k) {
+            const uint32_t nx = (uint32_t)tr[k] & 0xFFFFFFu;
+            if (nx != DSA_DEAD && nx >= h.dsa_states) return bad("transition target out of range");
+            if (!ref_ok((uint32_t)(tr[k] >> 32))) return bad("transition output out of range");
+        }
+        const uint64_t *si = reinterpret_cast<const uint64_t *>(b + h.off_sinfo);
+        for (uint32_t k = 0; k < h.dsa_states; ++k)
+            if (!ref_ok((uint32_t)(si[k] >> 32))) return bad("final output out of range");
+        if (h.off_ctrans) {
+            const uint32_t *ct = reinterpret_cast<const uint32_t *>(b + h.off_ctrans);
+            for (uint64_t k = 0; k < cells; ++k)
+                if ((ct[k] & 0xFFFFFFu) != DSA_DEAD && (ct[k] & 0xFFFFFFu) >= h.dsa_states) return bad("compact transition out of range");
+        }
+        if (h.off_eout) {
+            const uint32_t *eo = reinterpret_cast<const uint32_t *>(b + h.off_eout);
+            for (uint64_t k = 0; k < cells + h.dsa_states; ++k)
+                if ((uint64_t)(eo[k] & 0xFFFFFFu) + (eo[k] >> 24) > h.pool_bytes) return bad("match output out of range");
+        }
+    }
+    if (h.nft_states) {
+        if (h.nft_start < -1 || h.nft_start >= (int32_t)h.nft_states) return bad("NFT start out of range");
+        const NftFlat *nf = reinterpret_cast<const NftFlat *>(b + h.off_nft);
+        for (uint32_t k = 0; k < h.nft_states; ++k)
+            if (nf[k].op > N_FINAL || nf[k].a < -1 || nf[k].a >= (int32_t)h.nft_states || nf[k].b < -1 || nf[k].b >= (int32_t)h.nft_states)
+                return bad("NFT link out of range");
+    } else if (h.exec_kind == TRRE_EXEC_BACKTRACK || h.exec_kind == TRRE_EXEC_LAZY) {
+        return bad("executor needs the NFT");
+    }
     return true;
 }
 

@@ -210,6 +210,15 @@ int get_state(const trre_prog *cp, int device, DeviceState **out) {
     }
     if (device < 0 || device >= ndev) { g_last_error = "device index out of range"; return TRRE_E_ARG; }
     DeviceState *d = new DeviceState();
+    struct Undo {                                          // a CUDA_TRY that fails below must not leak the half-built state
+        DeviceState *d;
+        ~Undo() {
+            if (!d) return;
+            cudaFree(d->d_blob); cudaFree(d->d_total); cudaFree(d->d_status);
+            cudaFreeHost(d->h_total); cudaFreeHost(d->h_status);
+            delete d;
+        }
+    } undo{d};
     d->device = device;
     const BlobHeader &h = p->hdr;
     CUDA_TRY(cudaMalloc(&d->d_blob, p->blob.size()));
@@ -289,6 +298,7 @@ int get_state(const trre_prog *cp, int device, DeviceState **out) {
         }
     }
     p->dev[device] = d;
+    undo.d = nullptr;
     *out = d;
     return TRRE_OK;
 }
@@ -863,6 +873,21 @@ const char *trre_version(void) { return "trre_b200 0.1 (sm_100a)"; }
 const char *trre_last_error(void) { return g_last_error.c_str(); }
 void trre_free(void *p) { std::free(p); }
 
+void *trre_host_alloc(size_t nbytes) {
+    void *p = nullptr;
+    cudaError_t e = cudaHostAlloc(&p, nbytes ? nbytes : 1, cudaHostAllocPortable);
+    if (e != cudaSuccess) {
+        g_last_error = std::string("no CUDA device: the trre_b200 scan path has no CPU fallback (") + cudaGetErrorString(e) + ")";
+        cudaGetLastError();
+        return nullptr;
+    }
+    return p;
+}
+
+void trre_host_free(void *p) {
+    if (p) cudaFreeHost(p);
+}
+
 int trre_compile(const char *expr, int flavor, trre_prog **out, char *err, size_t errcap) {
     if (!expr || !out) { set_err(err, errcap, "null argument"); return TRRE_E_ARG; }
     *out = nullptr;
@@ -1007,6 +1032,7 @@ int trre_scan_device(const trre_prog *p, int device, const uint8_t *d_in, size_t
 int trre_scan_status(const trre_prog *p, int device, size_t *out_n, void *stream) {
     if (!p) return TRRE_E_ARG;
     DeviceGuard guard(device);
+    if (!guard.ok) { g_last_error = "no CUDA device: the trre_b200 scan path has no CPU fallback"; return TRRE_E_CUDA; }
     DeviceState *d = nullptr;
     int rc = get_state(p, device, &d);
     if (rc != TRRE_OK) return rc;
@@ -1015,6 +1041,8 @@ int trre_scan_status(const trre_prog *p, int device, size_t *out_n, void *stream
 
 int trre_scan_launches(const trre_prog *p, int device) {
     if (!p) return -1;
+    DeviceGuard guard(device);
+    if (!guard.ok) return -1;
     DeviceState *d = nullptr;
     if (get_state(p, device, &d) != TRRE_OK) return -1;
     return d->launches;
@@ -1024,6 +1052,7 @@ int trre_scan_into(const trre_prog *p, int device, const uint8_t *in, size_t n, 
                    size_t *out_n) {
     if (!p || (n && !in)) { g_last_error = "null argument"; return TRRE_E_ARG; }
     if (out_n) *out_n = 0;
+    if (n == 0) return TRRE_OK;                                   // empty input: empty output (trre_nft.c:776: no record)
     DeviceGuard guard(device);
     if (!guard.ok) { g_last_error = "no CUDA device: the trre_b200 scan path has no CPU fallback"; return TRRE_E_CUDA; }
     DeviceState *d = nullptr;
@@ -1111,6 +1140,9 @@ int trre_scan_multi(const trre_prog *p, const int *devices, int ndev, const uint
     if (!p || !devices || ndev < 1 || !out || !out_n || (n && !in)) { g_last_error = "bad argument"; return TRRE_E_ARG; }
     *out = nullptr; *out_n = 0;
     if (ndev == 1) return trre_scan(p, devices[0], in, n, out, out_n);
+    for (int a = 0; a < ndev; ++a)
+        for (int b = a + 1; b < ndev; ++b)
+            if (devices[a] == devices[b]) { g_last_error = "trre_scan_multi: the same device is listed twice"; return TRRE_E_ARG; }
     std::vector<size_t> cuts((size_t)ndev + 1);
     int rc = trre_shard_lines(in, n, ndev, cuts.data());
     if (rc != TRRE_OK) return rc;

@@ -30,7 +30,7 @@ constexpr int kMatchThreads = 512;
 constexpr int kMatchWarps = kMatchThreads / 32;
 constexpr int kTile = 512;                       // bytes per warp iteration
 constexpr int kWarpSmem = 544 + 544 + 1024 + 16; // s_in (+halo), s_out (+halo), list of real matches (u16 x 512), its counter
-constexpr int kWarmTiles = 8;                    // warm-up looks back at most 4 KB for a '\n'
+constexpr int kWarmTiles = 128;                  // warm-up looks back at most 64 KB for a '\n' (stops at the first one)
 
 struct MatchArgs {
     DevProg P;
