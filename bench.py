@@ -304,6 +304,64 @@ def cpu_baseline(T, spec):
                       "oracle/_ref/%s is single threaded (host has %d cores)" % (sample_n // MiB, refbin, os.cpu_count() or 0)}
 
 
+def cli_end_to_end(T, name, spec):
+    """What a user of the drop-in feels: `bin/trre_dft EXPR FILE > /dev/null` on a file in /dev/shm, wall clock of the
+    whole process (CUDA context creation, compilation, streaming read -> GPU -> write), next to the reference binary on a
+    sample of the same file."""
+    pattern, flavor, nbytes, words, p_hit, lower, seed, refbin = spec
+    exe = os.path.join(ROOT, "bin", refbin)
+    ref = os.path.join(ROOT, "oracle", "_ref", refbin)
+    if not os.access(exe, os.X_OK):
+        return None
+    shm = "/dev/shm" if os.path.isdir("/dev/shm") else tempfile.gettempdir()
+    path = os.path.join(shm, "trre_bench_cli_%d.txt" % os.getpid())
+    tile = bytes(T.synth_text(seed, min(TILE, nbytes), words, p_hit, lower))
+    reps = max(1, nbytes // len(tile))
+    try:
+        with open(path, "wb") as f:
+            for _ in range(reps):
+                f.write(tile)
+        n = reps * len(tile)
+        times = []
+        for _ in range(2):
+            t0 = time.perf_counter()
+            with open(os.devnull, "wb") as fout:
+                subprocess.run([exe, pattern, path], stdout=fout, check=True)
+            times.append(time.perf_counter() - t0)
+        # correctness of the streamed output: sha256 of the whole stdout against the reference's hash, tile by tile
+        h = hashlib.sha256()
+        p = subprocess.Popen([exe, pattern, path], stdout=subprocess.PIPE)
+        first = p.stdout.read(len(tile))
+        rest_ok = True
+        for _ in range(1, reps):
+            rest_ok = rest_ok and p.stdout.read(len(tile)) == first
+        tail = p.stdout.read()
+        p.wait()
+        rec = [t for t in config_hashes().get(name, {}).get("tiles", []) if t["rank"] == 0 and t["tile_bytes"] == len(tile)]
+        verified = None
+        if rec and rec[0]["out_bytes"] == len(tile):
+            verified = hashlib.sha256(first).hexdigest() == rec[0]["out_sha256"] and rest_ok and tail == b"" and p.returncode == 0
+        out = {"seconds": min(times), "value": n / min(times) / 1e9, "unit": "GB/s", "bytes": n, "verified": verified,
+               "command": "bin/%s EXPR FILE > /dev/null, file in /dev/shm, best of 2, whole process" % refbin}
+        if os.access(ref, os.X_OK):
+            sample = min(n, 64 * MiB)
+            spath = path + ".sample"
+            with open(spath, "wb") as f:
+                f.write(tile[:sample])
+            t0 = time.perf_counter()
+            with open(os.devnull, "wb") as fout:
+                subprocess.run([ref, pattern, spath], stdout=fout, check=True)
+            dt = time.perf_counter() - t0
+            os.unlink(spath)
+            out["reference_gbs"] = sample / dt / 1e9
+            out["reference_sample_bytes"] = sample
+            out["speedup_vs_reference_cli"] = out["value"] / out["reference_gbs"]
+        return out
+    finally:
+        if os.path.exists(path):
+            os.unlink(path)
+
+
 # ---------------------------------------------------------------------------------------------------------------------
 # the B200 arm
 # ---------------------------------------------------------------------------------------------------------------------
@@ -590,7 +648,7 @@ def main():
 
     # ---- calibration outside the clock: a plain device copy of the SAME size (the roofline denominator in
     # MEASURED_PEAKS.json was taken on 2 GiB buffers; fixed launch cost weighs more on 1 GiB)
-    copy_gbs = None
+    copy_gbs = sm_copy_gbs = None
     try:
         for _ in range(3):
             d_out[:n].copy_(d_in)
@@ -602,6 +660,18 @@ def main():
         c1.record(ctx.stream)
         torch.cuda.synchronize()
         copy_gbs = 2.0 * n * 10 / (c0.elapsed_time(c1) * 1e-3) / 1e9
+        # the copy above is a DMA-engine memcpy; what an SM streaming kernel gets on the same buffers (torch's vectorised
+        # elementwise kernel on 8-byte words) calibrates how much of the remaining gap is the SM load/store path itself
+        v_in, v_out = d_in[:n - n % 8].view(torch.int64), d_out[:n - n % 8].view(torch.int64)
+        for _ in range(3):
+            torch.bitwise_and(v_in, 0x5F5F5F5F5F5F5F5F, out=v_out)
+        torch.cuda.synchronize()
+        c0.record(ctx.stream)
+        for _ in range(10):
+            torch.bitwise_and(v_in, 0x5F5F5F5F5F5F5F5F, out=v_out)
+        c1.record(ctx.stream)
+        torch.cuda.synchronize()
+        sm_copy_gbs = 2.0 * (n - n % 8) * 10 / (c0.elapsed_time(c1) * 1e-3) / 1e9
         prog.scan_device(d_in.data_ptr(), n, d_out.data_ptr(), d_out.numel(), device=ctx.local_rank, stream=ctx.sp, sync=True)   # restore d_out
     except Exception:
         pass
@@ -741,7 +811,7 @@ def main():
                      "traffic": traffic, "traffic_source": traffic_src, "kernel": kernel, "peak_source": peak_src,
                      "algorithmic_bytes_per_launch": algo_bytes,
                      "input_read_frac_of_peak": value / world / peak,
-                     "torch_copy_same_size_gbs": copy_gbs},
+                     "torch_copy_same_size_gbs": copy_gbs, "torch_elementwise_kernel_same_size_gbs": sm_copy_gbs},
         "verified": r["verified"], "verified_how": r["verified_how"],
         "output_bytes_per_rank": sizes_all,
         "gather": gather,
@@ -749,6 +819,10 @@ def main():
     }
     if world == 1 and not args.no_cpu_baseline:
         line["cpu_baseline"] = cpu_baseline(T, spec)
+        try:
+            line["cli_e2e"] = cli_end_to_end(T, name, spec)
+        except Exception as e:
+            line["cli_e2e"] = {"error": str(e)[:200]}
     print(json.dumps(line))
     if world > 1:
         ctx.dist.destroy_process_group()

@@ -390,7 +390,7 @@ def test_dfs_executor_has_the_reference_stack_capacity():
     expr = "(a:x)*b|a"
     prog = T.compile(expr, NFT)
     assert prog.exec_kind == T.EXEC_BACKTRACK
-    for run in (20000, 60000):
+    for run in (12000, 30000):
         data = b"ab\n" + b"a" * run + b"\n" + b"aaab\n"
         rc, want, _ = oracle_run(expr.encode(), data, flavor=NFT)
         assert rc == 0 and prog.scan(data) == want, run
@@ -400,3 +400,18 @@ def test_dfs_executor_has_the_reference_stack_capacity():
     with pytest.raises(T.TrreError) as ei:
         T.compile(expr, NFT).scan(data)
     assert ei.value.code == 5 and "stack max capacity reached" in ei.value.text
+
+
+# ---- automata with a cycle on the position-parallel kernels (attempts capped at 16 bytes) ---------------------------
+
+@pytest.mark.parametrize("expr,flavor", [("[0-9]+:#", NFT), ("a+:x", NFT), ("(a:b)+", NFT), ("[a-c]+ing:X", NFT), ("(ab)+:X", NFT),
+                                         ("a*b:x", NFT), ("(a:b)+c", DFT)])
+def test_cyclic_automata_short_attempts_stay_position_parallel(expr, flavor):
+    prog = T.compile(expr, flavor)
+    assert prog.info["max_depth"] == 0xFFFFFFFF and prog.info["fast_path"] in (2, 4), prog.info
+    text = bytes(T.synth_text(0x72726508, 2 << 20, ["ab", "abab", "aab", "bing", "acing", "1234", "77"], 0.3))
+    for data in (text,                                                  # attempts of at most ~10 bytes: fast path
+                 text[:1 << 20] + b"x" + b"7" * 40 + b"ab" * 30 + b"a" * 100 + b"b ing\n" + text[:1 << 19],   # long attempts: fallback
+                 _ab_text(91, 1 << 20, b"ab1 ", 0, 300)):
+        rc, want, _ = oracle_run(expr.encode(), data, flavor=flavor)
+        assert rc == 0 and prog.scan(data) == want, (expr, flavor, len(data))

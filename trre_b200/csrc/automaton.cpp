@@ -718,8 +718,11 @@ std::vector<uint8_t> assemble(const Program &P, const Nft &g) {
     h.off_nft = (uint32_t)off; off += g.st.size() * sizeof(NftFlat); off = (off + 127) & ~(size_t)127;
     if (P.exec_kind == TRRE_EXEC_BYTEMAP) { h.off_pairlut = (uint32_t)off; off += 65536 * 2; }
     // compact tables of the position-parallel kernel (k_match): length-preserving, acyclic, short attempts
-    const bool matchable = P.exec_kind == TRRE_EXEC_TABLE && (P.flags & PF_LENGTH_PRESERVING) && (P.flags & PF_ACYCLIC) &&
-                           !(P.flags & (PF_CAN_MATCH_EMPTY | PF_HAS_DIVERGE)) && P.max_depth >= 1 && P.max_depth <= 16;
+    // attempts of at most 16 bytes; an automaton with a cycle qualifies as well ([0-9]+:#, (a:b)+): its attempts are short
+    // on ordinary text, and the kernel hands the buffer to the per-line path when one is still alive after 16 bytes
+    const bool short_attempts = (P.flags & PF_ACYCLIC) ? (P.max_depth >= 1 && P.max_depth <= 16) : true;
+    const bool matchable = P.exec_kind == TRRE_EXEC_TABLE && (P.flags & PF_LENGTH_PRESERVING) && short_attempts &&
+                           !(P.flags & (PF_CAN_MATCH_EMPTY | PF_HAS_DIVERGE)) && !P.trans.empty();
     std::vector<uint8_t> vpool;
     std::vector<uint32_t> vent(256, 0);
     if (P.vmap) {
@@ -737,9 +740,8 @@ std::vector<uint8_t> assemble(const Program &P, const Nft &g) {
     }
     // the same, but a match may print more or fewer bytes than it consumes (s/cat/mouse/): needs the single
     // output string per match (PF_OUT_LATE tables); byte maps have their own kernels
-    const bool matchable_var = P.exec_kind == TRRE_EXEC_TABLE && !(P.flags & PF_LENGTH_PRESERVING) && (P.flags & PF_ACYCLIC) &&
-                               !(P.flags & (PF_CAN_MATCH_EMPTY | PF_HAS_DIVERGE)) && P.max_depth >= 1 && P.max_depth <= 16 &&
-                               !P.eout.empty() && !P.vmap;
+    const bool matchable_var = P.exec_kind == TRRE_EXEC_TABLE && !(P.flags & PF_LENGTH_PRESERVING) && short_attempts &&
+                               !(P.flags & (PF_CAN_MATCH_EMPTY | PF_HAS_DIVERGE)) && !P.eout.empty() && !P.vmap;
     if (!P.trans.empty()) {                                   // compact tables: every table program
         h.off_row0 = (uint32_t)off; off += 256 * 4;
         h.off_ctrans = (uint32_t)off; off += P.trans.size() * 4; off = align16(off);

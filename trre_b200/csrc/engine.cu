@@ -92,7 +92,6 @@ struct DeviceState {
     bool gram_small = false;
     const void *gram_fn = nullptr;
     SwarMap swar{};                // table-free byte map (n == 0: not of that form)
-    int swar_ctas = 2, swar_variant = 0;
     // TRRE_EXEC_LAZY: device copies of the rows built so far (automaton.hpp, LazyDsa)
     uint64_t *lz_rows = nullptr, *lz_sinfo = nullptr;
     uint8_t *lz_pool = nullptr;
@@ -186,16 +185,19 @@ int plan_match(const BlobHeader &h, size_t warp_bytes, size_t budget, int sm_cou
     return TRRE_OK;
 }
 
-const void *gram_kernel(uint32_t depth, bool small) {
+const void *gram_kernel(uint32_t depth, bool small, bool reg) {
+#define GK(D) (small ? (reg ? (const void *)k_gram<D, true, true> : (const void *)k_gram<D, true, false>) \
+                     : (reg ? (const void *)k_gram<D, false, true> : (const void *)k_gram<D, false, false>))
     switch (depth) {
-        case 1: return small ? (const void *)k_gram<1, true> : (const void *)k_gram<1, false>;
-        case 2: return small ? (const void *)k_gram<2, true> : (const void *)k_gram<2, false>;
-        case 3: return small ? (const void *)k_gram<3, true> : (const void *)k_gram<3, false>;
-        case 4: return small ? (const void *)k_gram<4, true> : (const void *)k_gram<4, false>;
-        case 5: return small ? (const void *)k_gram<5, true> : (const void *)k_gram<5, false>;
-        case 6: return small ? (const void *)k_gram<6, true> : (const void *)k_gram<6, false>;
+        case 1: return GK(1);
+        case 2: return GK(2);
+        case 3: return GK(3);
+        case 4: return GK(4);
+        case 5: return GK(5);
+        case 6: return GK(6);
         default: return nullptr;
     }
+#undef GK
 }
 
 int get_state(const trre_prog *cp, int device, DeviceState **out) {
@@ -261,8 +263,6 @@ int get_state(const trre_prog *cp, int device, DeviceState **out) {
             d->swar.half[k] = lo < 0x80u ? 0x80808080u : 0u;
             d->swar.delta[k] = delta;
         }
-        if (const char *e = std::getenv("TRRE_SWAR_CTAS")) { int v = std::atoi(e); if (v >= 1 && v <= 16) d->swar_ctas = v; }
-        if (const char *e = std::getenv("TRRE_SWAR_VARIANT")) { int v = std::atoi(e); if (v >= 0 && v <= 2) d->swar_variant = v; }
     }
     if (h.flags & PF_MATCHABLE) {
         int rc2 = plan_match(h, (size_t)kMatchWarps * kWarpSmem, 108 * 1024, d->sm_count, OP_INPLACE, &d->mp);
@@ -287,10 +287,14 @@ int get_state(const trre_prog *cp, int device, DeviceState **out) {
         d->gram_small = h.gram_entries <= kGramSmallEntries;
         g.gout_in_smem = h.gram_entries <= 4096 ? 1u : 0u;
         g.pool_in_smem = (h.gpool_bytes && h.gpool_bytes <= 4096) ? 1u : 0u;
+        // the register form: one common match length, printed bytes in a word (with small tables: in the hit word, <= 3)
+        const bool reg = (h.gram_flags & GRAM_DIRECT) && h.gram_len >= 1 && h.gram_len <= (d->gram_small ? 3u : 4u) &&
+                         !std::getenv("TRRE_GRAM_NO_REG");
+        g.len_mask = h.gram_len >= 4 ? 0xFFFFFFFFu : ((1u << (8 * h.gram_len)) - 1u);
         d->gram_smem = 256 * 32 * 4 + (d->gram_small ? (size_t)h.gram_entries * 128 : (size_t)((words + 3) & ~3u) * 4) +
                        (g.gout_in_smem ? (size_t)((h.gram_entries + 3) & ~3u) * 4 : 0) +
-                       (g.pool_in_smem ? ((h.gpool_bytes + 15) & ~15u) : 0) + (size_t)kGramWarps * kGramWarpSmem;
-        d->gram_fn = gram_kernel(h.gram_depth, d->gram_small);
+                       (g.pool_in_smem ? ((h.gpool_bytes + 15) & ~15u) : 0) + (reg ? 0 : (size_t)kGramWarps * kGramWarpSmem);
+        d->gram_fn = gram_kernel(h.gram_depth, d->gram_small, reg);
         if (d->gram_fn && d->gram_smem <= 220 * 1024) {
             CUDA_TRY(cudaFuncSetAttribute(d->gram_fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)d->gram_smem));
         } else {
@@ -415,20 +419,9 @@ int launch_fast(const trre_prog *p, DeviceState *d, const uint8_t *d_in, size_t 
                 uint32_t *status, cudaStream_t st) {
     const BlobHeader &h = p->hdr;
     const bool aligned = ((reinterpret_cast<uintptr_t>(d_in) ^ reinterpret_cast<uintptr_t>(d_out)) & 15) == 0;
-    if (h.exec_kind == TRRE_EXEC_BYTEMAP && aligned && d->swar.n && d->swar_variant) {
+    if (h.exec_kind == TRRE_EXEC_BYTEMAP && aligned && d->swar.n) {
         const size_t nvec = n / 16 + 1;
-        const int grid = d->swar_variant == 1 ? d->sm_count * d->swar_ctas : (int)((nvec + 1023) / 1024);
-#define SWAR_LAUNCH(K, NR) K<NR><<<grid, 256, 0, st>>>(d_in, d_out, n, d->swar, d->P.lut, status)
-        if (d->swar_variant == 1) {
-            switch (d->swar.n) { case 1: SWAR_LAUNCH(k_bytemap_swar_v1, 1); break; case 2: SWAR_LAUNCH(k_bytemap_swar_v1, 2); break;
-                                 case 3: SWAR_LAUNCH(k_bytemap_swar_v1, 3); break; default: SWAR_LAUNCH(k_bytemap_swar_v1, 4); break; }
-        } else {
-            switch (d->swar.n) { case 1: SWAR_LAUNCH(k_bytemap_swar_v2, 1); break; case 2: SWAR_LAUNCH(k_bytemap_swar_v2, 2); break;
-                                 case 3: SWAR_LAUNCH(k_bytemap_swar_v2, 3); break; default: SWAR_LAUNCH(k_bytemap_swar_v2, 4); break; }
-        }
-#undef SWAR_LAUNCH
-    } else if (h.exec_kind == TRRE_EXEC_BYTEMAP && aligned && d->swar.n) {
-        const int grid = d->sm_count * d->swar_ctas;
+        const int grid = (int)((nvec + kSwarVecPerCta - 1) / kSwarVecPerCta);
         switch (d->swar.n) {
             case 1: k_bytemap_swar<1><<<grid, kSwarThreads, 0, st>>>(d_in, d_out, n, d->swar, d->P.lut, status); break;
             case 2: k_bytemap_swar<2><<<grid, kSwarThreads, 0, st>>>(d_in, d_out, n, d->swar, d->P.lut, status); break;

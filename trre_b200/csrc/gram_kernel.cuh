@@ -16,8 +16,10 @@
 //   C  index of the D-gram at each position by Horner steps over the classes (IMAD), one bitmap lookup -> candidate
 //      mask.  With matches of one common length (every BASELINE config) their lengths need no lookup at all.
 //   D  chain resolution (resolve_chain, shared with k_match): which candidates start outside an earlier match
-//   E  the real matches - a few per cent of the positions - fetch their output from gout (the bytes themselves when
-//      they fit a word) and overwrite their span of the staged output tile
+//   E  the real matches - a few per cent of the positions - fetch their output from gout and overwrite their span of the
+//      tile.  When every match prints the same number (<= 4) of bytes the whole tile stays in REGISTERS: the bytes come
+//      with the hit word (small tables) or one predicated gout load per position, and are merged into the lane's four
+//      output words at compile-time byte offsets; otherwise the tile is staged in shared memory
 //   F  16-byte vector store per lane
 // Scan-driver semantics, warm-up from the last '\n' before a warp's span and ST_IRREGULAR handling are k_match's
 // (trre_nft.c:778-789 on a regular buffer: an attempt at every position not covered by an earlier match).
@@ -55,6 +57,7 @@ struct GramArgs {
     uint32_t gflags;
     uint32_t gout_in_smem;
     uint32_t pool_in_smem;
+    uint32_t len_mask;           // REG form: 0xFF in the low uniform_len bytes
 };
 
 struct GramTables {
@@ -85,19 +88,12 @@ __device__ __forceinline__ uint32_t class_of(const GramTables &T, uint32_t w) {
     return *reinterpret_cast<const uint32_t *>(T.cls_b + ((sh & 0x7F80u) | T.lane4));
 }
 
-template <int D, bool SMALL, bool STORE>
-__device__ __forceinline__ void gram_tile(const GramArgs &a, const GramTables &T, uint8_t *s_in, uint8_t *s_out,
-                                          size_t base, bool full, uint4 x, uint4 x_next,
-                                          uint32_t lane, uint32_t first_valid, uint32_t &carry_e, uint4 &carry_halo,
-                                          uint32_t &nul_acc) {
-    // ---- A: stage the tile (input and default output = raw copy); lane 0 of the next tile is the halo ---------------
-    *reinterpret_cast<uint4 *>(s_in + lane * 16) = x;
-    *reinterpret_cast<uint4 *>(s_out + lane * 16) = x;
-    if (lane == 0) {
-        *reinterpret_cast<uint4 *>(s_in + kTile) = x_next;
-        *reinterpret_cast<uint4 *>(s_out + kTile) = x_next;
-    }
-    nul_acc |= ((x.x - 0x01010101u) & ~x.x) | ((x.y - 0x01010101u) & ~x.y) | ((x.z - 0x01010101u) & ~x.z) | ((x.w - 0x01010101u) & ~x.w);
+// Steps A-C shared by both tile forms: classes of the lane's 16 (+ D-1) bytes, gram index per position, candidate mask.
+// pay[j] = what step E needs for position j: SMALL: the hit word itself (bit 31 = match, REG: low 24 bits = the printed
+// bytes); otherwise the gram index.
+template <int D, bool SMALL>
+__device__ __forceinline__ uint32_t gram_candidates(const GramArgs &a, const GramTables &T, uint4 x, uint4 x_next,
+                                                    uint32_t lane, uint32_t first_valid, uint32_t (&pay)[16]) {
     // the D-1 bytes after this lane's 16: the neighbour's first words (lane 31: the next tile's)
     uint32_t h0 = __shfl_down_sync(0xFFFFFFFFu, x.x, 1), h1 = 0;
     const uint32_t n0 = __shfl_sync(0xFFFFFFFFu, x_next.x, 0);
@@ -107,7 +103,6 @@ __device__ __forceinline__ void gram_tile(const GramArgs &a, const GramTables &T
         const uint32_t n1 = __shfl_sync(0xFFFFFFFFu, x_next.y, 0);
         if (lane == 31) h1 = n1;
     }
-
     // ---- B: byte classes, conflict free (bank = lane) ------------------------------------------------------------------
     const uint32_t ncls = a.n_classes;
     uint32_t cls[16 + kGramMaxDepth - 1];
@@ -123,32 +118,95 @@ __device__ __forceinline__ void gram_tile(const GramArgs &a, const GramTables &T
     // ---- C: D-gram index per position (Horner over the classes), one lookup each -> candidate mask --------------------
     // positions are taken from 15 down to 0 and the hit bit enters the mask through a funnel shift: 1 instruction
     uint32_t cand = 0;
-    {
-        const uint32_t n2 = ncls * ncls, n4 = n2 * n2;
-        uint32_t q[16 + kGramMaxDepth - 1];                       // pair codes cls[t] + ncls * cls[t+1]
-        if (D >= 3) {
+    const uint32_t n2 = ncls * ncls, n4 = n2 * n2;
+    uint32_t q[16 + kGramMaxDepth - 1];                           // pair codes cls[t] + ncls * cls[t+1]
+    if (D >= 3) {
 #pragma unroll
-            for (int t = 0; t < 16 + D - 2; ++t) q[t] = cls[t] + ncls * cls[t + 1];
-        }
+        for (int t = 0; t < 16 + D - 2; ++t) q[t] = cls[t] + ncls * cls[t + 1];
+    }
 #pragma unroll
-        for (int j = 15; j >= 0; --j) {
-            uint32_t idx;
-            if (D == 1) idx = cls[j];
-            else if (D == 2) idx = cls[j] + ncls * cls[j + 1];
-            else if (D == 3) idx = q[j] + n2 * cls[j + 2];
-            else if (D == 4) idx = q[j] + n2 * q[j + 2];
-            else if (D == 5) idx = q[j] + n2 * q[j + 2] + n4 * cls[j + 4];
-            else idx = q[j] + n2 * q[j + 2] + n4 * q[j + 4];
-            uint32_t hit;                                           // bit 31 = the attempt at position j matches
-            if (SMALL) hit = *reinterpret_cast<const uint32_t *>(T.hit_b + ((idx << 7) | T.lane4));
-            else hit = T.bits[idx >> 5] << (idx & 31u);
-            cand = __funnelshift_l(hit, cand, 1);
+    for (int j = 15; j >= 0; --j) {
+        uint32_t idx;
+        if (D == 1) idx = cls[j];
+        else if (D == 2) idx = cls[j] + ncls * cls[j + 1];
+        else if (D == 3) idx = q[j] + n2 * cls[j + 2];
+        else if (D == 4) idx = q[j] + n2 * q[j + 2];
+        else if (D == 5) idx = q[j] + n2 * q[j + 2] + n4 * cls[j + 4];
+        else idx = q[j] + n2 * q[j + 2] + n4 * q[j + 4];
+        uint32_t hit;                                               // bit 31 = the attempt at position j matches
+        if (SMALL) { hit = *reinterpret_cast<const uint32_t *>(T.hit_b + ((idx << 7) | T.lane4)); pay[j] = hit; }
+        else { hit = T.bits[idx >> 5] << (idx & 31u); pay[j] = idx; }
+        cand = __funnelshift_l(hit, cand, 1);
+    }
+    const uint32_t my0 = lane * 16;
+    if (first_valid > my0) cand &= (first_valid - my0 >= 16) ? 0u : (0xFFFFu << (first_valid - my0));
+    return cand;
+}
+
+// The tile in registers (GRAM_DIRECT programs: one common match length L <= 4, the printed bytes fit a word): no
+// shared-memory staging at all.  After the chain is resolved the real matches are merged into the lane's four output
+// words position by position (compile-time byte offsets, predicated on the `real` bit); the up to three bytes a match
+// at positions 13..15 prints past the lane's end travel to the next lane (next tile: carry_sp / carry_sm) by shuffle.
+template <int D, bool SMALL, bool STORE>
+__device__ __forceinline__ void gram_tile_reg(const GramArgs &a, const GramTables &T, size_t base, bool full, uint4 x, uint4 x_next,
+                                              uint32_t lane, uint32_t first_valid, uint32_t &carry_e, uint32_t &carry_sp,
+                                              uint32_t &carry_sm, uint32_t &nul_acc) {
+    nul_acc |= ((x.x - 0x01010101u) & ~x.x) | ((x.y - 0x01010101u) & ~x.y) | ((x.z - 0x01010101u) & ~x.z) | ((x.w - 0x01010101u) & ~x.w);
+    uint32_t pay[16];
+    const uint32_t cand = gram_candidates<D, SMALL>(a, T, x, x_next, lane, first_valid, pay);
+    Front f;
+    f.lens = 0x1111111111111111ull * (unsigned long long)(a.uniform_len - 1);
+    resolve_chain(f, cand, lane, carry_e);
+    // ---- E in registers --------------------------------------------------------------------------------------------------
+    const uint32_t M = a.len_mask;                                  // 0xFF in the low L bytes
+    uint32_t o[5] = {x.x, x.y, x.z, x.w, 0u};
+    uint32_t sm = 0;                                                // which bytes of o[4] (positions 16..19) are written
+#pragma unroll
+    for (int j = 0; j < 16; ++j) {
+        if (f.real & (1u << j)) {
+            const uint32_t g = SMALL ? pay[j] : T.gout[pay[j]];     // SMALL: the bytes came with the hit word
+            const int r = 8 * (j & 3), w = j >> 2;                  // compile-time after unrolling
+            o[w] = (o[w] & ~(M << r)) | ((g << r) & (M << r));
+            if (r) {
+                const uint32_t m2 = M >> (32 - r);
+                o[w + 1] = (o[w + 1] & ~m2) | ((g >> (32 - r)) & m2);
+                if (w == 3) sm |= m2;
+            }
         }
     }
-    {
-        const uint32_t my0 = lane * 16;
-        if (first_valid > my0) cand &= (first_valid - my0 >= 16) ? 0u : (0xFFFFu << (first_valid - my0));
+    uint32_t sp_in = __shfl_up_sync(0xFFFFFFFFu, o[4], 1), sm_in = __shfl_up_sync(0xFFFFFFFFu, sm, 1);
+    if (lane == 0) { sp_in = carry_sp; sm_in = carry_sm; }
+    o[0] = (o[0] & ~sm_in) | (sp_in & sm_in);
+    if (STORE) {
+        const size_t my = base + (size_t)lane * 16;
+        if (full || my + 16 <= a.n) {
+            *reinterpret_cast<uint4 *>(a.out + my) = make_uint4(o[0], o[1], o[2], o[3]);
+        } else if (my < a.n) {
+            for (int k = 0; k < 16 && my + k < a.n; ++k) a.out[my + k] = (uint8_t)(o[k >> 2] >> ((k & 3) * 8));
+        }
     }
+    carry_e = __shfl_sync(0xFFFFFFFFu, f.e_out, 31);
+    carry_sp = __shfl_sync(0xFFFFFFFFu, o[4], 31);
+    carry_sm = __shfl_sync(0xFFFFFFFFu, sm, 31);
+}
+
+// The general form: tile staged in shared memory, real matches write their span there (any length, pool strings).
+template <int D, bool SMALL, bool STORE>
+__device__ __forceinline__ void gram_tile(const GramArgs &a, const GramTables &T, uint8_t *s_in, uint8_t *s_out,
+                                          size_t base, bool full, uint4 x, uint4 x_next,
+                                          uint32_t lane, uint32_t first_valid, uint32_t &carry_e, uint4 &carry_halo,
+                                          uint32_t &nul_acc) {
+    // ---- A: stage the tile (input and default output = raw copy); lane 0 of the next tile is the halo ---------------
+    *reinterpret_cast<uint4 *>(s_in + lane * 16) = x;
+    *reinterpret_cast<uint4 *>(s_out + lane * 16) = x;
+    if (lane == 0) {
+        *reinterpret_cast<uint4 *>(s_in + kTile) = x_next;
+        *reinterpret_cast<uint4 *>(s_out + kTile) = x_next;
+    }
+    nul_acc |= ((x.x - 0x01010101u) & ~x.x) | ((x.y - 0x01010101u) & ~x.y) | ((x.z - 0x01010101u) & ~x.z) | ((x.w - 0x01010101u) & ~x.w);
+    uint32_t pay[16];
+    const uint32_t cand = gram_candidates<D, SMALL>(a, T, x, x_next, lane, first_valid, pay);
+    const uint32_t ncls = a.n_classes;
     __syncwarp();                                                     // the staged tile is visible
 
     // ---- lengths: one common length needs no lookup; otherwise one gout lookup per candidate ----------------------------
@@ -168,8 +226,7 @@ __device__ __forceinline__ void gram_tile(const GramArgs &a, const GramTables &T
     // ---- D ---------------------------------------------------------------------------------------------------------------
     resolve_chain(f, cand, lane, carry_e);
 
-    // ---- E: every real match overwrites its span of the output tile, written by the lane it starts in (matches are a few
-    // per cent of the positions: compacting them across the warp costs more than the divergence it removes) ----------
+    // ---- E: every real match overwrites its span of the output tile ----------------------------------------------------
     if (lane == 0 && carry_e) {
         const uint32_t h[4] = {carry_halo.x, carry_halo.y, carry_halo.z, carry_halo.w};
         for (uint32_t k = 0; k < carry_e; ++k) s_out[k] = (uint8_t)(h[k >> 2] >> ((k & 3) * 8));
@@ -207,7 +264,7 @@ __device__ __forceinline__ void gram_tile(const GramArgs &a, const GramTables &T
     __syncwarp();
 }
 
-template <int D, bool SMALL>
+template <int D, bool SMALL, bool REG>
 __global__ void __launch_bounds__(kGramThreads, 1)
 k_gram(GramArgs a) {
     extern __shared__ __align__(16) uint8_t smem[];
@@ -222,13 +279,14 @@ k_gram(GramArgs a) {
     if (a.gout_in_smem) { gout_s = reinterpret_cast<uint32_t *>(cur); cur += (size_t)((a.entries + 3) & ~3u) * 4; }
     uint8_t *pool_s = nullptr;
     if (a.pool_in_smem) { pool_s = cur; cur += (a.gpool_bytes + 15) & ~15u; }
-    uint8_t *warp_base = cur + warp * kGramWarpSmem;
+    uint8_t *warp_base = cur + (REG ? 0 : warp * kGramWarpSmem);     // REG: no staging area at all
 
     for (uint32_t k = threadIdx.x; k < 256u * 32u; k += blockDim.x) cls_s[k] = __ldg(a.classmap + (k >> 5));
     if (SMALL) {
         for (uint32_t k = threadIdx.x; k < a.entries * 32u; k += blockDim.x) {
             const uint32_t e = k >> 5;
-            bits_s[k] = ((__ldg(a.gbits + (e >> 5)) >> (e & 31u)) & 1u) << 31;
+            // REG: the (<= 3) printed bytes ride in the hit word
+            bits_s[k] = (((__ldg(a.gbits + (e >> 5)) >> (e & 31u)) & 1u) << 31) | (REG ? (__ldg(a.gout + e) & 0x00FFFFFFu) : 0u);
         }
     } else {
         for (uint32_t k = threadIdx.x; k < words; k += blockDim.x) bits_s[k] = __brev(__ldg(a.gbits + k));
@@ -257,7 +315,7 @@ k_gram(GramArgs a) {
     if (t1 > n_tiles) t1 = n_tiles;
     uint32_t status = 0, nul_acc = 0;
     if (t0 < t1) {
-        uint32_t carry_e = 0;
+        uint32_t carry_e = 0, carry_sp = 0, carry_sm = 0;
         uint4 carry_halo = make_uint4(0, 0, 0, 0);
         // ---- warm-up: the chain state at t0 is only known from the last '\n' before it (as k_match) ------------------
         size_t tw = t0;
@@ -292,8 +350,13 @@ k_gram(GramArgs a) {
             // prefetch; its lane 0 is this tile's halo.  Tiles whose successor lies inside the buffer skip every bounds check
             const bool full = base + 2 * (size_t)kTile <= n;
             const uint4 x_next = full ? ldg_vec(a.in + base + kTile + lane * 16) : load_padded(a.in, base + kTile + lane * 16, n);
-            if (t < t0) gram_tile<D, SMALL, false>(a, T, s_in, s_out, base, full, x, x_next, lane, first_valid, carry_e, carry_halo, nul_acc);
-            else        gram_tile<D, SMALL, true>(a, T, s_in, s_out, base, full, x, x_next, lane, first_valid, carry_e, carry_halo, nul_acc);
+            if (REG) {
+                if (t < t0) gram_tile_reg<D, SMALL, false>(a, T, base, full, x, x_next, lane, first_valid, carry_e, carry_sp, carry_sm, nul_acc);
+                else        gram_tile_reg<D, SMALL, true>(a, T, base, full, x, x_next, lane, first_valid, carry_e, carry_sp, carry_sm, nul_acc);
+            } else {
+                if (t < t0) gram_tile<D, SMALL, false>(a, T, s_in, s_out, base, full, x, x_next, lane, first_valid, carry_e, carry_halo, nul_acc);
+                else        gram_tile<D, SMALL, true>(a, T, s_in, s_out, base, full, x, x_next, lane, first_valid, carry_e, carry_halo, nul_acc);
+            }
             first_valid = 0;
             x = x_next;
         }

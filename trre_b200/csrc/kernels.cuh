@@ -92,9 +92,9 @@ __device__ __forceinline__ uint4 map_vec(const uint4 &x, uint32_t tab, uint32_t 
     return y;
 }
 
-// Static grid-stride sweep: at any moment the 148 CTAs work on one contiguous ~10 MB window of the
-// buffer (DRAM page locality).  A dynamic 8 KB-per-warp ticket scheme was measured and rejected
-// (0.458 ms vs 0.373 ms per GiB): it widens the window to ~40 MB and serialises on one atomic.
+// Static schedule: chunk k belongs to CTA k mod grid, so at any moment the 148 CTAs work on one contiguous ~10 MB
+// window of the buffer.  A dynamic 8 KB-per-warp ticket scheme was measured and rejected (0.458 ms vs 0.373 ms per
+// GiB): it widens the window to ~40 MB and serialises on one atomic.
 __global__ void __launch_bounds__(kBmThreads, 1)
 k_bytemap(const uint8_t *__restrict__ in, uint8_t *__restrict__ out, size_t n,
           const uint16_t *__restrict__ pairlut, const uint8_t *__restrict__ lut, uint32_t *__restrict__ status) {
@@ -122,37 +122,42 @@ k_bytemap(const uint8_t *__restrict__ in, uint8_t *__restrict__ out, size_t n,
     const uint4 *vin = reinterpret_cast<const uint4 *>(in + head);
     uint4 *vout = reinterpret_cast<uint4 *>(out + head);
 
-    const size_t stride = (size_t)gridDim.x * blockDim.x;
-    size_t v = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    // every CTA iteration maps one CONTIGUOUS chunk of kBmUnroll x 1024 vectors (64 KB); chunks are dealt round the grid.
+    // (The first version strode each thread's vectors a whole grid apart - 2.4 MB: scattered 512-byte accesses that cost
+    // 15 % of the DRAM bandwidth, see k_bytemap_swar.)  Software pipelined: while one chunk is mapped and stored, the
+    // next chunk's loads are already in flight.
+    const size_t per_cta = (size_t)kBmUnroll * blockDim.x;
+    const size_t full_chunks = nvec / per_cta;
+    size_t c = blockIdx.x;
     bool table_ready = false;
-    // main loop, software pipelined: while one batch of kBmUnroll vectors is mapped and stored, the next
-    // batch's loads are already in flight
-    if (v + (kBmUnroll - 1) * stride < nvec) {
+    if (c < full_chunks) {
         uint4 x[kBmUnroll];
 #pragma unroll
-        for (int u = 0; u < kBmUnroll; ++u) x[u] = ld_stream(vin + v + u * stride);
+        for (int u = 0; u < kBmUnroll; ++u) x[u] = ld_stream(vin + c * per_cta + u * blockDim.x + threadIdx.x);
         mbar_wait(&bar, 0);                                   // the first loads overlapped the table copy
         table_ready = true;
         for (;;) {
-            const size_t vn = v + kBmUnroll * stride;
-            const bool more = vn + (kBmUnroll - 1) * stride < nvec;
+            const size_t cn = c + gridDim.x;
+            const bool more = cn < full_chunks;
             uint4 xn[kBmUnroll];
             if (more) {
 #pragma unroll
-                for (int u = 0; u < kBmUnroll; ++u) xn[u] = ld_stream(vin + vn + u * stride);
+                for (int u = 0; u < kBmUnroll; ++u) xn[u] = ld_stream(vin + cn * per_cta + u * blockDim.x + threadIdx.x);
             }
 #pragma unroll
-            for (int u = 0; u < kBmUnroll; ++u) st_stream(vout + v + u * stride, map_vec(x[u], tab, nul));
-            v = vn;
+            for (int u = 0; u < kBmUnroll; ++u) st_stream(vout + c * per_cta + u * blockDim.x + threadIdx.x, map_vec(x[u], tab, nul));
+            c = cn;
             if (!more) break;
 #pragma unroll
             for (int u = 0; u < kBmUnroll; ++u) x[u] = xn[u];
         }
     }
     if (!table_ready) mbar_wait(&bar, 0);
-    for (; v < nvec; v += stride) {
-        uint4 x = ld_stream(vin + v);
-        st_stream(vout + v, map_vec(x, tab, nul));
+    if (blockIdx.x == full_chunks % gridDim.x) {               // the last, partial chunk
+        for (size_t v = full_chunks * per_cta + threadIdx.x; v < nvec; v += blockDim.x) {
+            uint4 x = ld_stream(vin + v);
+            st_stream(vout + v, map_vec(x, tab, nul));
+        }
     }
     nul &= 0x80808080u;
     // ragged head and tail: one thread, byte by byte
@@ -172,7 +177,7 @@ k_bytemap(const uint8_t *__restrict__ in, uint8_t *__restrict__ out, size_t n,
 // Most byte maps people write are "add a constant on a few byte ranges" ([a:A-z:Z]: a-z -32; Caesar: a-y +1,
 // z -25).  Those need no table: per 32-bit word, a 7-bit SWAR range test per range (two adds whose carries stay
 // inside their byte), the selected bytes' deltas accumulated with one IMAD per range, and a carry-isolated
-// byte-wise add.  No shared memory, no LSU traffic besides the stream itself, 2 x 1024 threads per SM.
+// byte-wise add.  No shared memory, no LSU traffic besides the stream itself, 8 x 256 threads per SM.
 // The host emits the ranges (BlobHeader::swar); maps that are not of this form keep k_bytemap's pair table.
 struct SwarMap {
     uint32_t n;
@@ -206,98 +211,16 @@ __device__ __forceinline__ uint4 swar_vec(const uint4 &x, const SwarMap &M, uint
     return y;
 }
 
-constexpr int kSwarThreads = 512;
-constexpr int kSwarUnroll = 4;
+// One CTA per 16 KB block of the buffer (256 threads x 4 vectors, the block contiguous), no persistence: the hardware
+// block scheduler walks the buffer front to back.  Measured against the persistent grid-stride sweep this kernel
+// started as (each thread's 4 vectors 2.4 MB apart): 0.318 vs 0.374 ms per GiB - 1.03 vs 0.87 of the measured copy peak
+// (gpurun_out/bench_cfg2_{default,v2}_r2b.json) - the sweep's scattered 512-byte accesses cost DRAM efficiency.
+constexpr int kSwarThreads = 256;
+constexpr int kSwarVecPerCta = 1024;
 
 template <int NR>
-__global__ void __launch_bounds__(kSwarThreads, 2)
+__global__ void __launch_bounds__(kSwarThreads, 8)
 k_bytemap_swar(const uint8_t *__restrict__ in, uint8_t *__restrict__ out, size_t n, const SwarMap M,
-               const uint8_t *__restrict__ lut, uint32_t *__restrict__ status) {
-    uint32_t nul = 0;
-    size_t head = ((16 - (reinterpret_cast<uintptr_t>(in) & 15)) & 15);
-    if (head > n) head = n;
-    const size_t nvec = (n - head) / 16;
-    const uint4 *vin = reinterpret_cast<const uint4 *>(in + head);
-    uint4 *vout = reinterpret_cast<uint4 *>(out + head);
-    // same sweep as k_bytemap: the whole grid inside one contiguous window, kSwarUnroll strided vectors per thread,
-    // the next batch's loads in flight while this one is mapped and stored
-    const size_t stride = (size_t)gridDim.x * blockDim.x;
-    size_t v = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (v + (kSwarUnroll - 1) * stride < nvec) {
-        uint4 x[kSwarUnroll];
-#pragma unroll
-        for (int u = 0; u < kSwarUnroll; ++u) x[u] = ld_stream(vin + v + u * stride);
-        for (;;) {
-            const size_t vn = v + kSwarUnroll * stride;
-            const bool more = vn + (kSwarUnroll - 1) * stride < nvec;
-            uint4 xn[kSwarUnroll];
-            if (more) {
-#pragma unroll
-                for (int u = 0; u < kSwarUnroll; ++u) xn[u] = ld_stream(vin + vn + u * stride);
-            }
-#pragma unroll
-            for (int u = 0; u < kSwarUnroll; ++u) st_stream(vout + v + u * stride, swar_vec<NR>(x[u], M, nul));
-            v = vn;
-            if (!more) break;
-#pragma unroll
-            for (int u = 0; u < kSwarUnroll; ++u) x[u] = xn[u];
-        }
-    }
-    for (; v < nvec; v += stride) {
-        uint4 x = ld_stream(vin + v);
-        st_stream(vout + v, swar_vec<NR>(x, M, nul));
-    }
-    nul &= 0x80808080u;
-    if (blockIdx.x == 0 && threadIdx.x == 0) {
-        for (size_t k = 0; k < head; ++k) { uint8_t c = in[k]; if (!c) nul = 1; out[k] = lut[c]; }
-        for (size_t k = head + nvec * 16; k < n; ++k) { uint8_t c = in[k]; if (!c) nul = 1; out[k] = lut[c]; }
-        if (n && in[n - 1] != '\n') nul = 1;
-    }
-    if (__any_sync(0xFFFFFFFFu, nul != 0)) {
-        if ((threadIdx.x & 31) == 0) atomicOr(status, ST_IRREGULAR);
-    }
-}
-
-// Experimental launch shapes of the same map (TRRE_SWAR_VARIANT=1/2), kept selectable until one wins on hardware:
-//  1: no register double buffering, 32 registers, up to 8 x 256 threads per SM (more loads in flight through warps)
-//  2: one CTA per 16 KB block of the buffer, 4 vectors per thread, hardware block scheduling instead of a sweep
-template <int NR>
-__global__ void __launch_bounds__(256, 8)
-k_bytemap_swar_v1(const uint8_t *__restrict__ in, uint8_t *__restrict__ out, size_t n, const SwarMap M,
-                  const uint8_t *__restrict__ lut, uint32_t *__restrict__ status) {
-    uint32_t nul = 0;
-    size_t head = ((16 - (reinterpret_cast<uintptr_t>(in) & 15)) & 15);
-    if (head > n) head = n;
-    const size_t nvec = (n - head) / 16;
-    const uint4 *vin = reinterpret_cast<const uint4 *>(in + head);
-    uint4 *vout = reinterpret_cast<uint4 *>(out + head);
-    const size_t stride = (size_t)gridDim.x * blockDim.x;
-    size_t v = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-    for (; v + 3 * stride < nvec; v += 4 * stride) {
-        uint4 x[4];
-#pragma unroll
-        for (int u = 0; u < 4; ++u) x[u] = ld_stream(vin + v + u * stride);
-#pragma unroll
-        for (int u = 0; u < 4; ++u) st_stream(vout + v + u * stride, swar_vec<NR>(x[u], M, nul));
-    }
-    for (; v < nvec; v += stride) {
-        uint4 x = ld_stream(vin + v);
-        st_stream(vout + v, swar_vec<NR>(x, M, nul));
-    }
-    nul &= 0x80808080u;
-    if (blockIdx.x == 0 && threadIdx.x == 0) {
-        for (size_t k = 0; k < head; ++k) { uint8_t c = in[k]; if (!c) nul = 1; out[k] = lut[c]; }
-        for (size_t k = head + nvec * 16; k < n; ++k) { uint8_t c = in[k]; if (!c) nul = 1; out[k] = lut[c]; }
-        if (n && in[n - 1] != '\n') nul = 1;
-    }
-    if (__any_sync(0xFFFFFFFFu, nul != 0)) {
-        if ((threadIdx.x & 31) == 0) atomicOr(status, ST_IRREGULAR);
-    }
-}
-
-template <int NR>
-__global__ void __launch_bounds__(256, 8)
-k_bytemap_swar_v2(const uint8_t *__restrict__ in, uint8_t *__restrict__ out, size_t n, const SwarMap M,
                   const uint8_t *__restrict__ lut, uint32_t *__restrict__ status) {
     uint32_t nul = 0;
     size_t head = ((16 - (reinterpret_cast<uintptr_t>(in) & 15)) & 15);
@@ -369,6 +292,8 @@ __device__ __forceinline__ size_t run_record(const DevProg &P, const BtScratch &
                  : EXEC == EXEC_LAZY ? attempt_lazy(L, in, p, lim, o, status)
                                      : attempt_table(P, in, p, lim, o, status);
         if (EXEC == EXEC_LAZY && k == -2) break;          // a row is missing: this pass is void, leave the record
+        if (status & (ST_STACK | ST_OBUF | ST_DIVERGE | ST_RUNAWAY)) break;   // the scan has failed (the reference exits here):
+                                                          // do not grind through the rest of the record
         if (at_end) break;                                // that was the attempt on the empty tail
         if (k > 0) p += (size_t)k;
         else { o.put(c); ++p; }                           // no match or empty match: copy one raw byte

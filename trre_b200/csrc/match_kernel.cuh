@@ -75,6 +75,7 @@ struct MatchTables {
     const uint32_t *ctrans_g;    // global, all rows
     const uint8_t *pool;         // shared copy when small, else global
     uint32_t n_classes, smem_states, lane;
+    uint32_t capped;             // the automaton has a cycle: an attempt still alive after 16 bytes is not ours to finish
 };
 
 // table layouts: TAB_PART  compact rows, the first smem_states of them in shared memory, the rest in L2
@@ -91,16 +92,16 @@ __device__ __forceinline__ uint32_t next_entry(const MatchTables &T, uint32_t s,
 
 // One finished walk: m = bytes consumed by the match (0 = no match).
 template <int TAB>
-__device__ __forceinline__ uint32_t walk_from(const MatchTables &T, const uint8_t *s_in, uint32_t p) {
+__device__ __forceinline__ uint32_t walk_from(const MatchTables &T, const uint8_t *s_in, uint32_t p, uint32_t &overflow) {
     uint32_t lo = T.row0_s[s_in[p]];
     uint32_t i = 1, m = (lo & DSA_E_MARK) ? 1u : 0u;
     while (!(lo & DSA_E_DECIDED)) {
         const uint32_t nx = next_entry<TAB>(T, lo & 0xFFFFFFu, s_in[p + i]);   // p + i <= 511 + 16: inside the halo
         if ((nx & 0xFFFFFFu) == DSA_DEAD) break;                     // '\n' (line end, padding) is dead
-        lo = nx;
+        if (i >= 16) { overflow |= T.capped; break; }                // only a cyclic automaton gets here alive (a{17,}, [0-9]+ on
+        lo = nx;                                                     // a run of 17 digits): the per-line kernels take the buffer
         ++i;
         if (lo & DSA_E_MARK) m = i;
-        if (i >= 16) break;
     }
     return (lo & (DSA_E_DECIDED | DSA_E_HASFINAL)) ? m : 0u;
 }
@@ -187,7 +188,7 @@ __device__ __forceinline__ void resolve_chain(Front &f, uint32_t C, uint32_t lan
 
 template <int TAB>
 __device__ __forceinline__ Front tile_frontend(const MatchTables &T, const uint8_t *s_in, uint4 x, uint32_t lane,
-                                               uint32_t first_valid, uint32_t carry_e) {
+                                               uint32_t first_valid, uint32_t carry_e, uint32_t &overflow) {
     // ---- B: can an attempt starting with this byte survive its first transition? -> candidate mask ---
     uint32_t cand = 0;
     {
@@ -220,7 +221,7 @@ __device__ __forceinline__ Front tile_frontend(const MatchTables &T, const uint8
     while (cand) {
         const uint32_t j = __ffs(cand) - 1;
         cand &= cand - 1;
-        const uint32_t m = walk_from<TAB>(T, s_in, lane * 16 + j);
+        const uint32_t m = walk_from<TAB>(T, s_in, lane * 16 + j, overflow);
         if (m) { C |= 1u << j; f.lens |= (unsigned long long)(m - 1) << (4 * j); }
     }
 
@@ -244,7 +245,9 @@ __device__ __forceinline__ void match_tile(const MatchArgs &a, const MatchTables
     }
     nul_acc |= ((x.x - 0x01010101u) & ~x.x) | ((x.y - 0x01010101u) & ~x.y) | ((x.z - 0x01010101u) & ~x.z) | ((x.w - 0x01010101u) & ~x.w);
 
-    const Front f = tile_frontend<TAB>(T, s_in, x, lane, first_valid, carry_e);
+    uint32_t overflow = 0;
+    const Front f = tile_frontend<TAB>(T, s_in, x, lane, first_valid, carry_e, overflow);
+    if (overflow) status |= ST_IRREGULAR;
     uint32_t real = f.real;
     const unsigned long long lens = f.lens;
     const uint32_t e_out = f.e_out;
@@ -345,7 +348,9 @@ __device__ __forceinline__ void var_count_tile(const MatchArgs &a, const MatchTa
     *reinterpret_cast<uint4 *>(W.s_in + lane * 16) = x;
     if (lane == 0) { *reinterpret_cast<uint4 *>(W.s_in + kTile) = halo_in; *W.s_count = 0; }
     nul_acc |= ((x.x - 0x01010101u) & ~x.x) | ((x.y - 0x01010101u) & ~x.y) | ((x.z - 0x01010101u) & ~x.z) | ((x.w - 0x01010101u) & ~x.w);
-    const Front f = tile_frontend<TAB>(T, W.s_in, x, lane, first_valid, carry_e);
+    uint32_t overflow = 0;
+    const Front f = tile_frontend<TAB>(T, W.s_in, x, lane, first_valid, carry_e, overflow);
+    if (overflow) nul_acc |= 0x80u;                                   // reported as ST_IRREGULAR with the NUL detector
     carry_e = __shfl_sync(0xFFFFFFFFu, f.e_out, 31);
     if (ACTIVE) {
         const size_t my = base + (size_t)lane * 16;
@@ -375,7 +380,8 @@ __device__ __forceinline__ void var_write_tile(const MatchArgs &a, const MatchTa
                                                OutWindow &ow) {
     *reinterpret_cast<uint4 *>(W.s_in + lane * 16) = x;
     if (lane == 0) { *reinterpret_cast<uint4 *>(W.s_in + kTile) = halo_in; *W.s_count = 0; }
-    const Front f = tile_frontend<TAB>(T, W.s_in, x, lane, first_valid, carry_e);
+    uint32_t overflow = 0;                                            // the count pass has already reported it
+    const Front f = tile_frontend<TAB>(T, W.s_in, x, lane, first_valid, carry_e, overflow);
     carry_e = __shfl_sync(0xFFFFFFFFu, f.e_out, 31);
     if (!ACTIVE) { __syncwarp(); return; }
     const uint32_t slot0 = publish_matches(f, W, lane);
@@ -491,6 +497,7 @@ k_match(MatchArgs a) {
     T.live_s = live_s; T.row0_s = row0_s; T.classmap_s = classmap_s; T.ctrans_s = ctrans_s; T.ctrans_g = a.P.ctrans;
     T.pool = pool_s ? pool_s : a.P.pool;
     T.n_classes = a.P.n_classes; T.smem_states = a.smem_states; T.lane = lane;
+    T.capped = (a.P.flags & PF_ACYCLIC) ? 0u : 1u;
 
     uint8_t *s_in = warp_base, *s_out = warp_base + 544;
     uint16_t *s_list = reinterpret_cast<uint16_t *>(warp_base + 1088);
