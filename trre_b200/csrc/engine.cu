@@ -87,6 +87,10 @@ struct DeviceState {
     cudaEvent_t slot_done[kSlots] = {nullptr, nullptr, nullptr};
     MatchPlan mp, mpv;             // k_match launch plans: length preserving / variable length
     bool staged_attr = false;
+    GramArgs gramv{};              // k_gram_var: the same tables for programs whose matches change the length
+    size_t gramv_smem = 0;
+    bool gramv_small = false;
+    const void *gramv_fn[2] = {nullptr, nullptr};   // count, write
     GramArgs gram{};               // k_gram tables (entries == 0: none)
     size_t gram_smem = 0;
     bool gram_small = false;
@@ -183,6 +187,21 @@ int plan_match(const BlobHeader &h, size_t warp_bytes, size_t budget, int sm_cou
     }
     mp->blocks = sm_count * (per_sm < 1 ? 1 : per_sm);
     return TRRE_OK;
+}
+
+const void *gram_var_kernel(uint32_t depth, bool small, int op) {
+#define GV(D) (small ? (op == OP_COUNT ? (const void *)k_gram_var<D, true, OP_COUNT> : (const void *)k_gram_var<D, true, OP_WRITE>) \
+                     : (op == OP_COUNT ? (const void *)k_gram_var<D, false, OP_COUNT> : (const void *)k_gram_var<D, false, OP_WRITE>))
+    switch (depth) {
+        case 1: return GV(1);
+        case 2: return GV(2);
+        case 3: return GV(3);
+        case 4: return GV(4);
+        case 5: return GV(5);
+        case 6: return GV(6);
+        default: return nullptr;
+    }
+#undef GV
 }
 
 const void *gram_kernel(uint32_t depth, bool small, bool reg) {
@@ -297,6 +316,33 @@ int get_state(const trre_prog *cp, int device, DeviceState **out) {
         d->gram_fn = gram_kernel(h.gram_depth, d->gram_small, reg);
         if (d->gram_fn && d->gram_smem <= 220 * 1024) {
             CUDA_TRY(cudaFuncSetAttribute(d->gram_fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)d->gram_smem));
+        } else {
+            g.entries = 0;
+        }
+    }
+    if ((h.flags & PF_GRAM) && (h.flags & PF_MATCHABLE_VAR)) {
+        GramArgs &g = d->gramv;
+        g.classmap = d->P.classmap;
+        g.gbits = reinterpret_cast<const uint32_t *>(d->d_blob + h.off_gbits);
+        g.gout = reinterpret_cast<const uint32_t *>(d->d_blob + h.off_gout);
+        g.gpool = d->d_blob + h.off_gpool;
+        g.gpool_bytes = h.gpool_bytes;
+        g.n_classes = h.n_classes;
+        g.entries = h.gram_entries;
+        g.uniform_len = h.gram_len;
+        g.gflags = h.gram_flags;
+        const uint32_t words = (h.gram_entries + 31) / 32;
+        d->gramv_small = h.gram_entries <= kGramSmallEntries;
+        g.gout_in_smem = h.gram_entries <= 4096 ? 1u : 0u;
+        g.pool_in_smem = (h.gpool_bytes && h.gpool_bytes <= 4096) ? 1u : 0u;
+        d->gramv_smem = 256 * 32 * 4 + (d->gramv_small ? (size_t)h.gram_entries * 128 : (size_t)((words + 3) & ~3u) * 4) +
+                        (g.gout_in_smem ? (size_t)((h.gram_entries + 3) & ~3u) * 4 : 0) +
+                        (g.pool_in_smem ? ((h.gpool_bytes + 15) & ~15u) : 0) + (size_t)kGramWarps * kVarWarpSmem;
+        d->gramv_fn[0] = gram_var_kernel(h.gram_depth, d->gramv_small, OP_COUNT);
+        d->gramv_fn[1] = gram_var_kernel(h.gram_depth, d->gramv_small, OP_WRITE);
+        if (d->gramv_fn[0] && d->gramv_smem <= 220 * 1024 && !(h.gram_flags & GRAM_DIRECT)) {
+            CUDA_TRY(cudaFuncSetAttribute(d->gramv_fn[0], cudaFuncAttributeMaxDynamicSharedMemorySize, (int)d->gramv_smem));
+            CUDA_TRY(cudaFuncSetAttribute(d->gramv_fn[1], cudaFuncAttributeMaxDynamicSharedMemorySize, (int)d->gramv_smem));
         } else {
             g.entries = 0;
         }
@@ -594,10 +640,12 @@ bool mv_capable(const trre_prog *p, const DeviceState *d, const uint8_t *d_in) {
 // variable-length matches on a regular buffer: k_match<OP_COUNT> -> scan over the warp spans -> k_match<OP_WRITE>
 int launch_mv(const trre_prog *p, DeviceState *d, const uint8_t *d_in, size_t n, uint8_t *d_out, size_t out_cap,
               cudaStream_t st, int phase, int *launches, const Ws *ws = nullptr) {
+    const bool gram = d->gramv.entries && !std::getenv("TRRE_NO_GRAM");
+    const size_t warps = gram ? kGramWarps : kMatchWarps;
     const size_t n_tiles = (n + kTile - 1) / kTile;
-    size_t blocks = std::min<size_t>((size_t)d->mpv.blocks, (n_tiles + 16 * kMatchWarps - 1) / (16 * kMatchWarps));
+    size_t blocks = std::min<size_t>(gram ? (size_t)d->sm_count : (size_t)d->mpv.blocks, (n_tiles + 16 * warps - 1) / (16 * warps));
     if (blocks < 1) blocks = 1;
-    const size_t n_spans = blocks * kMatchWarps;
+    const size_t n_spans = blocks * warps;
     if (!ws) { int rc = ensure_workspace(d, 0, n_spans, false, 0); if (rc != TRRE_OK) return rc; }
     MatchArgs m{};
     m.P = d->P; m.in = d_in; m.out = d_out; m.n = n; m.status = ws ? ws->status : d->d_status;
@@ -605,8 +653,11 @@ int launch_mv(const trre_prog *p, DeviceState *d, const uint8_t *d_in, size_t n,
     m.tiles_per_warp = (n_tiles + n_spans - 1) / n_spans;
     m.gsum = ws ? ws->gsum : d->d_gsum; m.total = ws ? ws->total : d->d_total; m.out_cap = out_cap;
     const int tab = d->mpv.tab;
+    GramArgs g = d->gramv;
+    void *gargs[] = {&m, &g};
     if (phase != PH_WRITE) {
-        if (tab == TAB_WIDE) k_match<TAB_WIDE, OP_COUNT><<<(int)blocks, kMatchThreads, d->mpv.smem, st>>>(m);
+        if (gram) CUDA_TRY(cudaLaunchKernel(d->gramv_fn[0], dim3((unsigned)blocks), dim3(kGramThreads), gargs, d->gramv_smem, st));
+        else if (tab == TAB_WIDE) k_match<TAB_WIDE, OP_COUNT><<<(int)blocks, kMatchThreads, d->mpv.smem, st>>>(m);
         else if (tab == TAB_ALL) k_match<TAB_ALL, OP_COUNT><<<(int)blocks, kMatchThreads, d->mpv.smem, st>>>(m);
         else k_match<TAB_PART, OP_COUNT><<<(int)blocks, kMatchThreads, d->mpv.smem, st>>>(m);
         k_scan_groups<<<1, kScanThreads, 0, st>>>(m.gsum, n_spans, const_cast<unsigned long long *>(m.total));
@@ -614,7 +665,8 @@ int launch_mv(const trre_prog *p, DeviceState *d, const uint8_t *d_in, size_t n,
         if (!ws) d->counts_kind = 3;
     }
     if (phase != PH_SIZE) {
-        if (tab == TAB_WIDE) k_match<TAB_WIDE, OP_WRITE><<<(int)blocks, kMatchThreads, d->mpv.smem, st>>>(m);
+        if (gram) CUDA_TRY(cudaLaunchKernel(d->gramv_fn[1], dim3((unsigned)blocks), dim3(kGramThreads), gargs, d->gramv_smem, st));
+        else if (tab == TAB_WIDE) k_match<TAB_WIDE, OP_WRITE><<<(int)blocks, kMatchThreads, d->mpv.smem, st>>>(m);
         else if (tab == TAB_ALL) k_match<TAB_ALL, OP_WRITE><<<(int)blocks, kMatchThreads, d->mpv.smem, st>>>(m);
         else k_match<TAB_PART, OP_WRITE><<<(int)blocks, kMatchThreads, d->mpv.smem, st>>>(m);
         *launches += 1;

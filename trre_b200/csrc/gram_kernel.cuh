@@ -264,12 +264,10 @@ __device__ __forceinline__ void gram_tile(const GramArgs &a, const GramTables &T
     __syncwarp();
 }
 
-template <int D, bool SMALL, bool REG>
-__global__ void __launch_bounds__(kGramThreads, 1)
-k_gram(GramArgs a) {
-    extern __shared__ __align__(16) uint8_t smem[];
-    const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    // layout: [class table 32 KB] [SMALL: hit words x32 | bitmap] [gout]? [pool]? [per warp: s_in, s_out]
+// Tables into shared memory (every thread of the CTA takes part, ends with __syncthreads); returns where the per-warp
+// areas start.  layout: [class table 32 KB] [SMALL: hit words x32 | bitmap] [gout]? [pool]?
+template <bool SMALL, bool REG>
+__device__ __forceinline__ uint8_t *gram_setup(const GramArgs &a, uint8_t *smem, uint32_t lane, GramTables &T) {
     uint8_t *cur = smem;
     uint32_t *cls_s = reinterpret_cast<uint32_t *>(cur); cur += 256 * 32 * 4;
     uint32_t *bits_s = reinterpret_cast<uint32_t *>(cur);
@@ -279,7 +277,6 @@ k_gram(GramArgs a) {
     if (a.gout_in_smem) { gout_s = reinterpret_cast<uint32_t *>(cur); cur += (size_t)((a.entries + 3) & ~3u) * 4; }
     uint8_t *pool_s = nullptr;
     if (a.pool_in_smem) { pool_s = cur; cur += (a.gpool_bytes + 15) & ~15u; }
-    uint8_t *warp_base = cur + (REG ? 0 : warp * kGramWarpSmem);     // REG: no staging area at all
 
     for (uint32_t k = threadIdx.x; k < 256u * 32u; k += blockDim.x) cls_s[k] = __ldg(a.classmap + (k >> 5));
     if (SMALL) {
@@ -297,13 +294,69 @@ k_gram(GramArgs a) {
         for (uint32_t k = threadIdx.x; k < a.gpool_bytes; k += blockDim.x) pool_s[k] = __ldg(a.gpool + k);
     __syncthreads();
 
-    GramTables T;
     T.cls_b = reinterpret_cast<const uint8_t *>(cls_s);
     T.hit_b = reinterpret_cast<const uint8_t *>(bits_s);
     T.bits = bits_s;
     T.gout = gout_s ? gout_s : a.gout;
     T.pool = pool_s ? pool_s : a.gpool;
     T.lane4 = lane * 4;
+    return cur;
+}
+
+// ---- variable-length matches through the gram tables (PF_MATCHABLE_VAR programs with gram tables: cat:mouse, (cat):) ----
+// The front end of the count / write tiles of match_kernel.cuh, as a policy: candidates and their consumed lengths come
+// from the tables instead of a walk; what a real match prints is gout's pool reference.
+template <int D, bool SMALL>
+struct GramFE {
+    const GramArgs &g;
+    const GramTables &T;
+    __device__ __forceinline__ const uint8_t *pool() const { return T.pool; }
+    __device__ __forceinline__ Front front(const uint8_t *s_in, uint4 x, uint4 halo, uint32_t lane, uint32_t first_valid,
+                                           uint32_t carry_e, uint32_t &overflow) const {
+        (void)overflow;
+        uint32_t pay[16];
+        const uint32_t cand = gram_candidates<D, SMALL>(g, T, x, halo, lane, first_valid, pay);   // every lane holds the halo
+        __syncwarp();                                                 // the staged tile is visible
+        Front f;
+        if (g.uniform_len) {
+            f.lens = 0x1111111111111111ull * (unsigned long long)(g.uniform_len - 1);
+        } else {
+            f.lens = 0;
+            uint32_t c2 = cand;
+            while (c2) {
+                const uint32_t j = __ffs(c2) - 1;
+                c2 &= c2 - 1;
+                const uint32_t e = T.gout[gram_index_at<D>(T, s_in, lane * 16 + j, g.n_classes)];
+                f.lens |= (unsigned long long)(e >> 28) << (4 * j);
+            }
+        }
+        resolve_chain(f, cand, lane, carry_e);
+        return f;
+    }
+    __device__ __forceinline__ uint32_t entry(const uint8_t *s_in, uint32_t p) const {
+        const uint32_t e = T.gout[gram_index_at<D>(T, s_in, p, g.n_classes)];
+        return (e & 0xFFFFFu) | (((e >> 20) & 0xFFu) << 24);          // offset(24) | printed length(8), as WalkFE::entry
+    }
+};
+
+template <int D, bool SMALL, int OP>
+__global__ void __launch_bounds__(kGramThreads, 1)
+k_gram_var(MatchArgs m, GramArgs g) {
+    extern __shared__ __align__(16) uint8_t smem[];
+    const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    GramTables T;
+    uint8_t *cur = gram_setup<SMALL, false>(g, smem, lane, T);
+    span_loop<OP>(m, GramFE<D, SMALL>{g, T}, cur + warp * kVarWarpSmem, lane);
+}
+
+template <int D, bool SMALL, bool REG>
+__global__ void __launch_bounds__(kGramThreads, 1)
+k_gram(GramArgs a) {
+    extern __shared__ __align__(16) uint8_t smem[];
+    const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    GramTables T;
+    uint8_t *cur = gram_setup<SMALL, REG>(a, smem, lane, T);
+    uint8_t *warp_base = cur + (REG ? 0 : warp * kGramWarpSmem);     // REG: no staging area at all
 
     uint8_t *s_in = warp_base, *s_out = warp_base + 544;
 

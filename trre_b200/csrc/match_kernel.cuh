@@ -311,6 +311,24 @@ __device__ __forceinline__ uint32_t match_entry(const MatchArgs &a, const MatchT
     return __ldg(a.P.eout + slot);
 }
 
+// The front end as a policy, so that the variable-length tiles serve both table forms: WalkFE walks the compact
+// automaton (here), GramFE looks every attempt up in the gram tables (gram_kernel.cuh).
+//   front()  steps B-D of a tile: which matches of the lane's 16 positions are real
+//   entry()  offset(24) | length(8) of what the real match at tile position p prints, in pool()
+template <int TAB>
+struct WalkFE {
+    static constexpr int kTab = TAB;
+    const MatchArgs &a;
+    const MatchTables &T;
+    __device__ __forceinline__ const uint8_t *pool() const { return T.pool; }
+    __device__ __forceinline__ Front front(const uint8_t *s_in, uint4 x, uint4 halo, uint32_t lane, uint32_t first_valid,
+                                           uint32_t carry_e, uint32_t &overflow) const {
+        (void)halo;
+        return tile_frontend<TAB>(T, s_in, x, lane, first_valid, carry_e, overflow);
+    }
+    __device__ __forceinline__ uint32_t entry(const uint8_t *s_in, uint32_t p) const { return match_entry<TAB>(a, T, s_in, p); }
+};
+
 // positions of this lane covered by a match (its own real ones or the one hanging in from before)
 __device__ __forceinline__ uint32_t covered_mask(const Front &f) {
     uint32_t cov = (1u << f.e_in) - 1u;
@@ -341,15 +359,15 @@ __device__ __forceinline__ uint32_t publish_matches(const Front &f, const VarWar
     return slot0;
 }
 
-template <bool ACTIVE, int TAB>
-__device__ __forceinline__ void var_count_tile(const MatchArgs &a, const MatchTables &T, const VarWarp &W, size_t base, uint4 x,
+template <bool ACTIVE, class FE>
+__device__ __forceinline__ void var_count_tile(const MatchArgs &a, const FE &fe, const VarWarp &W, size_t base, uint4 x,
                                                uint4 halo_in, uint32_t lane, uint32_t first_valid, uint32_t &carry_e,
                                                uint32_t &nul_acc, unsigned long long &span_sum) {
     *reinterpret_cast<uint4 *>(W.s_in + lane * 16) = x;
     if (lane == 0) { *reinterpret_cast<uint4 *>(W.s_in + kTile) = halo_in; *W.s_count = 0; }
     nul_acc |= ((x.x - 0x01010101u) & ~x.x) | ((x.y - 0x01010101u) & ~x.y) | ((x.z - 0x01010101u) & ~x.z) | ((x.w - 0x01010101u) & ~x.w);
     uint32_t overflow = 0;
-    const Front f = tile_frontend<TAB>(T, W.s_in, x, lane, first_valid, carry_e, overflow);
+    const Front f = fe.front(W.s_in, x, halo_in, lane, first_valid, carry_e, overflow);
     if (overflow) nul_acc |= 0x80u;                                   // reported as ST_IRREGULAR with the NUL detector
     carry_e = __shfl_sync(0xFFFFFFFFu, f.e_out, 31);
     if (ACTIVE) {
@@ -359,7 +377,7 @@ __device__ __forceinline__ void var_count_tile(const MatchArgs &a, const MatchTa
         publish_matches(f, W, lane);
         __syncwarp();
         const uint32_t total = *W.s_count;
-        for (uint32_t q = lane; q < total; q += 32) mine += match_entry<TAB>(a, T, W.s_in, W.s_ent[q]) >> 24;
+        for (uint32_t q = lane; q < total; q += 32) mine += fe.entry(W.s_in, W.s_ent[q]) >> 24;
 #pragma unroll
         for (int d = 16; d; d >>= 1) mine += __shfl_xor_sync(0xFFFFFFFFu, mine, d);
         span_sum += mine;
@@ -374,21 +392,21 @@ struct OutWindow {
     uint32_t fill, foreign;
 };
 
-template <bool ACTIVE, int TAB>
-__device__ __forceinline__ void var_write_tile(const MatchArgs &a, const MatchTables &T, const VarWarp &W, size_t base, uint4 x,
+template <bool ACTIVE, class FE>
+__device__ __forceinline__ void var_write_tile(const MatchArgs &a, const FE &fe, const VarWarp &W, size_t base, uint4 x,
                                                uint4 halo_in, uint32_t lane, uint32_t first_valid, uint32_t &carry_e,
                                                OutWindow &ow) {
     *reinterpret_cast<uint4 *>(W.s_in + lane * 16) = x;
     if (lane == 0) { *reinterpret_cast<uint4 *>(W.s_in + kTile) = halo_in; *W.s_count = 0; }
     uint32_t overflow = 0;                                            // the count pass has already reported it
-    const Front f = tile_frontend<TAB>(T, W.s_in, x, lane, first_valid, carry_e, overflow);
+    const Front f = fe.front(W.s_in, x, halo_in, lane, first_valid, carry_e, overflow);
     carry_e = __shfl_sync(0xFFFFFFFFu, f.e_out, 31);
     if (!ACTIVE) { __syncwarp(); return; }
     const uint32_t slot0 = publish_matches(f, W, lane);
     __syncwarp();
     {
         const uint32_t total = *W.s_count;
-        for (uint32_t q = lane; q < total; q += 32) W.s_ent[q] = match_entry<TAB>(a, T, W.s_in, W.s_ent[q]);
+        for (uint32_t q = lane; q < total; q += 32) W.s_ent[q] = fe.entry(W.s_in, W.s_ent[q]);
     }
     __syncwarp();
     // lengths of this lane's 16 positions
@@ -420,7 +438,7 @@ __device__ __forceinline__ void var_write_tile(const MatchArgs &a, const MatchTa
         for (int j = 0; j < 16; ++j) {
             if (f.real & (1u << j)) {
                 const uint32_t ent = W.s_ent[slot0 + k++];
-                const uint8_t *src = T.pool + (ent & 0xFFFFFFu);
+                const uint8_t *src = fe.pool() + (ent & 0xFFFFFFu);
                 const uint32_t len = ent >> 24;
                 for (uint32_t q = 0; q < len; ++q) dst[at + q] = src[q];
                 at += len;
@@ -461,44 +479,10 @@ __device__ __forceinline__ void var_write_tile(const MatchArgs &a, const MatchTa
     __syncwarp();
 }
 
-template <int TAB, int OP>
-__global__ void __launch_bounds__(kMatchThreads)
-k_match(MatchArgs a) {
-    extern __shared__ __align__(16) uint8_t smem[];
-    const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    // layout: [live 32 KB]? [row0 1 KB] [classmap 256] [pool copy]? [ctrans rows] [per warp: s_in, s_out, list]
-    uint8_t *cur = smem;
-    uint32_t *live_s = nullptr;
-    if (a.row0_replicated) { live_s = reinterpret_cast<uint32_t *>(cur); cur += 256 * 32 * 4; }
-    uint32_t *row0_s = reinterpret_cast<uint32_t *>(cur); cur += 1024;
-    uint8_t *classmap_s = cur; cur += 256;
-    uint8_t *pool_s = nullptr;
-    if (a.pool_in_smem) { pool_s = cur; cur += (a.P.pool_bytes + 15) & ~15u; }
-    uint32_t *ctrans_s = reinterpret_cast<uint32_t *>(cur);
-    const uint32_t ct_words = TAB == TAB_WIDE ? a.P.n_states * 256u : a.smem_states * a.P.n_classes;
-    cur += ((ct_words + 3) & ~3u) * 4;
-    uint8_t *warp_base = cur + warp * (OP == OP_INPLACE ? kWarpSmem : kVarWarpSmem);
-
-    if (live_s)
-        for (uint32_t k = threadIdx.x; k < 256u * 32u; k += blockDim.x)
-            live_s[k] = (__ldg(a.P.row0 + (k >> 5)) & 0xFFFFFFu) != DSA_DEAD ? 1u : 0u;
-    for (uint32_t k = threadIdx.x; k < 256; k += blockDim.x) { row0_s[k] = __ldg(a.P.row0 + k); classmap_s[k] = __ldg(a.P.classmap + k); }
-    if (pool_s)
-        for (uint32_t k = threadIdx.x; k < a.P.pool_bytes; k += blockDim.x) pool_s[k] = __ldg(a.P.pool + k);
-    if (TAB == TAB_WIDE) {
-        for (uint32_t k = threadIdx.x; k < ct_words; k += blockDim.x)
-            ctrans_s[k] = __ldg(a.P.ctrans + (k >> 8) * a.P.n_classes + __ldg(a.P.classmap + (k & 255u)));
-    } else {
-        for (uint32_t k = threadIdx.x; k < ct_words; k += blockDim.x) ctrans_s[k] = __ldg(a.P.ctrans + k);
-    }
-    __syncthreads();
-
-    MatchTables T;
-    T.live_s = live_s; T.row0_s = row0_s; T.classmap_s = classmap_s; T.ctrans_s = ctrans_s; T.ctrans_g = a.P.ctrans;
-    T.pool = pool_s ? pool_s : a.P.pool;
-    T.n_classes = a.P.n_classes; T.smem_states = a.smem_states; T.lane = lane;
-    T.capped = (a.P.flags & PF_ACYCLIC) ? 0u : 1u;
-
+// One warp's span of tiles, after the kernel has set its tables up: warm-up from the last '\n' before the span, then the
+// tiles (in place / count / write).  Shared by k_match (WalkFE) and k_gram_var (GramFE).
+template <int OP, class FE>
+__device__ __forceinline__ void span_loop(const MatchArgs &a, const FE &fe, uint8_t *warp_base, uint32_t lane) {
     uint8_t *s_in = warp_base, *s_out = warp_base + 544;
     uint16_t *s_list = reinterpret_cast<uint16_t *>(warp_base + 1088);
     uint32_t *s_count = reinterpret_cast<uint32_t *>(warp_base + 1088 + 1024);
@@ -516,7 +500,7 @@ k_match(MatchArgs a) {
     }
     const size_t n = a.n;
     const size_t n_tiles = (n + kTile - 1) / kTile;
-    const size_t gwarp = (size_t)blockIdx.x * kMatchWarps + warp;
+    const size_t gwarp = (size_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     const size_t t0 = gwarp * a.tiles_per_warp;
     size_t t1 = t0 + a.tiles_per_warp;
     if (t1 > n_tiles) t1 = n_tiles;
@@ -568,15 +552,15 @@ k_match(MatchArgs a) {
             uint4 halo_in = load_padded(a.in, base + kTile, n);
             uint4 x_next = make_uint4(0x0A0A0A0Au, 0x0A0A0A0Au, 0x0A0A0A0Au, 0x0A0A0A0Au);
             if (t + 1 < t1) x_next = load_padded(a.in, base + kTile + lane * 16, n);   // prefetch
-            if (OP == OP_INPLACE) {
-                if (t < t0) match_tile<false, TAB>(a, T, s_in, s_out, s_list, s_count, base, x, halo_in, lane, first_valid, carry_e, carry_halo, nul_acc, status);
-                else        match_tile<true, TAB>(a, T, s_in, s_out, s_list, s_count, base, x, halo_in, lane, first_valid, carry_e, carry_halo, nul_acc, status);
-            } else if (OP == OP_COUNT) {
-                if (t < t0) var_count_tile<false, TAB>(a, T, W, base, x, halo_in, lane, first_valid, carry_e, nul_acc, span_sum);
-                else        var_count_tile<true, TAB>(a, T, W, base, x, halo_in, lane, first_valid, carry_e, nul_acc, span_sum);
+            if constexpr (OP == OP_INPLACE) {
+                if (t < t0) match_tile<false, FE::kTab>(a, fe.T, s_in, s_out, s_list, s_count, base, x, halo_in, lane, first_valid, carry_e, carry_halo, nul_acc, status);
+                else        match_tile<true, FE::kTab>(a, fe.T, s_in, s_out, s_list, s_count, base, x, halo_in, lane, first_valid, carry_e, carry_halo, nul_acc, status);
+            } else if constexpr (OP == OP_COUNT) {
+                if (t < t0) var_count_tile<false, FE>(a, fe, W, base, x, halo_in, lane, first_valid, carry_e, nul_acc, span_sum);
+                else        var_count_tile<true, FE>(a, fe, W, base, x, halo_in, lane, first_valid, carry_e, nul_acc, span_sum);
             } else {
-                if (t < t0) var_write_tile<false, TAB>(a, T, W, base, x, halo_in, lane, first_valid, carry_e, ow);
-                else        var_write_tile<true, TAB>(a, T, W, base, x, halo_in, lane, first_valid, carry_e, ow);
+                if (t < t0) var_write_tile<false, FE>(a, fe, W, base, x, halo_in, lane, first_valid, carry_e, ow);
+                else        var_write_tile<true, FE>(a, fe, W, base, x, halo_in, lane, first_valid, carry_e, ow);
             }
             first_valid = 0;
             x = x_next;
@@ -589,6 +573,47 @@ k_match(MatchArgs a) {
     if (nul_acc & 0x80808080u) status |= ST_IRREGULAR;
     if (blockIdx.x == 0 && threadIdx.x == 0 && n && a.in[n - 1] != '\n') status |= ST_IRREGULAR;
     if (status) atomicOr(a.status, status);
+}
+
+template <int TAB, int OP>
+__global__ void __launch_bounds__(kMatchThreads)
+k_match(MatchArgs a) {
+    extern __shared__ __align__(16) uint8_t smem[];
+    const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    // layout: [live 32 KB]? [row0 1 KB] [classmap 256] [pool copy]? [ctrans rows] [per warp: s_in, s_out, list]
+    uint8_t *cur = smem;
+    uint32_t *live_s = nullptr;
+    if (a.row0_replicated) { live_s = reinterpret_cast<uint32_t *>(cur); cur += 256 * 32 * 4; }
+    uint32_t *row0_s = reinterpret_cast<uint32_t *>(cur); cur += 1024;
+    uint8_t *classmap_s = cur; cur += 256;
+    uint8_t *pool_s = nullptr;
+    if (a.pool_in_smem) { pool_s = cur; cur += (a.P.pool_bytes + 15) & ~15u; }
+    uint32_t *ctrans_s = reinterpret_cast<uint32_t *>(cur);
+    const uint32_t ct_words = TAB == TAB_WIDE ? a.P.n_states * 256u : a.smem_states * a.P.n_classes;
+    cur += ((ct_words + 3) & ~3u) * 4;
+    uint8_t *warp_base = cur + warp * (OP == OP_INPLACE ? kWarpSmem : kVarWarpSmem);
+
+    if (live_s)
+        for (uint32_t k = threadIdx.x; k < 256u * 32u; k += blockDim.x)
+            live_s[k] = (__ldg(a.P.row0 + (k >> 5)) & 0xFFFFFFu) != DSA_DEAD ? 1u : 0u;
+    for (uint32_t k = threadIdx.x; k < 256; k += blockDim.x) { row0_s[k] = __ldg(a.P.row0 + k); classmap_s[k] = __ldg(a.P.classmap + k); }
+    if (pool_s)
+        for (uint32_t k = threadIdx.x; k < a.P.pool_bytes; k += blockDim.x) pool_s[k] = __ldg(a.P.pool + k);
+    if (TAB == TAB_WIDE) {
+        for (uint32_t k = threadIdx.x; k < ct_words; k += blockDim.x)
+            ctrans_s[k] = __ldg(a.P.ctrans + (k >> 8) * a.P.n_classes + __ldg(a.P.classmap + (k & 255u)));
+    } else {
+        for (uint32_t k = threadIdx.x; k < ct_words; k += blockDim.x) ctrans_s[k] = __ldg(a.P.ctrans + k);
+    }
+    __syncthreads();
+
+    MatchTables T;
+    T.live_s = live_s; T.row0_s = row0_s; T.classmap_s = classmap_s; T.ctrans_s = ctrans_s; T.ctrans_g = a.P.ctrans;
+    T.pool = pool_s ? pool_s : a.P.pool;
+    T.n_classes = a.P.n_classes; T.smem_states = a.smem_states; T.lane = lane;
+    T.capped = (a.P.flags & PF_ACYCLIC) ? 0u : 1u;
+
+    span_loop<OP>(a, WalkFE<TAB>{a, T}, warp_base, lane);
 }
 
 }  // namespace trre
