@@ -35,7 +35,7 @@
 extern "C" {
 #endif
 
-#define TRRE_B200_ABI_VERSION 1
+#define TRRE_B200_ABI_VERSION 2
 
 /* which reference binary's semantics: `trre` (leftmost, first-by-priority, empty matches allowed)
  * or `trre_dft` (leftmost, shortest non-empty match). */
