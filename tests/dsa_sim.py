@@ -84,12 +84,8 @@ class Blob:
                 continue
             g = gout[idx]
             if h["gram_flags"] & 1:
-                # delta form: printed = consumed + signed difference, as little-endian integers of gram_len bytes
                 m = h["gram_len"]
-                d = g - (1 << 32) if g & 0x80000000 else g
-                f_new = int.from_bytes(data[p:p + m], "little") + d
-                assert 0 <= f_new < 1 << (8 * m), (idx, g)
-                rep = f_new.to_bytes(m, "little")
+                rep = bytes((g >> (8 * k)) & 0xFF for k in range(m))
             else:
                 m = (g >> 28) + 1
                 ln = (g >> 20) & 0xFF

@@ -675,38 +675,15 @@ bool build_grams(const Program &P, GramTables &G) {
     }
     if (!common) return false;                                    // nothing can match: leave it to the generic kernels
     G.uniform_len = uniform ? common : 0;
-    // GRAM_DIRECT ("delta form"): every match consumes and prints the same number L <= 4 of bytes AND the consumed bytes
-    // are known from the gram itself (every byte class at a consumed position holds exactly one byte - true for literal
-    // words).  Then gout holds the signed difference between the printed and the consumed bytes read as little-endian
-    // integers: adding it at the match's byte offset replaces the field exactly, with no masking (k_gram's register form).
-    int byte_of_class[256];
-    {
-        int count[256] = {0};
-        for (int c = 0; c < 256; ++c) { byte_of_class[c] = -1; }
-        for (int c = 0; c < 256; ++c) { ++count[P.classmap[c]]; byte_of_class[P.classmap[c]] = c; }
-        for (int k = 0; k < 256; ++k) if (count[k] != 1) byte_of_class[k] = -1;
-    }
-    bool direct = uniform && all_short && lp && common <= 4;
-    std::vector<int64_t> delta(direct ? entries : 0, 0);
-    for (uint64_t idx = 0; idx < entries && direct; ++idx) {
-        if (!consumed[idx]) continue;
-        uint64_t rest = idx, f_old = 0, f_new = 0;
-        for (uint32_t i = 0; i < common; ++i) {
-            const int b = byte_of_class[rest % ncls];
-            rest /= ncls;
-            if (b < 0) { direct = false; break; }
-            f_old |= (uint64_t)b << (8 * i);
-            f_new |= (uint64_t)(uint8_t)strs[idx][i] << (8 * i);
-        }
-        delta[idx] = (int64_t)f_new - (int64_t)f_old;
-        if (delta[idx] > INT32_MAX || delta[idx] < INT32_MIN) direct = false;
-    }
+    const bool direct = uniform && all_short && lp;
     if (direct) G.flags |= GRAM_DIRECT_FLAG;
     for (uint64_t idx = 0; idx < entries; ++idx) {
         if (!consumed[idx]) continue;
         const std::string &o = strs[idx];
         if (direct) {
-            G.out[idx] = (uint32_t)(int32_t)delta[idx];
+            uint32_t w = 0;
+            for (size_t k = 0; k < o.size(); ++k) w |= (uint32_t)(uint8_t)o[k] << (8 * k);
+            G.out[idx] = w;
         } else {
             uint32_t off = 0;
             if (!o.empty()) {

@@ -97,8 +97,8 @@ struct BlobHeader {
     uint32_t gram_len;         // > 0: every match consumes exactly this many bytes
     uint32_t gram_flags;       // GRAM_*
     uint32_t off_gbits;        // u32[(gram_entries + 31) / 32]: the attempt matches
-    uint32_t off_gout;         // u32[gram_entries]: GRAM_DIRECT: (printed - consumed) bytes as a signed little-endian integer
-                               // difference; else offset into gpool(20) | printed length(8) << 20 | (consumed - 1) << 28
+    uint32_t off_gout;         // u32[gram_entries]: GRAM_DIRECT: the printed bytes; else offset into gpool(20) |
+                               // printed length(8) << 20 | (consumed - 1) << 28
     uint32_t off_gpool;
     uint32_t gpool_bytes;
 };

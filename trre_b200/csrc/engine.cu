@@ -306,14 +306,13 @@ int get_state(const trre_prog *cp, int device, DeviceState **out) {
         d->gram_small = h.gram_entries <= kGramSmallEntries;
         g.gout_in_smem = h.gram_entries <= 4096 ? 1u : 0u;
         g.pool_in_smem = (h.gpool_bytes && h.gpool_bytes <= 4096) ? 1u : 0u;
-        // the delta form (registers only): GRAM_DIRECT programs
-        const bool reg = (h.gram_flags & GRAM_DIRECT) && h.gram_len >= 1 && h.gram_len <= 4 && !std::getenv("TRRE_GRAM_NO_REG");
-        g.len_mask = 0;
-        for (int k = 0; k < 4; ++k) g.mul[k] = 1 << (8 * k);
-        d->gram_smem = 256 * 32 * 4 + (d->gram_small ? (size_t)h.gram_entries * (reg ? 256 : 128) : (size_t)((words + 3) & ~3u) * 4) +
+        // the register form: one common match length, printed bytes in a word (with small tables: in the hit word, <= 3)
+        const bool reg = (h.gram_flags & GRAM_DIRECT) && h.gram_len >= 1 && h.gram_len <= (d->gram_small ? 3u : 4u) &&
+                         !std::getenv("TRRE_GRAM_NO_REG");
+        g.len_mask = h.gram_len >= 4 ? 0xFFFFFFFFu : ((1u << (8 * h.gram_len)) - 1u);
+        d->gram_smem = 256 * 32 * 4 + (d->gram_small ? (size_t)h.gram_entries * 128 : (size_t)((words + 3) & ~3u) * 4) +
                        (g.gout_in_smem ? (size_t)((h.gram_entries + 3) & ~3u) * 4 : 0) +
-                       (g.pool_in_smem ? ((h.gpool_bytes + 15) & ~15u) : 0) +
-                       (size_t)kGramWarps * (reg ? kGramStageBytes : kGramWarpSmem);
+                       (g.pool_in_smem ? ((h.gpool_bytes + 15) & ~15u) : 0) + (reg ? 0 : (size_t)kGramWarps * kGramWarpSmem);
         d->gram_fn = gram_kernel(h.gram_depth, d->gram_small, reg);
         if (d->gram_fn && d->gram_smem <= 220 * 1024) {
             CUDA_TRY(cudaFuncSetAttribute(d->gram_fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)d->gram_smem));

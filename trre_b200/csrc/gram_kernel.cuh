@@ -17,9 +17,9 @@
 //      mask.  With matches of one common length (every BASELINE config) their lengths need no lookup at all.
 //   D  chain resolution (resolve_chain, shared with k_match): which candidates start outside an earlier match
 //   E  the real matches - a few per cent of the positions - fetch their output from gout and overwrite their span of the
-//      tile.  Literal-word programs with one common match length <= 4 (every BASELINE config) use the DELTA form
-//      (gram_tile_delta): the output stays in registers and a match is one predicated IMAD.WIDE; otherwise the tile is
-//      staged in shared memory and matches copy their string
+//      tile.  When every match prints the same number (<= 4) of bytes the whole tile stays in REGISTERS: the bytes come
+//      with the hit word (small tables) or one predicated gout load per position, and are merged into the lane's four
+//      output words at compile-time byte offsets; otherwise the tile is staged in shared memory
 //   F  16-byte vector store per lane
 // Scan-driver semantics, warm-up from the last '\n' before a warp's span and ST_IRREGULAR handling are k_match's
 // (trre_nft.c:778-789 on a regular buffer: an attempt at every position not covered by an earlier match).
@@ -37,7 +37,7 @@ constexpr int kGramWarpSmem = 544 + 544;             // s_in (+halo), s_out (+ha
 constexpr uint32_t kGramSmallEntries = 512;          // up to here: one u32 per combination and lane (conflict free)
 
 enum : uint32_t {
-    GRAM_DIRECT = 1u,       // delta form: one common match length L <= 4, gout = (printed - consumed) as a signed integer
+    GRAM_DIRECT = 1u,       // gout holds the output bytes themselves (every match prints <= 4 bytes, one common length)
 };
 
 struct GramArgs {
@@ -48,7 +48,7 @@ struct GramArgs {
     size_t tiles_per_warp;
     const uint8_t *classmap;     // u8[256]
     const uint32_t *gbits;       // u32[(entries + 31) / 32]
-    const uint32_t *gout;        // u32[entries]: GRAM_DIRECT: delta; else pool offset(20) | printed length(8) << 20 | (consumed - 1) << 28
+    const uint32_t *gout;        // u32[entries]: GRAM_DIRECT: bytes; else pool offset(20) | printed length(8) << 20 | (consumed - 1) << 28
     const uint8_t *gpool;
     uint32_t gpool_bytes;
     uint32_t n_classes;
@@ -57,15 +57,12 @@ struct GramArgs {
     uint32_t gflags;
     uint32_t gout_in_smem;
     uint32_t pool_in_smem;
-    uint32_t len_mask;           // (unused)
-    int mul[4];                  // 1, 2^8, 2^16, 2^24 - as run-time values, so that "delta << (8 * offset)" stays ONE multiply-add on
-                                 // the FMA pipe (a literal power of two is strength-reduced to LEA + LEA.HI.X + 2 SEL on the ALU pipe)
+    uint32_t len_mask;           // REG form: 0xFF in the low uniform_len bytes
 };
 
 struct GramTables {
     const uint8_t *cls_b;        // shared: class of byte c for lane l at byte offset c * 128 + l * 4 (32 KB, bank = lane)
     const uint8_t *hit_b;        // SMALL: u32 per combination and lane at idx * 128 + l * 4, bit 31 = the attempt matches
-                                 //        (delta form: {flag, delta} at idx * 256 + l * 8)
     const uint32_t *bits;        // !SMALL: bitmap, bit (31 - idx % 32) of word idx / 32 (reversed: a left shift by idx
                                  // brings the bit to position 31)
     const uint32_t *gout;        // shared or global
@@ -146,117 +143,51 @@ __device__ __forceinline__ uint32_t gram_candidates(const GramArgs &a, const Gra
     return cand;
 }
 
-// The tile in registers - the delta form (GRAM_DIRECT programs: one common match length L <= 4, consumed bytes known from
-// the gram).  What bounds this kernel is the ALU pipe (LOP3 / SHF / IADD3 issue at half rate), so everything per
-// position runs on the LSU and FMA pipes instead:
-//   A  the lane's 16 bytes go to a per-warp staging row with a 20-byte stride (5 words: conflict free), and come back
-//      one byte at a time as LDS.U8 - no shift / mask to extract a byte
-//   B  class lookup address = byte * 128 + lane * 4 (IMAD), conflict-free LDS
-//   C  gram index by IMAD; small tables: one LDS.64 per position brings {hit flag, delta}; mask = mask * 2 + flag (IMAD)
-//   E  a real match adds delta << (8 * byte offset) to the 64-bit pair of output words it lies in - ONE predicated
-//      IMAD.WIDE replaces the field exactly (printed - consumed as integers: no masking, no byte permutes); the pairs are
-//      folded into the five words with four 64-bit adds.  What a match at positions 13..15 changes in the next lane's
-//      first word travels as a difference by shuffle (next tile: carry_sp).
-constexpr int kGramStageBytes = 672;                             // 33 rows of 20 bytes (32 lanes + the next tile's first words)
-
+// The tile in registers (GRAM_DIRECT programs: one common match length L <= 4, the printed bytes fit a word): no
+// shared-memory staging at all.  After the chain is resolved the real matches are merged into the lane's four output
+// words position by position (compile-time byte offsets, predicated on the `real` bit); the up to three bytes a match
+// at positions 13..15 prints past the lane's end travel to the next lane (next tile: carry_sp / carry_sm) by shuffle.
 template <int D, bool SMALL, bool STORE>
-__device__ __forceinline__ void gram_tile_delta(const GramArgs &a, const GramTables &T, uint8_t *s_st, size_t base, bool full,
-                                                uint4 x, uint4 x_next, uint32_t lane, uint32_t first_valid, uint32_t &carry_e,
-                                                int32_t &carry_sp, uint32_t &nul_acc) {
+__device__ __forceinline__ void gram_tile_reg(const GramArgs &a, const GramTables &T, size_t base, bool full, uint4 x, uint4 x_next,
+                                              uint32_t lane, uint32_t first_valid, uint32_t &carry_e, uint32_t &carry_sp,
+                                              uint32_t &carry_sm, uint32_t &nul_acc) {
     nul_acc |= ((x.x - 0x01010101u) & ~x.x) | ((x.y - 0x01010101u) & ~x.y) | ((x.z - 0x01010101u) & ~x.z) | ((x.w - 0x01010101u) & ~x.w);
-    // ---- A ---------------------------------------------------------------------------------------------------------------
-    {
-        uint32_t *sw = reinterpret_cast<uint32_t *>(s_st) + lane * 5;
-        sw[0] = x.x; sw[1] = x.y; sw[2] = x.z; sw[3] = x.w;
-        if (lane == 0) {
-            uint32_t *hw = reinterpret_cast<uint32_t *>(s_st) + 160;
-            hw[0] = x_next.x; hw[1] = x_next.y;
-        }
-    }
-    __syncwarp();
-    const uint8_t *sb = s_st + lane * 20;
-    // ---- B ---------------------------------------------------------------------------------------------------------------
-    const uint32_t ncls = a.n_classes;
-    uint32_t cls[16 + kGramMaxDepth - 1];
-#pragma unroll
-    for (int t = 0; t < 16 + D - 1; ++t) {
-        const uint32_t c = sb[t < 16 ? t : t + 4];                  // past the lane's 16 bytes: the next row
-        cls[t] = *reinterpret_cast<const uint32_t *>(T.cls_b + (c * 128u + T.lane4));
-    }
-    // ---- C ---------------------------------------------------------------------------------------------------------------
-    uint32_t cand = 0, pay[16];
-    {
-        const uint32_t n2 = ncls * ncls, n4 = n2 * n2;
-        uint32_t q[16 + kGramMaxDepth - 1];
-        if (D >= 3) {
-#pragma unroll
-            for (int t = 0; t < 16 + D - 2; ++t) q[t] = cls[t] + ncls * cls[t + 1];
-        }
-#pragma unroll
-        for (int j = 15; j >= 0; --j) {
-            uint32_t idx;
-            if (D == 1) idx = cls[j];
-            else if (D == 2) idx = cls[j] + ncls * cls[j + 1];
-            else if (D == 3) idx = q[j] + n2 * cls[j + 2];
-            else if (D == 4) idx = q[j] + n2 * q[j + 2];
-            else if (D == 5) idx = q[j] + n2 * q[j + 2] + n4 * cls[j + 4];
-            else idx = q[j] + n2 * q[j + 2] + n4 * q[j + 4];
-            if (SMALL) {
-                const uint2 h = *reinterpret_cast<const uint2 *>(T.hit_b + (idx * 256u + 2u * T.lane4));
-                cand = cand * 2u + h.x;
-                pay[j] = h.y;
-            } else {
-                cand = __funnelshift_l(T.bits[idx >> 5] << (idx & 31u), cand, 1);
-                pay[j] = idx;
-            }
-        }
-    }
-    {
-        const uint32_t my0 = lane * 16;
-        if (first_valid > my0) cand &= (first_valid - my0 >= 16) ? 0u : (0xFFFFu << (first_valid - my0));
-    }
-    // ---- D ---------------------------------------------------------------------------------------------------------------
+    uint32_t pay[16];
+    const uint32_t cand = gram_candidates<D, SMALL>(a, T, x, x_next, lane, first_valid, pay);
     Front f;
     f.lens = 0x1111111111111111ull * (unsigned long long)(a.uniform_len - 1);
     resolve_chain(f, cand, lane, carry_e);
-    // ---- E ---------------------------------------------------------------------------------------------------------------
-    const uint32_t h0 = *reinterpret_cast<const uint32_t *>(sb + 20);       // the next lane's first word (lane 31: the halo)
-    long long acc[4] = {0, 0, 0, 0};
-    // acc += (real ? delta : 0) * 2^(8 * byte offset): one SEL and one IMAD.WIDE with accumulate (FMA pipe).  The multipliers
-    // come from the kernel arguments: a literal power of two is strength-reduced to LEA + LEA.HI.X on the ALU pipe.
-#define TRRE_EMIT(J)                                                                                              \
-    {                                                                                                             \
-        const bool on = (f.real & (1u << (J))) != 0;                                                              \
-        int d = 0;                                                                                                \
-        if (SMALL) d = on ? (int)pay[J] : 0;                                                                      \
-        else if (on) d = (int)T.gout[pay[J]];                                                                     \
-        acc[(J) >> 2] += (long long)d * (long long)a.mul[(J) & 3];                                                \
+    // ---- E in registers --------------------------------------------------------------------------------------------------
+    const uint32_t M = a.len_mask;                                  // 0xFF in the low L bytes
+    uint32_t o[5] = {x.x, x.y, x.z, x.w, 0u};
+    uint32_t sm = 0;                                                // which bytes of o[4] (positions 16..19) are written
+#pragma unroll
+    for (int j = 0; j < 16; ++j) {
+        if (f.real & (1u << j)) {
+            const uint32_t g = SMALL ? pay[j] : T.gout[pay[j]];     // SMALL: the bytes came with the hit word
+            const int r = 8 * (j & 3), w = j >> 2;                  // compile-time after unrolling
+            o[w] = (o[w] & ~(M << r)) | ((g << r) & (M << r));
+            if (r) {
+                const uint32_t m2 = M >> (32 - r);
+                o[w + 1] = (o[w + 1] & ~m2) | ((g >> (32 - r)) & m2);
+                if (w == 3) sm |= m2;
+            }
+        }
     }
-    TRRE_EMIT(0) TRRE_EMIT(1) TRRE_EMIT(2) TRRE_EMIT(3) TRRE_EMIT(4) TRRE_EMIT(5) TRRE_EMIT(6) TRRE_EMIT(7)
-    TRRE_EMIT(8) TRRE_EMIT(9) TRRE_EMIT(10) TRRE_EMIT(11) TRRE_EMIT(12) TRRE_EMIT(13) TRRE_EMIT(14) TRRE_EMIT(15)
-#undef TRRE_EMIT
-    unsigned long long p;
-    uint32_t o0, o1, o2, o3, o4;
-    p = ((unsigned long long)x.y << 32 | x.x) + (unsigned long long)acc[0]; o0 = (uint32_t)p; o1 = (uint32_t)(p >> 32);
-    p = ((unsigned long long)x.z << 32 | o1) + (unsigned long long)acc[1];  o1 = (uint32_t)p; o2 = (uint32_t)(p >> 32);
-    p = ((unsigned long long)x.w << 32 | o2) + (unsigned long long)acc[2];  o2 = (uint32_t)p; o3 = (uint32_t)(p >> 32);
-    p = ((unsigned long long)h0 << 32 | o3) + (unsigned long long)acc[3];   o3 = (uint32_t)p; o4 = (uint32_t)(p >> 32);
-    const int32_t sp = (int32_t)(o4 - h0);                           // what this lane's last matches change in the next word
-    int32_t sp_in = __shfl_up_sync(0xFFFFFFFFu, sp, 1);
-    if (lane == 0) sp_in = carry_sp;
-    o0 += (uint32_t)sp_in;                                            // fields are disjoint: no carry leaves the word
+    uint32_t sp_in = __shfl_up_sync(0xFFFFFFFFu, o[4], 1), sm_in = __shfl_up_sync(0xFFFFFFFFu, sm, 1);
+    if (lane == 0) { sp_in = carry_sp; sm_in = carry_sm; }
+    o[0] = (o[0] & ~sm_in) | (sp_in & sm_in);
     if (STORE) {
         const size_t my = base + (size_t)lane * 16;
         if (full || my + 16 <= a.n) {
-            *reinterpret_cast<uint4 *>(a.out + my) = make_uint4(o0, o1, o2, o3);
+            *reinterpret_cast<uint4 *>(a.out + my) = make_uint4(o[0], o[1], o[2], o[3]);
         } else if (my < a.n) {
-            const uint32_t w[4] = {o0, o1, o2, o3};
-            for (int k = 0; k < 16 && my + k < a.n; ++k) a.out[my + k] = (uint8_t)(w[k >> 2] >> ((k & 3) * 8));
+            for (int k = 0; k < 16 && my + k < a.n; ++k) a.out[my + k] = (uint8_t)(o[k >> 2] >> ((k & 3) * 8));
         }
     }
     carry_e = __shfl_sync(0xFFFFFFFFu, f.e_out, 31);
-    carry_sp = __shfl_sync(0xFFFFFFFFu, sp, 31);
-    __syncwarp();                                                     // the staging rows are free again
+    carry_sp = __shfl_sync(0xFFFFFFFFu, o[4], 31);
+    carry_sm = __shfl_sync(0xFFFFFFFFu, sm, 31);
 }
 
 // The general form: tile staged in shared memory, real matches write their span there (any length, pool strings).
@@ -307,12 +238,9 @@ __device__ __forceinline__ void gram_tile(const GramArgs &a, const GramTables &T
             real &= real - 1;
             const uint32_t p = lane * 16 + j;
             const uint32_t g = T.gout[gram_index_at<D>(T, s_in, p, ncls)];
-            if (a.gflags & GRAM_DIRECT) {                          // delta form: printed = consumed + g as integers
+            if (a.gflags & GRAM_DIRECT) {
                 const uint32_t m = a.uniform_len;
-                uint32_t f_old = 0;
-                for (uint32_t k = 0; k < m; ++k) f_old |= (uint32_t)s_in[p + k] << (8 * k);
-                const uint32_t f_new = f_old + g;
-                for (uint32_t k = 0; k < m; ++k) s_out[p + k] = (uint8_t)(f_new >> (8 * k));
+                for (uint32_t k = 0; k < m; ++k) s_out[p + k] = (uint8_t)(g >> (8 * k));
             } else {
                 const uint8_t *src = T.pool + (g & 0xFFFFFu);
                 const uint32_t m = (g >> 28) + 1;                      // length preserving: printed == consumed
@@ -344,23 +272,18 @@ __device__ __forceinline__ uint8_t *gram_setup(const GramArgs &a, uint8_t *smem,
     uint32_t *cls_s = reinterpret_cast<uint32_t *>(cur); cur += 256 * 32 * 4;
     uint32_t *bits_s = reinterpret_cast<uint32_t *>(cur);
     const uint32_t words = (a.entries + 31) / 32;
-    cur += SMALL ? (size_t)a.entries * (REG ? 256 : 128) : (size_t)((words + 3) & ~3u) * 4;
+    cur += SMALL ? (size_t)a.entries * 128 : (size_t)((words + 3) & ~3u) * 4;
     uint32_t *gout_s = nullptr;
     if (a.gout_in_smem) { gout_s = reinterpret_cast<uint32_t *>(cur); cur += (size_t)((a.entries + 3) & ~3u) * 4; }
     uint8_t *pool_s = nullptr;
     if (a.pool_in_smem) { pool_s = cur; cur += (a.gpool_bytes + 15) & ~15u; }
 
     for (uint32_t k = threadIdx.x; k < 256u * 32u; k += blockDim.x) cls_s[k] = __ldg(a.classmap + (k >> 5));
-    if (SMALL && REG) {                                           // {hit flag, delta} per combination and lane
+    if (SMALL) {
         for (uint32_t k = threadIdx.x; k < a.entries * 32u; k += blockDim.x) {
             const uint32_t e = k >> 5;
-            bits_s[2 * k] = (__ldg(a.gbits + (e >> 5)) >> (e & 31u)) & 1u;
-            bits_s[2 * k + 1] = __ldg(a.gout + e);
-        }
-    } else if (SMALL) {
-        for (uint32_t k = threadIdx.x; k < a.entries * 32u; k += blockDim.x) {
-            const uint32_t e = k >> 5;
-            bits_s[k] = ((__ldg(a.gbits + (e >> 5)) >> (e & 31u)) & 1u) << 31;
+            // REG: the (<= 3) printed bytes ride in the hit word
+            bits_s[k] = (((__ldg(a.gbits + (e >> 5)) >> (e & 31u)) & 1u) << 31) | (REG ? (__ldg(a.gout + e) & 0x00FFFFFFu) : 0u);
         }
     } else {
         for (uint32_t k = threadIdx.x; k < words; k += blockDim.x) bits_s[k] = __brev(__ldg(a.gbits + k));
@@ -433,7 +356,7 @@ k_gram(GramArgs a) {
     const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     GramTables T;
     uint8_t *cur = gram_setup<SMALL, REG>(a, smem, lane, T);
-    uint8_t *warp_base = cur + warp * (REG ? kGramStageBytes : kGramWarpSmem);
+    uint8_t *warp_base = cur + (REG ? 0 : warp * kGramWarpSmem);     // REG: no staging area at all
 
     uint8_t *s_in = warp_base, *s_out = warp_base + 544;
 
@@ -445,8 +368,7 @@ k_gram(GramArgs a) {
     if (t1 > n_tiles) t1 = n_tiles;
     uint32_t status = 0, nul_acc = 0;
     if (t0 < t1) {
-        uint32_t carry_e = 0;
-        int32_t carry_sp = 0;
+        uint32_t carry_e = 0, carry_sp = 0, carry_sm = 0;
         uint4 carry_halo = make_uint4(0, 0, 0, 0);
         // ---- warm-up: the chain state at t0 is only known from the last '\n' before it (as k_match) ------------------
         size_t tw = t0;
@@ -482,8 +404,8 @@ k_gram(GramArgs a) {
             const bool full = base + 2 * (size_t)kTile <= n;
             const uint4 x_next = full ? ldg_vec(a.in + base + kTile + lane * 16) : load_padded(a.in, base + kTile + lane * 16, n);
             if (REG) {
-                if (t < t0) gram_tile_delta<D, SMALL, false>(a, T, warp_base, base, full, x, x_next, lane, first_valid, carry_e, carry_sp, nul_acc);
-                else        gram_tile_delta<D, SMALL, true>(a, T, warp_base, base, full, x, x_next, lane, first_valid, carry_e, carry_sp, nul_acc);
+                if (t < t0) gram_tile_reg<D, SMALL, false>(a, T, base, full, x, x_next, lane, first_valid, carry_e, carry_sp, carry_sm, nul_acc);
+                else        gram_tile_reg<D, SMALL, true>(a, T, base, full, x, x_next, lane, first_valid, carry_e, carry_sp, carry_sm, nul_acc);
             } else {
                 if (t < t0) gram_tile<D, SMALL, false>(a, T, s_in, s_out, base, full, x, x_next, lane, first_valid, carry_e, carry_halo, nul_acc);
                 else        gram_tile<D, SMALL, true>(a, T, s_in, s_out, base, full, x, x_next, lane, first_valid, carry_e, carry_halo, nul_acc);
