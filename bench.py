@@ -527,13 +527,26 @@ def measure(ctx, name, nbytes, steps, warmup, collectives=False, tile_rank=None,
     return res
 
 
+def kernel_label(T, info):
+    if info["exec_kind"] == T.EXEC_BACKTRACK:
+        return "k_lines<dfs> count + k_scan_groups + k_lines<dfs> write"
+    if info["exec_kind"] == T.EXEC_LAZY:
+        return "k_lines<lazy> count (repeated while rows are missing) + k_scan_groups + k_lines<lazy> write"
+    if info["exec_kind"] == T.EXEC_BYTEMAP:
+        return "k_bytemap_swar" if os.environ.get("TRRE_NO_SWAR") is None else "k_bytemap"
+    label = KERNELS[info["fast_path"]]
+    if info.get("gram_tables") and os.environ.get("TRRE_NO_GRAM") is None:
+        label = label.replace("k_match", "k_gram_var") if info["fast_path"] == 4 else label.replace("k_match", "k_gram")
+    return label
+
+
 def summarize(ctx, name, r, total_bytes):
     peak, _ = measured_hbm_peak()
     secs = r["ms_per_step"] * 1e-3
     algo = float(r["n"] + r["out_n"])
     return {"workload": name, "pattern": short_pattern(WORKLOADS[name][0]), "bytes_total": total_bytes, "bytes_per_gpu": r["n"],
             "value": total_bytes / secs / 1e9, "unit": "GB/s", "ms_per_step": r["ms_per_step"],
-            "roofline_frac": algo / secs / 1e9 / peak, "exec": KERNELS[r["info"]["fast_path"]],
+            "roofline_frac": algo / secs / 1e9 / peak, "exec": kernel_label(ctx.T, r["info"]),
             "launches_per_step": r["launches_per_step"], "verified": r["verified"], "verified_how": r["verified_how"]}
 
 
@@ -793,9 +806,7 @@ def main():
             traffic_src = tj.get("source", "ncu --set full capture committed under profiles/ (not measured in this run)")
         except Exception:
             pass
-    kernel = KERNELS[info["fast_path"]] if info["exec_kind"] != T.EXEC_BACKTRACK else "k_lines<dfs> count + k_scan_groups + k_lines<dfs> write"
-    if info["exec_kind"] == T.EXEC_BYTEMAP:
-        kernel = "k_bytemap_swar" if os.environ.get("TRRE_NO_SWAR") is None else "k_bytemap"
+    kernel = kernel_label(T, info)
     line = {
         "metric": METRIC, "value": value, "unit": "GB/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,

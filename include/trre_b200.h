@@ -87,6 +87,8 @@ typedef struct trre_prog_info {
     uint32_t can_match_empty;    /* 1: an attempt can succeed without consuming                              */
     uint32_t table_bytes;        /* size of the device-resident tables                                       */
     uint32_t fast_path;          /* TRRE_FAST_*: which position-parallel kernel serves a regular buffer      */
+    uint32_t gram_tables;        /* 1: every attempt is tabulated by byte classes (k_gram / k_gram_var serve   */
+                                 /*    TRRE_FAST_MATCH / TRRE_FAST_MATCH_VAR instead of the walking k_match)   */
 } trre_prog_info;
 
 /* ---- host side: pattern -> program (no GPU needed) ------------------------------------------- */

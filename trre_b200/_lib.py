@@ -27,7 +27,7 @@ class TrreError(RuntimeError):
 class _Info(ctypes.Structure):
     _fields_ = [(n, ctypes.c_uint32) for n in (
         "abi_version", "flavor", "exec_kind", "nft_states", "dsa_states", "byte_classes",
-        "max_depth", "length_preserving", "can_match_empty", "table_bytes", "fast_path")]
+        "max_depth", "length_preserving", "can_match_empty", "table_bytes", "fast_path", "gram_tables")]
 
 
 _L = None

@@ -1050,6 +1050,7 @@ int trre_prog_get_info(const trre_prog *p, trre_prog_info *info) {
                       : (h.flags & PF_MATCHABLE_VAR)    ? TRRE_FAST_MATCH_VAR
                       : ((h.flags & PF_LENGTH_PRESERVING) && h.exec_kind == TRRE_EXEC_TABLE) ? TRRE_FAST_INPLACE
                                                         : TRRE_FAST_NONE;
+    info->gram_tables = (h.flags & PF_GRAM) ? 1 : 0;
     return TRRE_OK;
 }
 
