@@ -1,5 +1,5 @@
 # round 2, fifth GPU pass: delta-form k_gram
-TAG=${1:-r2f}
+TAG=${1:-r2g}
 mkdir -p gpurun_out
 timeout 1200 python -m pytest tests/test_gpu_parity.py tests/test_gpu_configs.py -x -q -m gpu --durations=5 -k "gram or dictionary or cfg1 or cfg3 or cfg5_dictionary_10k or config_patterns or irregular or random_patterns_on_inputs or nft_flavour" 2>&1 | tail -12
 B="--bytes 1073741824 --steps 10 --warmup 3 --no-cpu-baseline --e2e-steps 0 --no-others"

@@ -312,7 +312,7 @@ int get_state(const trre_prog *cp, int device, DeviceState **out) {
         g.len_mask = h.gram_len >= 4 ? 0xFFFFFFFFu : ((1u << (8 * h.gram_len)) - 1u);
         d->gram_smem = 256 * 32 * 4 + (d->gram_small ? (size_t)h.gram_entries * 128 : (size_t)((words + 3) & ~3u) * 4) +
                        (g.gout_in_smem ? (size_t)((h.gram_entries + 3) & ~3u) * 4 : 0) +
-                       (g.pool_in_smem ? ((h.gpool_bytes + 15) & ~15u) : 0) + (reg ? 0 : (size_t)kGramWarps * kGramWarpSmem);
+                       (g.pool_in_smem ? ((h.gpool_bytes + 15) & ~15u) : 0) + (reg ? 8 * 256 * 2 : (size_t)kGramWarps * kGramWarpSmem);
         d->gram_fn = gram_kernel(h.gram_depth, d->gram_small, reg);
         if (d->gram_fn && d->gram_smem <= 220 * 1024) {
             CUDA_TRY(cudaFuncSetAttribute(d->gram_fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)d->gram_smem));

@@ -68,6 +68,8 @@ struct GramTables {
     const uint32_t *gout;        // shared or global
     const uint8_t *pool;         // shared or global
     uint32_t lane4;              // lane * 4
+    const uint16_t *chain_lut;   // register form: greedy selection of non-overlapping matches of the common length, 8
+                                 // candidate bits at a time: [carry-in << 8 | bits] -> real bits | carry-out << 8
 };
 
 // index of the D-gram starting at tile position p, from the staged bytes (any lane, any position)
@@ -143,6 +145,38 @@ __device__ __forceinline__ uint32_t gram_candidates(const GramArgs &a, const Gra
     return cand;
 }
 
+// resolve_chain for matches of ONE common length: the lane-local part - "take the lowest candidate, skip its length,
+// repeat" - is a function of (8 candidate bits, carry-in), tabulated once per CTA: two shared-memory lookups replace the
+// divergent loop over the lane's matches (2.8 iterations of 12 instructions on the BASELINE corpora).
+__device__ __forceinline__ void resolve_chain_lut(Front &f, uint32_t C, uint32_t lane, uint32_t carry_e, const uint16_t *lut) {
+    const uint32_t first = C ? (uint32_t)__ffs(C) - 1 : 16u;
+    uint32_t e_used = (lane == 0) ? carry_e : 0u, real = 0, e_out = 0;
+    auto chain = [&](uint32_t e) {
+        const uint32_t lo = lut[(e << 8) | (C & 0xFFu)];
+        const uint32_t hi = lut[(lo & 0xFF00u) | (C >> 8)];
+        real = (lo & 0xFFu) | ((hi & 0xFFu) << 8);
+        e_out = hi >> 8;
+    };
+    chain(e_used);
+    for (;;) {
+        uint32_t prev = __shfl_up_sync(0xFFFFFFFFu, e_out, 1);
+        if (lane == 0) prev = carry_e;
+        const bool differs = prev != e_used;
+        const bool need = differs && (prev > first || e_used > first);
+        if (differs) e_used = prev;
+        if (!__any_sync(0xFFFFFFFFu, need)) break;
+        if (need) chain(e_used);
+    }
+    f.real = real; f.e_in = e_used; f.e_out = e_out;
+}
+
+// (a & ~m) | (b & m)
+__device__ __forceinline__ uint32_t bitsel(uint32_t a, uint32_t b, uint32_t m) {
+    uint32_t d;
+    asm("lop3.b32 %0, %1, %2, %3, 0xD8;" : "=r"(d) : "r"(a), "r"(b), "r"(m));
+    return d;
+}
+
 // The tile in registers (GRAM_DIRECT programs: one common match length L <= 4, the printed bytes fit a word): no
 // shared-memory staging at all.  After the chain is resolved the real matches are merged into the lane's four output
 // words position by position (compile-time byte offsets, predicated on the `real` bit); the up to three bytes a match
@@ -155,8 +189,7 @@ __device__ __forceinline__ void gram_tile_reg(const GramArgs &a, const GramTable
     uint32_t pay[16];
     const uint32_t cand = gram_candidates<D, SMALL>(a, T, x, x_next, lane, first_valid, pay);
     Front f;
-    f.lens = 0x1111111111111111ull * (unsigned long long)(a.uniform_len - 1);
-    resolve_chain(f, cand, lane, carry_e);
+    resolve_chain_lut(f, cand, lane, carry_e, T.chain_lut);
     // ---- E in registers --------------------------------------------------------------------------------------------------
     const uint32_t M = a.len_mask;                                  // 0xFF in the low L bytes
     uint32_t o[5] = {x.x, x.y, x.z, x.w, 0u};
@@ -166,10 +199,12 @@ __device__ __forceinline__ void gram_tile_reg(const GramArgs &a, const GramTable
         if (f.real & (1u << j)) {
             const uint32_t g = SMALL ? pay[j] : T.gout[pay[j]];     // SMALL: the bytes came with the hit word
             const int r = 8 * (j & 3), w = j >> 2;                  // compile-time after unrolling
-            o[w] = (o[w] & ~(M << r)) | ((g << r) & (M << r));
+            // field insert = one LOP3 per word touched (spelled in PTX: left to itself the compiler masks g first and
+            // spends two more ALU instructions per match position)
+            o[w] = bitsel(o[w], g << r, M << r);
             if (r) {
                 const uint32_t m2 = M >> (32 - r);
-                o[w + 1] = (o[w + 1] & ~m2) | ((g >> (32 - r)) & m2);
+                o[w + 1] = bitsel(o[w + 1], g >> (32 - r), m2);
                 if (w == 3) sm |= m2;
             }
         }
@@ -292,6 +327,19 @@ __device__ __forceinline__ uint8_t *gram_setup(const GramArgs &a, uint8_t *smem,
         for (uint32_t k = threadIdx.x; k < a.entries; k += blockDim.x) gout_s[k] = __ldg(a.gout + k);
     if (pool_s)
         for (uint32_t k = threadIdx.x; k < a.gpool_bytes; k += blockDim.x) pool_s[k] = __ldg(a.gpool + k);
+    uint16_t *lut_s = reinterpret_cast<uint16_t *>(cur);
+    if (REG) {
+        cur += 8 * 256 * sizeof(uint16_t);
+        const uint32_t L = a.uniform_len;                          // 1..4; carry-in < L (8 rows cover the index range)
+        for (uint32_t k = threadIdx.x; k < 8u * 256u; k += blockDim.x) {
+            const uint32_t bits = k & 0xFFu;
+            uint32_t pos = k >> 8, r = 0;
+            while (pos < 8) {
+                if ((bits >> pos) & 1u) { r |= 1u << pos; pos += L; } else ++pos;
+            }
+            lut_s[k] = (uint16_t)(r | ((pos - 8) << 8));
+        }
+    }
     __syncthreads();
 
     T.cls_b = reinterpret_cast<const uint8_t *>(cls_s);
@@ -300,6 +348,7 @@ __device__ __forceinline__ uint8_t *gram_setup(const GramArgs &a, uint8_t *smem,
     T.gout = gout_s ? gout_s : a.gout;
     T.pool = pool_s ? pool_s : a.gpool;
     T.lane4 = lane * 4;
+    T.chain_lut = lut_s;
     return cur;
 }
 
