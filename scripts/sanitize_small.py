@@ -12,8 +12,14 @@ def text(n, alphabet=b"abcd cat dog", hi=90):
         out += bytes(rng.choice(alphabet) for _ in range(rng.randint(0, hi))) + b"\n"
     return bytes(out[:n - 1]) + b"\n"
 
-cases = [("[a:A-z:Z]", 1), ("(cat:dog|dog:cat)", 0), ("aba:xyz", 0), ("a:", 0), ("a:xyz", 1), ("cat:mouse|dog:d", 0),
-         ("(cat):", 1), ("a+:x", 0), (":=", 0), ("(a:b)+", 0), ("(a:x)*b|a", 0), ("abcabcabcabcabca:ABCABCABCABCABCA|bc:XY", 0)]
+# every kernel family: k_bytemap_swar, k_bytemap (pair table), k_gram small/REG, k_gram non-uniform (staged), k_gram with the
+# bitmap (many classes), k_bmv, k_gram_var, k_match (deep / cyclic, in place and count/write), k_lines_s, k_lines<inplace>,
+# the DFS and the lazy-table executors
+words = ["".join(chr(97 + (k * 7 + j * 3) % 26) for j in range(4)) + "q"[:k % 2] for k in range(40)]
+cases = [("[a:A-z:Z]", 1), ("a:b|c:d|e:f|g:h|i:j|k:l", 0), ("(cat:dog|dog:cat)", 0), ("aba:xyz", 0), ("ab:XY|abc:XYZ|a:Z", 0),
+         ("|".join("%s:%s" % (w[:4], w[:4].upper()) for w in words), 1), ("a:", 0), ("a:xyz", 1), ("cat:mouse|dog:d", 0),
+         ("(cat):", 1), ("a+:x", 0), ("[0-9a]+:#", 0), (":=", 0), ("(a:b)+", 0), ("(a:b)*", 0), ("(a:x)*b|a", 0),
+         ("abcabcabcabcabca:ABCABCABCABCABCA|bc:XY", 0), ("(a|b)*a(a|b){15}", 1)]
 for expr, flavor in cases:
     prog = T.compile(expr, flavor)
     for n in (1, 17, 511, 513, 4097, 70001, 300007):
