@@ -1,17 +1,18 @@
-# Round-end evidence: full GPU test-suite, smoke, official bench line (both arms), ncu launch list + full capture.
-TAG=${1:-r1_final}
+# Round-end evidence: full GPU test-suite, smoke, official bench line (both arms), ncu launch list.
+TAG=${1:-r2_final}
 mkdir -p gpurun_out
-python -m pytest tests -q -m gpu 2>&1 | tail -3
+timeout 1500 python -m pytest tests -q -m gpu --durations=8 2>&1 | tail -14
 python __graft_entry__.py smoke 2>&1 | tail -1
-python bench.py --impl reference --steps 3 --warmup 1 > gpurun_out/bench_ref_$TAG.json 2>/dev/null
-python bench.py --steps 20 --warmup 3 > gpurun_out/bench_$TAG.json 2> gpurun_out/bench_$TAG.err; cat gpurun_out/bench_$TAG.json | cut -c1-300
-ncu --metrics gpu__time_duration.sum --clock-control none -c 80 --csv --log-file gpurun_out/launches_$TAG.csv \
-    python bench.py --steps 5 --warmup 3 --no-cpu-baseline --e2e-steps 0 > /dev/null 2>&1
-ncu --set full --clock-control none --import-source on -k regex:k_bytemap -s 3 -c 1 -o gpurun_out/prof_$TAG -f \
-    python bench.py --steps 2 --warmup 3 --no-cpu-baseline --e2e-steps 0 > /dev/null 2>&1
-for w in cfg1 cfg3 cfg5 del sub num cfg4; do
-  python bench.py --workload $w --bytes 1073741824 --steps 5 --warmup 3 --no-cpu-baseline --e2e-steps 1 2>/dev/null | tail -1 > gpurun_out/bench_${w}_$TAG.json
-  python -c "
-import json,sys
-d=json.load(open('gpurun_out/bench_${w}_$TAG.json')); print('$w', round(d['value'],1),'GB/s', round(d['ms_per_step'],3),'ms frac',round(d['roofline']['frac'],3), d['config']['exec'], 'verified',d['verified'],'e2e',round(d['e2e']['value'],1))"
-done
+python bench.py --impl reference --steps 3 --warmup 1 > gpurun_out/bench_ref_$TAG.json 2>/dev/null; cut -c1-200 gpurun_out/bench_ref_$TAG.json
+python bench.py --steps 50 --warmup 3 > gpurun_out/bench_$TAG.json 2> gpurun_out/bench_$TAG.err; tail -2 gpurun_out/bench_$TAG.err
+python - <<PY
+import json
+d=json.loads(open('gpurun_out/bench_$TAG.json').read().strip().splitlines()[-1])
+print('value',round(d['value'],1),'ms',round(d['ms_per_step'],4),'frac',round(d['roofline']['frac'],4),'verified',d['verified'], 'clocks', d['clocks'])
+print('e2e', {k:v for k,v in d['e2e'].items() if k!='pcie'}); print('pcie', d['e2e'].get('pcie'))
+print('cli', d.get('cli_e2e')); print('cpu', d.get('cpu_baseline'))
+for k,v in (d.get('others') or {}).items(): print(k, {a:(round(b,4) if isinstance(b,float) else b) for a,b in v.items() if a not in ('pattern','verified_how')})
+PY
+ncu --metrics gpu__time_duration.sum --clock-control none -c 120 --csv --log-file gpurun_out/launches_$TAG.csv python bench.py --steps 5 --warmup 3 --no-cpu-baseline --e2e-steps 0 --no-others > /dev/null 2>&1
+for w in num sub del; do python bench.py --workload $w --steps 5 --warmup 3 --no-cpu-baseline --e2e-steps 1 2>/dev/null | tail -1 > gpurun_out/bench_${w}_$TAG.json; python -c "
+import json,sys; d=json.loads(open('gpurun_out/bench_${w}_$TAG.json').read()); print('$w', round(d['value'],1), round(d['roofline']['frac'],4), d['config_detail']['exec'], d['verified'], 'e2e', round(d['e2e']['value'],1))"; done

@@ -12,7 +12,8 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 
 
 def lib_path():
-    return os.path.join(_HERE, "lib", "libtrre_b200.so")
+    # TRRE_B200_LIB: an alternative build of the same library (experiments with compile-time knobs)
+    return os.environ.get("TRRE_B200_LIB") or os.path.join(_HERE, "lib", "libtrre_b200.so")
 
 
 class TrreError(RuntimeError):

@@ -34,7 +34,10 @@ void set_err(char *err, size_t cap, const std::string &s) {
     }
 }
 
-constexpr int kSlots = 3;                 // pipelined host path: chunks in flight
+#ifndef TRRE_SLOTS
+#define TRRE_SLOTS 3
+#endif
+constexpr int kSlots = TRRE_SLOTS;        // pipelined host path: chunks in flight
 
 // where a count/scan/write launch keeps its sums and reports: the per-device workspace, or one pipeline slot's
 struct Ws {
@@ -79,12 +82,12 @@ struct DeviceState {
     const uint8_t *pend_in = nullptr; uint8_t *pend_out = nullptr; size_t pend_n = 0, pend_cap = 0;
     // host-buffer path: cached device buffers
     uint8_t *buf_in = nullptr, *buf_out = nullptr; size_t cap_in = 0, cap_out = 0;
-    uint8_t *slot_in[kSlots] = {nullptr, nullptr, nullptr}, *slot_out[kSlots] = {nullptr, nullptr, nullptr};
-    cudaStream_t slot_stream[kSlots] = {nullptr, nullptr, nullptr};
+    uint8_t *slot_in[kSlots] = {}, *slot_out[kSlots] = {};
+    cudaStream_t slot_stream[kSlots] = {};
     size_t slot_cap = 0, slot_out_cap = 0;
-    unsigned long long *slot_gsum[kSlots] = {nullptr, nullptr, nullptr};   // per-slot span sums (k_bmv / k_match var)
+    unsigned long long *slot_gsum[kSlots] = {};   // per-slot span sums (k_bmv / k_match var)
     unsigned long long *d_slot_total = nullptr, *h_slot_total = nullptr;     // [kSlots]
-    cudaEvent_t slot_done[kSlots] = {nullptr, nullptr, nullptr};
+    cudaEvent_t slot_done[kSlots] = {};
     MatchPlan mp, mpv;             // k_match launch plans: length preserving / variable length
     bool staged_attr = false;
     GramArgs gramv{};              // k_gram_var: the same tables for programs whose matches change the length
@@ -807,6 +810,27 @@ int ensure_slots(DeviceState *d, size_t chunk, size_t out_cap) {
     return TRRE_OK;
 }
 
+// Pinned-host copies reach the full PCIe rate only from / to 256-byte aligned HOST addresses (measured with bare chunked
+// copies, scripts/e2e_probe2.py: 48.2 GB/s aligned, 42.8 GB/s at any other offset - exactly what the pipeline lost; the
+// device-side alignment does not matter).  Chunks start where lines start, so every copy is split into a head of < 256
+// bytes and an aligned bulk.
+cudaError_t copy_h2d(uint8_t *d_dst, const uint8_t *h_src, size_t n, cudaStream_t st) {
+    size_t head = (256 - (reinterpret_cast<uintptr_t>(h_src) & 255)) & 255;
+    if (head > n) head = n;
+    cudaError_t e = cudaSuccess;
+    if (n > head) e = cudaMemcpyAsync(d_dst + head, h_src + head, n - head, cudaMemcpyHostToDevice, st);
+    if (e == cudaSuccess && head) e = cudaMemcpyAsync(d_dst, h_src, head, cudaMemcpyHostToDevice, st);
+    return e;
+}
+cudaError_t copy_d2h(uint8_t *h_dst, const uint8_t *d_src, size_t n, cudaStream_t st) {
+    size_t head = (256 - (reinterpret_cast<uintptr_t>(h_dst) & 255)) & 255;
+    if (head > n) head = n;
+    cudaError_t e = cudaSuccess;
+    if (n > head) e = cudaMemcpyAsync(h_dst + head, d_src + head, n - head, cudaMemcpyDeviceToHost, st);
+    if (e == cudaSuccess && head) e = cudaMemcpyAsync(h_dst, d_src, head, cudaMemcpyDeviceToHost, st);
+    return e;
+}
+
 size_t host_chunk_bytes() {
     size_t chunk = 32u << 20;
     if (const char *e = std::getenv("TRRE_CHUNK_MB")) { long v = std::atol(e); if (v >= 1 && v <= 1024) chunk = (size_t)v << 20; }
@@ -843,7 +867,7 @@ int pipelined_var(const trre_prog *p, DeviceState *d, const uint8_t *in, size_t 
         CUDA_TRY(cudaEventSynchronize(d->slot_done[slot]));
         const size_t total = (size_t)d->h_slot_total[slot];
         if (d->h_status[1 + slot] || total > d->slot_out_cap || host_off + total > out_cap) { give_up = true; return TRRE_OK; }
-        CUDA_TRY(cudaMemcpyAsync(out + host_off, d->slot_out[slot], total, cudaMemcpyDeviceToHost, d->slot_stream[slot]));
+        CUDA_TRY(copy_d2h(out + host_off, d->slot_out[slot], total, d->slot_stream[slot]));
         host_off += total;
         return TRRE_OK;
     };
@@ -851,7 +875,7 @@ int pipelined_var(const trre_prog *p, DeviceState *d, const uint8_t *in, size_t 
         const int slot = (int)(k % kSlots);
         cudaStream_t st = d->slot_stream[slot];
         Ws ws{d->slot_gsum[slot], d->d_slot_total + slot, d->d_status + 1 + slot};
-        CUDA_TRY(cudaMemcpyAsync(d->slot_in[slot], in + pieces[k].pos, pieces[k].len, cudaMemcpyHostToDevice, st));
+        CUDA_TRY(copy_h2d(d->slot_in[slot], in + pieces[k].pos, pieces[k].len, st));
         rc = bmv ? launch_bmv(p, d, d->slot_in[slot], pieces[k].len, d->slot_out[slot], d->slot_out_cap, st, PH_ALL, launches, &ws)
                  : launch_mv(p, d, d->slot_in[slot], pieces[k].len, d->slot_out[slot], d->slot_out_cap, st, PH_ALL, launches, &ws);
         if (rc != TRRE_OK) return rc;
@@ -891,10 +915,10 @@ int pipelined_lp(const trre_prog *p, DeviceState *d, const uint8_t *in, size_t n
         }
         const int slot = k % kSlots;
         cudaStream_t st = d->slot_stream[slot];               // stream order = reuse order of the slot
-        CUDA_TRY(cudaMemcpyAsync(d->slot_in[slot], in + pos, end - pos, cudaMemcpyHostToDevice, st));
+        CUDA_TRY(copy_h2d(d->slot_in[slot], in + pos, end - pos, st));
         rc = launch_fast(p, d, d->slot_in[slot], end - pos, d->slot_out[slot], d->d_status + 1 + slot, st);
         if (rc != TRRE_OK) return rc;
-        CUDA_TRY(cudaMemcpyAsync(out + pos, d->slot_out[slot], end - pos, cudaMemcpyDeviceToHost, st));
+        CUDA_TRY(copy_d2h(out + pos, d->slot_out[slot], end - pos, st));
         *launches += 1;
         pos = end;
         ++k;
@@ -1126,7 +1150,7 @@ int trre_scan_into(const trre_prog *p, int device, const uint8_t *in, size_t n, 
     }
     rc = ensure_host_path_buffers(d, n, 0);
     if (rc != TRRE_OK) return rc;
-    CUDA_TRY(cudaMemcpyAsync(d->buf_in, in, n, cudaMemcpyHostToDevice, st));
+    CUDA_TRY(copy_h2d(d->buf_in, in, n, st));
     size_t total = 0;
     rc = enqueue_scan(p, d, d->buf_in, n, nullptr, 0, st, true);      // count + scan: exact output size
     if (rc != TRRE_OK) return rc;
@@ -1152,7 +1176,7 @@ int trre_scan_into(const trre_prog *p, int device, const uint8_t *in, size_t n, 
         d->launches = launches + wl;
         if (rc != TRRE_OK) return rc;
     }
-    CUDA_TRY(cudaMemcpyAsync(out, d->buf_out, total, cudaMemcpyDeviceToHost, st));
+    CUDA_TRY(copy_d2h(out, d->buf_out, total, st));
     CUDA_TRY(cudaStreamSynchronize(st));
     return TRRE_OK;
 }
