@@ -1129,7 +1129,25 @@ int trre_scan_into(const trre_prog *p, int device, const uint8_t *in, size_t n, 
     int rc = get_state(p, device, &d);
     if (rc != TRRE_OK) return rc;
     d->launches = 0;
-    if (n == 0) return TRRE_OK;
+    // A buffer whose last record has no '\n' (a file without a final newline) is irregular only in that record - getline's
+    // last record loses its last byte (trre_nft.c:776-777).  The position-parallel kernels take everything up to the last
+    // '\n'; only the tail goes to the per-line kernels, instead of the whole buffer.
+    if (in[n - 1] != '\n' && p->hdr.exec_kind != TRRE_EXEC_BACKTRACK && p->hdr.exec_kind != TRRE_EXEC_LAZY) {
+        if (const void *nl = memrchr(in, '\n', n)) {
+            const size_t cut = (size_t)(static_cast<const uint8_t *>(nl) - in) + 1;
+            size_t n1 = 0, n2 = 0;
+            int rc1 = trre_scan_into(p, device, in, cut, out, out_cap, &n1);
+            if (rc1 != TRRE_OK && rc1 != TRRE_E_NOSPACE) return rc1;
+            const int l1 = d->launches;
+            const bool room = rc1 == TRRE_OK && out && out_cap >= n1;
+            int rc2 = trre_scan_into(p, device, in + cut, n - cut, room ? out + n1 : nullptr, room ? out_cap - n1 : 0, &n2);
+            d->launches += l1;
+            if (out_n) *out_n = n1 + n2;
+            if (rc2 != TRRE_OK && rc2 != TRRE_E_NOSPACE) return rc2;
+            if (rc1 == TRRE_E_NOSPACE || rc2 == TRRE_E_NOSPACE) { g_last_error = "output buffer too small"; return TRRE_E_NOSPACE; }
+            return TRRE_OK;
+        }
+    }
     cudaStream_t st = nullptr;
     // length-preserving program and room for n bytes: chunked, copy/compute overlapped
     if (fast_capable(p->hdr) && out && out_cap >= n) {
