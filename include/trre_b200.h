@@ -15,7 +15,9 @@
  *   scan driver + infer_backtrack trre_nft.c:775-790, 593-657  trre_scan / trre_scan_device (NFT flavour)
  *   scan driver + infer_dft       trre_dft.c:1272-1286,
  *                                 1110-1196                    trre_scan / trre_scan_device (DFT flavour)
- *   match driver (-m, -a)         trre_nft.c:791-797           trre_match_host (host C++, not a GPU path)
+ *   -a in scan mode               trre_nft.c:635-648, 782-788  trre_prog_set_mode(p, 0, 1) + trre_scan*  (GPU, DFS executor)
+ *   match driver (-m, -ma)        trre_nft.c:635-642, 791-797  trre_prog_set_mode(p, 1, all) + trre_scan* (GPU, DFS executor)
+ *                                                              trre_match_host: the same on the host, kept as a cross-check
  *
  * Plain pointers and sizes only; no CUDA or torch types in any signature (a stream is passed as
  * `void *`, i.e. a cudaStream_t, 0 = default stream).  All scan entry points run on the GPU: there
@@ -35,7 +37,7 @@
 extern "C" {
 #endif
 
-#define TRRE_B200_ABI_VERSION 2
+#define TRRE_B200_ABI_VERSION 3
 
 /* which reference binary's semantics: `trre` (leftmost, first-by-priority, empty matches allowed)
  * or `trre_dft` (leftmost, shortest non-empty match). */
@@ -114,6 +116,19 @@ int  trre_lazy_build(trre_prog *p, const uint32_t *states, size_t n, uint32_t ex
 int  trre_lazy_view(const trre_prog *p, uint32_t *n_states, const uint64_t **rows, const uint64_t **sinfo,
                     const uint8_t **pool, size_t *pool_bytes);
 
+/* The CLI's -m / -a flags (trre_nft.c:728-741): which output every trre_scan* call of this program produces from now on.
+ *   match=0, all=0  scan mode (the default)
+ *   match=0, all=1  `trre -a`: at every position ALL accepting paths print, in DFS priority order, then the raw byte is
+ *                   copied (an attempt never "wins" with -a: trre_nft.c:646-648 falls through and returns -1)
+ *   match=1, all=0  `trre -m`: a record prints the output of its first accepting path over the WHOLE record + '\n',
+ *                   records that do not match print nothing (trre_nft.c:635-642, 792-796)
+ *   match=1, all=1  `trre -ma`: every accepting path
+ * These modes run the reference's priority DFS over the flat NFT on the GPU, one record per thread (k_lines with the DFS
+ * executor), whatever tables the program has.  DFT flavour: -m prints one bare newline per record (trre_dft.c:1287-1292);
+ * -a returns TRRE_E_UNSUPPORTED with the reference's text "Not supported yet" (trre_dft.c:1226).  The mode is not part
+ * of the blob: set it again on a program made by trre_prog_from_blob. */
+int  trre_prog_set_mode(trre_prog *p, int match, int all);
+
 /* 256-entry map for TRRE_EXEC_BYTEMAP programs (returns TRRE_E_ARG otherwise). */
 int  trre_prog_bytemap(const trre_prog *p, uint8_t lut[256]);
 
@@ -160,8 +175,8 @@ int  trre_shard_lines(const uint8_t *in, size_t n, int parts, size_t *cuts);
 
 /* ---- host-only helpers ------------------------------------------------------------------------ */
 
-/* Match mode (`-m`, with all!=0 `-ma`; with scan!=0 it is `-a` in scan mode): host C++ over the flat
- * NFT, used by the CLI; not a GPU path. */
+/* Match mode (`-m`, with all!=0 `-ma`; with scan!=0 it is `-a` in scan mode) on the HOST: C++ over the flat NFT.
+ * The CLI runs these flags on the GPU (trre_prog_set_mode); this stays as the host-side cross-check of that path. */
 int  trre_match_host(const trre_prog *p, int scan, int all,
                      const uint8_t *in, size_t n, uint8_t **out, size_t *out_n,
                      char *err, size_t errcap);

@@ -81,6 +81,38 @@ def main():
                    "vectors": vec}, f, separators=(",", ":"))
     print("wrote", out, len(vec), "vectors,", os.path.getsize(out), "bytes")
 
+    # ---- the other modes of the command line: -m, -ma, -a (trre_nft.c:635-648, 782-797; trre_dft.c:1287-1292) ----------
+    vec = []
+    modes = ((NFT, MATCH, False), (NFT, MATCH, True), (NFT, SCAN, True), (DFT, MATCH, False))
+    for mode, inp, tre, _ in KATS:
+        data = (inp + "\n").encode()
+        for fl, m, a in modes:
+            add(tre.encode(), data, fl, m, a, tag="test.sh " + mode)
+    for expr in (b"cat:dog", b"(cat:dog|dog:cat)", b"cat:x|cat:y|ca:z", b".*cat.*", b"[a-z ]*(cat:dog|dog:cat)[a-z ]*"):
+        for fl, m, a in modes:
+            add(expr, text[:1500], fl, m, a, tag="config text")
+            add(expr, text[:1499], fl, m, a, tag="config text, no final newline")
+    rng = random.Random(20260925)
+    n_rand = 0
+    while n_rand < 300:
+        pat = rand_expr(rng, 2).encode()
+        data = rand_input(rng, maxlen=12, final_newline=rng.random() < 0.85)
+        before = len(vec)
+        for fl, m, a in modes:
+            add(pat, data, fl, m, a, tag="random")
+        vec[before:] = [v for v in vec[before:] if len(v["out"]) < 20000]
+        n_rand += len(vec) - before
+    for data in (b"", b"\n", b"\n\n", b"a\0b\nab\n", b"\0\n", b"cat\ncat", b"a\n\0a\na"):
+        for expr in (b"cat:dog", b"a:", b":=", b".:x", b"a*", b"(a:x|a)*", b".*"):
+            for fl, m, a in modes:
+                add(expr, data, fl, m, a, tag="edge input")
+    vec = [v for v in vec if len(v["out"]) < 40000]             # -ma on long lines enumerates: keep the fixture small
+    out = os.path.join(HERE, "ref_mode_vectors.json")
+    with open(out, "w") as f:
+        json.dump({"generator": "tests/golden/make_golden.py", "reference": "c0stya/trre @ c474a68 (oracle/_ref)",
+                   "vectors": vec}, f, separators=(",", ":"))
+    print("wrote", out, len(vec), "vectors,", os.path.getsize(out), "bytes")
+
 
 if __name__ == "__main__":
     main()

@@ -69,11 +69,26 @@ def test_cli_prints_what_precedes_a_failing_block(monkeypatch):
     assert len(r.stdout) >= 1 << 20 and head.startswith(r.stdout)
 
 
-def test_cli_match_flags_stay_on_the_host():
+def test_cli_match_and_all_flags_run_on_the_gpu(monkeypatch):
+    """-m / -ma / -a (trre_nft.c:728-741, 635-648, 782-797): same argv as the reference, GPU DFS underneath, streamed."""
     r = subprocess.run([BIN[NFT], "-ma", "(.:x)*.*"], input=b"aaa\n", capture_output=True)
     assert r.stdout == b"xxx\nxxa\nxaa\naaa\n"
     r = subprocess.run([BIN[NFT], "-a", "a:x|a:y"], input=b"ab\n", capture_output=True)
     assert r.stdout == b"xyab\n"                                  # SURVEY s4.4: -a in scan mode
+    r = subprocess.run([BIN[DFT], "-a", "a:x"], input=b"ab\n", capture_output=True)
+    assert r.returncode == 1 and r.stderr == b"Not supported yet\n"
+    monkeypatch.setenv("TRRE_CLI_BLOCK_MB", "1")
+    big = bytes(T.synth_text(0x72726509, 3 << 20, ["cat", "dog", "catdog"], 0.25))
+    for flags, expr, flavor in ((["-m"], ".*cat.*", NFT), (["-a"], "(cat:dog|dog:cat|cat:CAT)", NFT), (["-m", "-a"], "[^c]*(c:C|c)*[^c]*", NFT),
+                                (["-m"], "cat:dog", DFT)):
+        if have_ref():
+            ref = subprocess.run([REF[flavor]] + flags + [expr], input=big, capture_output=True)
+            rc, want = ref.returncode, ref.stdout
+        else:
+            from oracle_util import MATCH, SCAN
+            rc, want, _ = oracle_run(expr.encode(), big, flavor=flavor, mode=MATCH if "-m" in flags else SCAN, all_="-a" in flags)
+        r = subprocess.run([BIN[flavor]] + flags + [expr], input=big, capture_output=True)
+        assert r.returncode == rc and r.stdout == want, (flags, expr, len(r.stdout), len(want), r.stderr[:200])
 
 
 def test_multi_gpu_scan_equals_single(monkeypatch):

@@ -405,3 +405,45 @@ def test_dfs_executor_has_the_reference_stack_capacity():
     with pytest.raises(T.TrreError) as ei:
         T.compile(expr, NFT).scan(data)
     assert ei.value.code == 5 and "stack max capacity reached" in ei.value.text
+
+
+@pytest.mark.parametrize("seed", range(4))
+def test_match_and_all_modes_on_the_gpu(seed):
+    """-m / -ma / -a (trre_nft.c:635-648, 782-797) through trre_prog_set_mode: GPU DFS vs the oracle on random
+    expressions and inputs; trre_dft -m prints a bare newline per record (trre_dft.c:1287-1292)."""
+    from oracle_util import MATCH, SCAN
+    rng = random.Random(7000 + seed)
+    ran = 0
+    for _ in range(50):
+        pat = rand_expr(rng, 2)
+        data = rand_input(rng, nlines=rng.randint(0, 40), maxlen=12, final_newline=rng.random() < 0.8)
+        for flavor, mode, all_ in ((NFT, SCAN, True), (NFT, MATCH, False), (NFT, MATCH, True), (DFT, MATCH, False)):
+            rc, want, err = oracle_run(pat if isinstance(pat, bytes) else pat.encode("latin1"), data, flavor=flavor, mode=mode, all_=all_)
+            if len(want) > (1 << 20):
+                continue
+            try:
+                prog = T.compile(pat, flavor).set_mode(match=mode == MATCH, all_=all_)
+            except T.TrreError:
+                continue
+            if rc != 0:
+                with pytest.raises(T.TrreError):
+                    prog.scan(data)
+                continue
+            got = prog.scan(data)
+            assert got == want, (pat, flavor, mode, all_, data[:80], got[:80], want[:80])
+            if flavor == NFT:
+                assert prog.match(data, all_=all_, scan=mode == SCAN) == want
+            ran += 1
+    assert ran > 60, ran
+
+
+def test_modes_on_config_text():
+    """-a in scan mode and -m on 1 MiB of the synthetic corpus: many records per kernel launch, chunk boundaries."""
+    from oracle_util import MATCH, SCAN
+    text = bytes(T.synth_text(0x72726503, 1 << 20, ["cat", "dog", "catdog", "dogcat", "ca", "do", "cot", "dig"], 0.25))
+    for expr, mode, all_ in (("(cat:dog|dog:cat)", SCAN, True), ("cat:x|cat:y|ca:z", SCAN, True), (".*cat.*", MATCH, False),
+                             ("(.:x|.)*", MATCH, False), ("[a-z ]*(cat:dog|dog:cat)[a-z ]*", MATCH, True)):
+        rc, want, _ = oracle_run(expr.encode(), text, flavor=NFT, mode=mode, all_=all_)
+        assert rc == 0
+        assert T.compile(expr, NFT).set_mode(match=mode == MATCH, all_=all_).scan(text) == want, expr
+    assert T.compile("cat:dog", DFT).set_mode(match=True).scan(text) == b"\n" * text.count(b"\n")

@@ -36,6 +36,24 @@ def test_golden_fixtures():
             assert err == v["err"], (v["expr"], err, v["err"])
 
 
+def test_golden_mode_fixtures():
+    """-m, -ma, scan-mode -a and `trre_dft -m` (stdout of the real binaries, tests/golden/ref_mode_vectors.json): the
+    oracle, and the product's host restatement of those modes (trre_match_host)."""
+    import trre_b200 as T
+    modes = load_golden("ref_mode_vectors.json")
+    assert len(modes) > 700
+    for v in modes:
+        rc, out, err = oracle_run(v["expr"], v["data"], flavor=v["flavor"], mode=v["mode"], all_=bool(v["all"]))
+        assert rc == v["rc"] and out == v["out"], (v["tag"], v["expr"], v["mode"], v["all"], v["data"], out, v["out"])
+        if v["rc"] == 0:
+            try:
+                prog = T.compile(v["expr"], v["flavor"])
+            except T.TrreError as e:
+                assert e.code == 2
+                continue
+            assert prog.match(v["data"], all_=bool(v["all"]), scan=v["mode"] == SCAN) == v["out"], (v["expr"], v["data"])
+
+
 @pytest.mark.skipif(not have_ref(), reason="oracle/_ref not built (needs /root/reference)")
 def test_probe_log_against_reference_binaries():
     for expr, data in PROBES:

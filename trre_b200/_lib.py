@@ -59,6 +59,8 @@ def _lib():
     L.trre_lazy_view.restype = ctypes.c_int
     L.trre_lazy_view.argtypes = [vp, ctypes.POINTER(ctypes.c_uint32), ctypes.POINTER(vp), ctypes.POINTER(vp),
                                  ctypes.POINTER(vp), ctypes.POINTER(sz)]
+    L.trre_prog_set_mode.restype = ctypes.c_int
+    L.trre_prog_set_mode.argtypes = [vp, ctypes.c_int, ctypes.c_int]
     L.trre_prog_bytemap.restype = ctypes.c_int
     L.trre_prog_bytemap.argtypes = [vp, ctypes.c_char_p]
     L.trre_scan.restype = ctypes.c_int
@@ -160,8 +162,15 @@ class Program:
             raise TrreError(rc, "not a lazily built program")
         return n.value, rows.value, sinfo.value, pool.value, pb.value
 
+    def set_mode(self, match=False, all_=False):
+        """The CLI's -m / -a: every later scan*() of this program runs that mode on the GPU (DFS executor)."""
+        rc = _lib().trre_prog_set_mode(self._h, int(match), int(all_))
+        if rc:
+            raise TrreError(rc, _last_error())
+        return self
+
     def match(self, data, all_=False, scan=False) -> bytes:
-        """`-m` / `-ma` (scan=False) or scan-mode `-a` (scan=True): host C++, not a GPU path."""
+        """`-m` / `-ma` (scan=False) or scan-mode `-a` (scan=True) on the HOST: cross-check of set_mode() + scan()."""
         addr, n, keep = _as_buffer(data)
         out, out_n = ctypes.c_void_p(), ctypes.c_size_t()
         err = ctypes.create_string_buffer(256)

@@ -8,7 +8,7 @@
 // C ABI (trre_scan_into: H2D, kernels and D2H pipelined inside), a writer thread writes the finished blocks to stdout
 // in order.  Memory is O(block), the first output appears after the first block, and input larger than RAM or an
 // endless pipe work.  Inputs that end inside the first block take the one-shot path (no pinned ring to set up).
-// -m / -a stay on the host (trre_match_host).
+// -m / -a run on the GPU as well (trre_prog_set_mode: the reference's DFS, one record per thread) and stream the same way.
 // GPU knobs come from the environment so the argv surface stays the reference's: TRRE_DEVICE (default 0),
 // TRRE_GPUS (default 1: number of devices, starting at TRRE_DEVICE, the lines of each block are sharded over),
 // TRRE_CLI_BLOCK_MB (default 64).
@@ -160,22 +160,9 @@ int main(int argc, char **argv) {
         if (!fp) { std::fprintf(stderr, "error: can not open file %s\n", argv[optind + 1]); return 1; }
     }
 
-    if (match || all) {                                    // host paths: whole input, as before
-        std::vector<unsigned char> in;
-        {
-            std::vector<unsigned char> buf(1 << 16);
-            size_t k;
-            while ((k = std::fread(buf.data(), 1, buf.size(), fp)) > 0) in.insert(in.end(), buf.begin(), buf.begin() + k);
-        }
-        if (fp != stdin) std::fclose(fp);
-        uint8_t *out = nullptr;
-        size_t out_n = 0;
-        rc = trre_match_host(prog, match ? 0 : 1, all ? 1 : 0, in.data(), in.size(), &out, &out_n, err, sizeof err);
-        if (out_n) std::fwrite(out, 1, out_n, stdout);
-        if (rc != TRRE_OK) { std::fflush(stdout); std::fputs(err, stderr); return 1; }
-        trre_free(out);
-        trre_prog_free(prog);
-        return 0;
+    if (match || all) {                                    // trre_nft.c:635-648, 782-797: same pipeline, other DFS mode
+        rc = trre_prog_set_mode(prog, match ? 1 : 0, all ? 1 : 0);
+        if (rc != TRRE_OK) return fail_scan(rc);
     }
 
     int device = 0, gpus = 1;

@@ -177,7 +177,16 @@ struct BtScratch {
     uint32_t  cap, ocap;
 };
 
-// priority DFS over the flat NFT from in[p..lim): first FINAL wins (trre_nft.c:598-655)
+// What one attempt of the DFS does at a FINAL state (trre_nft.c:635-648):
+//   AM_FIRST      scan mode: print, return the consumed length
+//   AM_SCAN_ALL   scan mode with -a: print, keep searching; every attempt "fails" (-1), so the driver copies the raw byte
+//   AM_MATCH      -m: only a FINAL at the end of the record counts; print + '\n', stop
+//   AM_MATCH_ALL  -ma: the same, keep searching
+//   AM_NEWLINES   `trre_dft -m`: one bare '\n' per record (trre_dft.c:1287-1292; infer_dft prints nothing in MATCH mode)
+enum { AM_FIRST = 0, AM_SCAN_ALL = 1, AM_MATCH = 2, AM_MATCH_ALL = 3, AM_NEWLINES = 4 };
+
+// priority DFS over the flat NFT from in[p..lim) (trre_nft.c:598-655)
+template <int AMODE = AM_FIRST>
 __device__ __forceinline__ long attempt_backtrack(const DevProg &P, const BtScratch &B,
                                                   const uint8_t *__restrict__ in, size_t p, size_t lim,
                                                   Sink &o, uint32_t &status) {
@@ -215,12 +224,21 @@ __device__ __forceinline__ long attempt_backtrack(const DevProg &P, const BtScra
                 s = n.a;
                 break;
             default: {   // N_FINAL: fputs(output) prints up to the first produced NUL (trre_nft.c:644-645)
-                for (uint32_t k = 0; k < w; ++k) {
-                    uint8_t b = B.obuf[k];
-                    if (!b) break;
-                    o.put(b);
+                bool accept = true;
+                if (AMODE == AM_MATCH || AMODE == AM_MATCH_ALL) {        // input[i] == '\0' (trre_nft.c:636)
+                    if (i < len) { const uint8_t c = __ldg(in + p + i); accept = (c == 0 || c == '\n'); }
                 }
-                return (long)i;
+                if (accept) {
+                    for (uint32_t k = 0; k < w; ++k) {
+                        uint8_t b = B.obuf[k];
+                        if (!b) break;
+                        o.put(b);
+                    }
+                    if (AMODE == AM_MATCH || AMODE == AM_MATCH_ALL) o.put('\n');
+                    if (AMODE == AM_FIRST || AMODE == AM_MATCH) return (long)i;
+                }
+                s = -1;
+                break;
             }
         }
     }

@@ -119,6 +119,7 @@ struct trre_prog {
     std::map<int, DeviceState *> dev;
     LazyDsa *lazy = nullptr;       // TRRE_EXEC_LAZY: the on-demand table builder, shared by all devices
     std::mutex lazy_mu;
+    int amode = AM_FIRST;          // trre_prog_set_mode: what the CLI's -m / -a ask for (AM_*, device_walk.cuh)
 };
 
 namespace {
@@ -389,8 +390,12 @@ int ensure_workspace(DeviceState *d, size_t n_chunks, size_t n_groups, bool back
 }
 
 template <int MODE>
-void launch_lines(int exec, int grid, cudaStream_t st, const LineArgs &a) {
-    if (exec == EXEC_DFS) k_lines<MODE, EXEC_DFS><<<grid, kLineThreads, 0, st>>>(a);
+void launch_lines(int exec, int grid, cudaStream_t st, const LineArgs &a, int amode = AM_FIRST) {
+    if (amode == AM_SCAN_ALL) k_lines<MODE, EXEC_DFS, AM_SCAN_ALL><<<grid, kLineThreads, 0, st>>>(a);
+    else if (amode == AM_MATCH) k_lines<MODE, EXEC_DFS, AM_MATCH><<<grid, kLineThreads, 0, st>>>(a);
+    else if (amode == AM_MATCH_ALL) k_lines<MODE, EXEC_DFS, AM_MATCH_ALL><<<grid, kLineThreads, 0, st>>>(a);
+    else if (amode == AM_NEWLINES) k_lines<MODE, EXEC_TABLE, AM_NEWLINES><<<grid, kLineThreads, 0, st>>>(a);
+    else if (exec == EXEC_DFS) k_lines<MODE, EXEC_DFS><<<grid, kLineThreads, 0, st>>>(a);
     else if (exec == EXEC_LAZY) k_lines<MODE, EXEC_LAZY><<<grid, kLineThreads, 0, st>>>(a);
     else k_lines<MODE, EXEC_TABLE><<<grid, kLineThreads, 0, st>>>(a);
 }
@@ -512,8 +517,11 @@ int launch_fast(const trre_prog *p, DeviceState *d, const uint8_t *d_in, size_t 
 // The general path: count -> scan -> (write).  3 kernels (2 when only sizing).
 int launch_general(const trre_prog *p, DeviceState *d, const uint8_t *d_in, size_t n, uint8_t *d_out,
                    size_t out_cap, cudaStream_t st, int phase, int *launches) {
-    const bool backtrack = p->hdr.exec_kind == TRRE_EXEC_BACKTRACK;
-    const bool lazy = p->hdr.exec_kind == TRRE_EXEC_LAZY;
+    // -a / -m / -ma run the reference's DFS whatever tables the program has (trre_nft.c:635-648)
+    const int amode = p->amode;
+    const bool dfs_mode = amode == AM_SCAN_ALL || amode == AM_MATCH || amode == AM_MATCH_ALL;
+    const bool backtrack = p->hdr.exec_kind == TRRE_EXEC_BACKTRACK || dfs_mode;
+    const bool lazy = p->hdr.exec_kind == TRRE_EXEC_LAZY && amode == AM_FIRST;
     const int exec = backtrack ? EXEC_DFS : lazy ? EXEC_LAZY : EXEC_TABLE;
     if (lazy) { int rc0 = lazy_sync(const_cast<trre_prog *>(p), d, st); if (rc0 != TRRE_OK) return rc0; }
     const size_t n_chunks = (n + kChunk - 1) / kChunk;
@@ -526,7 +534,7 @@ int launch_general(const trre_prog *p, DeviceState *d, const uint8_t *d_in, size
     if (phase != PH_WRITE) d->counts_kind = 1;
     LineArgs a = make_args(d, d_in, n, d_out, out_cap, d->d_status);
     if (lazy) a.L.start_info = p->lazy->start_info();
-    const bool staged = !backtrack && !lazy && d->P.ctrans && !std::getenv("TRRE_NO_STAGED_LINES");
+    const bool staged = !backtrack && !lazy && amode == AM_FIRST && d->P.ctrans && !std::getenv("TRRE_NO_STAGED_LINES");
     StagedArgs sa{};
     size_t smem_count = 0, smem_write = 0;
     int grid_s = grid;
@@ -580,7 +588,7 @@ int launch_general(const trre_prog *p, DeviceState *d, const uint8_t *d_in, size
         }
         *launches -= 1;                                       // the last pass is the one counted below
     } else if (phase != PH_WRITE) {
-        launch_lines<MODE_COUNT>(exec, grid, st, a);
+        launch_lines<MODE_COUNT>(exec, grid, st, a, amode);
     }
     if (phase != PH_WRITE) {
         k_scan_groups<<<1, kScanThreads, 0, st>>>(d->d_gsum, n_groups, d->d_total);
@@ -588,7 +596,7 @@ int launch_general(const trre_prog *p, DeviceState *d, const uint8_t *d_in, size
     }
     if (phase != PH_SIZE) {
         if (staged) k_lines_s<MODE_WRITE><<<std::min(grid_s, d->sm_count * 2), kLineThreads, smem_write, st>>>(sa);
-        else launch_lines<MODE_WRITE>(exec, grid, st, a);
+        else launch_lines<MODE_WRITE>(exec, grid, st, a, amode);
         *launches += 1;
     }
     CUDA_TRY(cudaGetLastError());
@@ -695,6 +703,10 @@ int enqueue_scan(const trre_prog *p, DeviceState *d, const uint8_t *d_in, size_t
     if (d->status_dirty) { int rc = clear_status(d, st); if (rc != TRRE_OK) return rc; }
     if (n == 0) return TRRE_OK;
     d->pend_phase = size_only ? PH_SIZE : PH_ALL;
+    if (p->amode != AM_FIRST) {
+        d->status_dirty = true;
+        return launch_general(p, d, d_in, n, d_out, out_cap, st, d->pend_phase, &d->launches);
+    }
     if (!size_only && fast_capable(p->hdr) && out_cap >= n) {
         int rc = launch_fast(p, d, d_in, n, d_out, d->d_status, st);
         if (rc != TRRE_OK) return rc;
@@ -750,7 +762,7 @@ int collect(const trre_prog *p, DeviceState *d, cudaStream_t st, size_t *out_n) 
         s = *d->h_status;
         total = (size_t)*d->h_total;
     }
-    if ((s & (ST_STACK | ST_OBUF)) && p->hdr.exec_kind == TRRE_EXEC_BACKTRACK && d->bt_tier == 0) {
+    if ((s & (ST_STACK | ST_OBUF)) && (p->hdr.exec_kind == TRRE_EXEC_BACKTRACK || p->amode != AM_FIRST) && d->bt_tier == 0) {
         // the small per-thread DFS stacks overflowed: once more with the reference's capacity (see ensure_workspace)
         d->bt_tier = 1;
         int rc = clear_status(d, st);
@@ -1078,6 +1090,14 @@ int trre_prog_get_info(const trre_prog *p, trre_prog_info *info) {
     return TRRE_OK;
 }
 
+int trre_prog_set_mode(trre_prog *p, int match, int all) {
+    if (!p) return TRRE_E_ARG;
+    if (all && p->hdr.flavor == TRRE_FLAVOR_DFT) { g_last_error = "Not supported yet\n"; return TRRE_E_UNSUPPORTED; }   // trre_dft.c:1226
+    p->amode = match ? (p->hdr.flavor == TRRE_FLAVOR_DFT ? AM_NEWLINES : all ? AM_MATCH_ALL : AM_MATCH)
+                     : (all ? AM_SCAN_ALL : AM_FIRST);
+    return TRRE_OK;
+}
+
 int trre_prog_bytemap(const trre_prog *p, uint8_t lut[256]) {
     if (!p || !lut || p->hdr.exec_kind != TRRE_EXEC_BYTEMAP) return TRRE_E_ARG;
     std::memcpy(lut, p->blob.data() + p->hdr.off_lut, 256);
@@ -1132,7 +1152,7 @@ int trre_scan_into(const trre_prog *p, int device, const uint8_t *in, size_t n, 
     // A buffer whose last record has no '\n' (a file without a final newline) is irregular only in that record - getline's
     // last record loses its last byte (trre_nft.c:776-777).  The position-parallel kernels take everything up to the last
     // '\n'; only the tail goes to the per-line kernels, instead of the whole buffer.
-    if (in[n - 1] != '\n' && p->hdr.exec_kind != TRRE_EXEC_BACKTRACK && p->hdr.exec_kind != TRRE_EXEC_LAZY) {
+    if (in[n - 1] != '\n' && p->hdr.exec_kind != TRRE_EXEC_BACKTRACK && p->hdr.exec_kind != TRRE_EXEC_LAZY && p->amode == AM_FIRST) {
         if (const void *nl = memrchr(in, '\n', n)) {
             const size_t cut = (size_t)(static_cast<const uint8_t *>(nl) - in) + 1;
             size_t n1 = 0, n2 = 0;
@@ -1150,14 +1170,14 @@ int trre_scan_into(const trre_prog *p, int device, const uint8_t *in, size_t n, 
     }
     cudaStream_t st = nullptr;
     // length-preserving program and room for n bytes: chunked, copy/compute overlapped
-    if (fast_capable(p->hdr) && out && out_cap >= n) {
+    if (fast_capable(p->hdr) && p->amode == AM_FIRST && out && out_cap >= n) {
         int launches = 0;
         rc = pipelined_lp(p, d, in, n, out, &launches);
         d->launches = launches;
         if (rc == 0) { if (out_n) *out_n = n; return TRRE_OK; }
         if (rc != 1) return rc;                                  // 1 = irregular buffer: general path below
     }
-    if (out && out_cap && ((p->hdr.flags & PF_BYTEMAP_VAR) || (p->hdr.flags & PF_MATCHABLE_VAR)) &&
+    if (out && out_cap && p->amode == AM_FIRST && ((p->hdr.flags & PF_BYTEMAP_VAR) || (p->hdr.flags & PF_MATCHABLE_VAR)) &&
         (bmv_capable(p, d, nullptr) || mv_capable(p, d, nullptr))) {
         int launches = 0;
         size_t total = 0;
@@ -1204,7 +1224,7 @@ int trre_scan(const trre_prog *p, int device, const uint8_t *in, size_t n, uint8
     *out = nullptr; *out_n = 0;
     // size first (cheap when length preserving: n), then fill
     size_t need = 0;
-    const bool lp = p && (p->hdr.flags & PF_LENGTH_PRESERVING) && p->hdr.exec_kind != TRRE_EXEC_BACKTRACK;
+    const bool lp = p && (p->hdr.flags & PF_LENGTH_PRESERVING) && p->hdr.exec_kind != TRRE_EXEC_BACKTRACK && p->amode == AM_FIRST;
     // length preserving: exactly n; otherwise guess a little more than n (one pipelined pass when it fits,
     // the exact size comes back with TRRE_E_NOSPACE when it does not)
     size_t cap = lp ? n : n + n / 4 + 4096;

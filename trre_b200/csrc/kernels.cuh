@@ -281,14 +281,20 @@ enum { EXEC_TABLE = 0, EXEC_DFS = 1, EXEC_LAZY = 2 };   // which per-attempt exe
 // for the record whose payload starts at `p`; `lim` = end of all payload bytes of the buffer (n, or
 // n-1 when the buffer does not end in '\n': getline's last record loses its last byte).
 // Returns the position just past the record.
-template <int EXEC>
+// AMODE != AM_FIRST (the CLI's -a / -m / -ma, trre_nft.c:635-648, 782-797) always runs the DFS executor.
+template <int EXEC, int AMODE = AM_FIRST>
 __device__ __forceinline__ size_t run_record(const DevProg &P, const BtScratch &B, const LazyDev &L, const uint8_t *__restrict__ in,
                                              size_t p, size_t lim, size_t n, Sink &o, uint32_t &status) {
-    for (;;) {
+    if (AMODE == AM_MATCH || AMODE == AM_MATCH_ALL || AMODE == AM_NEWLINES) {
+        // match mode: one attempt over the whole record, nothing copied, no newline of its own (trre_nft.c:792-796);
+        // trre_dft prints a bare newline per record instead (trre_dft.c:1288-1292)
+        if (AMODE == AM_NEWLINES) o.put('\n');
+        else attempt_backtrack<AMODE>(P, B, in, p, lim, o, status);
+    } else for (;;) {
         bool at_end = true;
         uint8_t c = 0;
         if (p < lim) { c = __ldg(in + p); at_end = (c == 0 || c == '\n'); }
-        long k = EXEC == EXEC_DFS    ? attempt_backtrack(P, B, in, p, lim, o, status)
+        long k = EXEC == EXEC_DFS    ? attempt_backtrack<AMODE>(P, B, in, p, lim, o, status)
                  : EXEC == EXEC_LAZY ? attempt_lazy(L, in, p, lim, o, status)
                                      : attempt_table(P, in, p, lim, o, status);
         if (EXEC == EXEC_LAZY && k == -2) break;          // a row is missing: this pass is void, leave the record
@@ -298,13 +304,13 @@ __device__ __forceinline__ size_t run_record(const DevProg &P, const BtScratch &
         if (k > 0) p += (size_t)k;
         else { o.put(c); ++p; }                           // no match or empty match: copy one raw byte
     }
-    o.put('\n');
+    if (AMODE == AM_FIRST || AMODE == AM_SCAN_ALL) o.put('\n');
     // skip what getline would still have consumed: the rest of the record after a NUL, and the '\n'
     while (p < n && __ldg(in + p) != '\n') ++p;
     return p + 1;
 }
 
-template <int MODE, int EXEC>
+template <int MODE, int EXEC, int AMODE = AM_FIRST>
 __global__ void __launch_bounds__(kLineThreads)
 k_lines(LineArgs a) {
     __shared__ unsigned long long warp_sums[kLineThreads / 32];
@@ -362,7 +368,7 @@ k_lines(LineArgs a) {
             while (p < cend) {                            // p < n here: a record starts at p
                 if (MODE == MODE_INPLACE) o.n = p;
                 size_t before = o.n;
-                p = run_record<EXEC>(a.P, B, a.L, in, p, lim, n, o, status);
+                p = run_record<EXEC, AMODE>(a.P, B, a.L, in, p, lim, n, o, status);
                 produced += o.n - before;
                 if (MODE == MODE_INPLACE && o.n != p) status |= ST_IRREGULAR;   // a NUL cut the line short
             }
