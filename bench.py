@@ -535,6 +535,8 @@ def kernel_label(T, info):
     if info["exec_kind"] == T.EXEC_BYTEMAP:
         return "k_bytemap_swar" if os.environ.get("TRRE_NO_SWAR") is None else "k_bytemap"
     label = KERNELS[info["fast_path"]]
+    if info.get("literal_words") and info["fast_path"] == 2 and os.environ.get("TRRE_NO_LIT") is None:
+        return "k_lit"
     if info.get("gram_tables") and os.environ.get("TRRE_NO_GRAM") is None:
         label = label.replace("k_match", "k_gram_var") if info["fast_path"] == 4 else label.replace("k_match", "k_gram")
     return label

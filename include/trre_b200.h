@@ -91,6 +91,8 @@ typedef struct trre_prog_info {
     uint32_t fast_path;          /* TRRE_FAST_*: which position-parallel kernel serves a regular buffer      */
     uint32_t gram_tables;        /* 1: every attempt is tabulated by byte classes (k_gram / k_gram_var serve   */
                                  /*    TRRE_FAST_MATCH / TRRE_FAST_MATCH_VAR instead of the walking k_match)   */
+    uint32_t literal_words;      /* > 0: the matches are that many fixed words of 2..4 bytes that cannot overlap */
+                                 /*    (cat:dog, (cat:dog|dog:cat)): k_lit compares in registers, no tables     */
 } trre_prog_info;
 
 /* ---- host side: pattern -> program (no GPU needed) ------------------------------------------- */

@@ -17,7 +17,9 @@ FIELDS = ("magic abi total_bytes flavor exec_kind flags nft_states nft_start dsa
 
 # header words beyond FIELDS (automaton.hpp BlobHeader): index -> name
 EXT = {28: "swar_n", 29: "swar0", 30: "swar1", 31: "swar2", 32: "swar3", 33: "gram_depth", 34: "gram_entries",
-       35: "gram_len", 36: "gram_flags", 37: "off_gbits", 38: "off_gout", 39: "off_gpool", 40: "gpool_bytes"}
+       35: "gram_len", 36: "gram_flags", 37: "off_gbits", 38: "off_gout", 39: "off_gpool", 40: "gpool_bytes",
+       41: "lit_words", 42: "lit_len"}
+EXT.update({43 + k: "lit%d" % k for k in range(16)})
 PF_MATCHABLE, PF_GRAM = 64, 512
 
 
@@ -40,7 +42,7 @@ class Blob:
         self.sinfo = struct.unpack_from("<%dQ" % ns, raw, h["off_sinfo"]) if ns else ()
         self.pool = raw[h["off_pool"]:h["off_pool"] + h["pool_bytes"]]
         self.nft = [struct.unpack_from("<BBBBii", raw, h["off_nft"] + 12 * k) for k in range(h["nft_states"])]
-        words = struct.unpack_from("<41I", raw, 0)
+        words = struct.unpack_from("<59I", raw, 0)
         for k, name in EXT.items():
             h[name] = words[k]
 
@@ -61,6 +63,22 @@ class Blob:
         return bytes(lut)
 
     # ---- gram tables (k_gram): position-parallel form of the scan over a REGULAR buffer ----------------------
+    def scan_lit(self, data: bytes) -> bytes:
+        """What k_lit computes (lit_kernel.cuh): wherever one of the lit_words words stands - position k of a word accepts
+        one byte range - its lit_len bytes are replaced by what it prints.  No line structure, no "inside an earlier
+        match" bookkeeping: the host only emits this form when words cannot overlap.  Regular buffers only."""
+        h = self.h
+        nw, L = h["lit_words"], h["lit_len"]
+        assert nw and data.endswith(b"\n") and b"\0" not in data
+        out = bytearray(data)
+        for p in range(len(data) - L + 1):
+            for w in range(nw):
+                slots = [h["lit%d" % (w * L + k)] for k in range(L)]
+                if all((s & 0xFF) <= data[p + k] <= ((s >> 8) & 0xFF) for k, s in enumerate(slots)):
+                    for k, s in enumerate(slots):
+                        out[p + k] = (s >> 16) & 0xFF
+        return bytes(out)
+
     def scan_gram(self, data: bytes) -> bytes:
         """What k_gram computes: a match starts at every position whose D-gram bit is set and that no earlier
         match of the line covers; it prints gout.  Regular buffers only (no NUL, final newline)."""

@@ -80,3 +80,36 @@ def ref_run(expr: bytes, data: bytes, flavor=NFT, mode=SCAN, all_=False, timeout
     argv.append(expr)
     p = subprocess.run(argv, input=data, stdout=subprocess.PIPE, stderr=subprocess.PIPE, timeout=timeout)
     return p.returncode, p.stdout, p.stderr.decode("latin1")
+
+
+def bounded_run(expr: bytes, data: bytes, flavor=NFT, mode=SCAN, all_=False, cpu_s=5, mem_mb=1024, out_mb=16):
+    """The reference binary (or, without it, the oracle) in a CHILD process under hard limits: CPU seconds, address space,
+    and the size of stdout (a file).  Generators and catastrophic backtracking are legal inputs of `trre -ma` and can
+    print gigabytes or run for hours; a test must never do that inside the pytest process (it took two GPU boxes down).
+    -> (rc, stdout) or None when a limit was hit."""
+    import resource, sys, tempfile
+
+    def limits():
+        resource.setrlimit(resource.RLIMIT_CPU, (cpu_s, cpu_s))
+        resource.setrlimit(resource.RLIMIT_AS, (mem_mb << 20, mem_mb << 20))
+        resource.setrlimit(resource.RLIMIT_FSIZE, (out_mb << 20, out_mb << 20))
+
+    if have_ref():
+        argv = [REF_NFT if flavor == NFT else REF_DFT] + (["-m"] if mode == MATCH else []) + (["-a"] if all_ else []) + [expr]
+    else:
+        code = ("import sys; sys.path.insert(0, %r); from oracle_util import oracle_run; "
+                "rc, out, _ = oracle_run(%r, sys.stdin.buffer.read(), flavor=%d, mode=%d, all_=%r); "
+                "sys.stdout.buffer.write(out); sys.exit(rc)" % (os.path.dirname(os.path.abspath(__file__)), expr, flavor, mode, bool(all_)))
+        argv = [sys.executable, "-c", code]
+    with tempfile.TemporaryFile() as fo:
+        try:
+            p = subprocess.run(argv, input=data, stdout=fo, stderr=subprocess.DEVNULL, preexec_fn=limits, timeout=4 * cpu_s + 10)
+        except subprocess.TimeoutExpired:
+            return None
+        if p.returncode not in (0, 1):
+            return None                                    # killed by a limit (SIGXCPU, SIGXFSZ, SIGSEGV on a failed malloc ...)
+        fo.seek(0)
+        out = fo.read()
+    if len(out) >= (out_mb << 20) - 4096:
+        return None
+    return p.returncode, out

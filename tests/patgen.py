@@ -69,3 +69,64 @@ def rand_input(rng, nlines=None, alphabet="abcd ", maxlen=12, final_newline=True
     if nlines and final_newline:
         s += "\n"
     return s.encode("latin1")
+
+
+def rand_word_expr(rng, alphabet="abcdefgh"):
+    """(w1):(o1)|(w2):(o2)... : 1-4 words of one length 2-4 over a small alphabet, a position sometimes a range; the
+    shapes k_lit serves when the words cannot overlap, k_gram otherwise."""
+    L = rng.randint(2, 4)
+    parts = []
+    for _ in range(rng.randint(1, 4)):
+        word = ""
+        for _k in range(L):
+            if rng.random() < 0.2:
+                a = rng.randrange(len(alphabet) - 1)
+                b = rng.randrange(a + 1, len(alphabet))
+                word += "[%s-%s]" % (alphabet[a], alphabet[b])
+            else:
+                word += rng.choice(alphabet)
+        out = "".join(rng.choice("XYZxyz01") for _k in range(L))
+        parts.append("(%s):(%s)" % (word, out))
+    return "|".join(parts)
+
+
+def rand_finite_expr(rng, alphabet="abc"):
+    """Expressions whose DFS is finite and small on short lines whatever the mode (-a / -ma enumerate EVERY accepting
+    path): iteration only over bodies that consume a byte, no empty-input producers inside loops, two or three
+    alternatives at most."""
+    def atom():
+        r = rng.random()
+        c = rng.choice(alphabet)
+        if r < 0.35:
+            return c
+        if r < 0.6:
+            return "%s:%s" % (c, rng.choice("XYZ"))
+        if r < 0.7:
+            return "(%s:)" % c
+        if r < 0.8:
+            return "[%s-%s]" % (alphabet[0], alphabet[-1])
+        if r < 0.9:
+            return "."
+        return "(%s|%s:%s)" % (c, rng.choice(alphabet), rng.choice("XYZ"))
+
+    def piece():
+        a = atom()
+        r = rng.random()
+        if r < 0.15:
+            return "(%s)*" % a
+        if r < 0.25:
+            return "(%s)+" % a
+        if r < 0.35:
+            return "(%s)?" % a
+        if r < 0.4:
+            return "(%s){1,2}" % a
+        return a
+
+    def seq():
+        return "".join(piece() for _ in range(rng.randint(1, 4)))
+
+    alts = [seq() for _ in range(rng.randint(1, 3))]
+    e = "|".join(alts)
+    if rng.random() < 0.3:
+        e = "(%s)(:%s)?" % (e, rng.choice("XYZ"))
+    return e

@@ -68,6 +68,14 @@ def test_scan_fails_loudly_without_a_gpu():
     assert ei.value.code == 3 and "no CPU fallback" in str(ei.value)
 
 
+def gpu_present():
+    try:
+        import torch
+        return torch.cuda.is_available()
+    except Exception:
+        return False
+
+
 def test_cli_contract_without_touching_the_scan_path():
     import subprocess
     exe = os.path.join(ROOT, "bin", "trre")
@@ -84,9 +92,14 @@ def test_cli_contract_without_touching_the_scan_path():
     assert r.returncode == 1 and b"Usage:" in r.stderr and b"[-d] [-m] expr [file]" in r.stderr
     r = subprocess.run([exe, ""], input=b"", capture_output=True)
     assert r.returncode == -6 or r.returncode == 134           # assert() abort, trre_nft.c:285
+    # -m / -a run on the GPU too (trre_prog_set_mode): without a device they fail loudly, there is no host fallback
     r = subprocess.run([exe, "-ma", ":a{,3}"], input=b"\n", capture_output=True)
-    assert r.returncode == 0 and r.stdout == b"aaa\naa\na\n\n"
-    r = subprocess.run([exe, "-m", "cat:dog"], input=b"cat\ncow\n", capture_output=True)
-    assert r.stdout == b"dog\n"
-    r = subprocess.run([exe_dft, "-m", "cat:dog"], input=b"cat\ncow\n", capture_output=True)
-    assert r.stdout == b"\n\n"                                  # trre_dft.c:1287-1293
+    if gpu_present():
+        assert r.returncode == 0 and r.stdout == b"aaa\naa\na\n\n"
+    else:
+        assert r.returncode == 1 and r.stdout == b"" and b"no CPU fallback" in r.stderr
+    if gpu_present():
+        r = subprocess.run([exe, "-m", "cat:dog"], input=b"cat\ncow\n", capture_output=True)
+        assert r.stdout == b"dog\n"
+        r = subprocess.run([exe_dft, "-m", "cat:dog"], input=b"cat\ncow\n", capture_output=True)
+        assert r.stdout == b"\n\n"                                  # trre_dft.c:1287-1293

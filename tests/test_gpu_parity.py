@@ -409,30 +409,28 @@ def test_dfs_executor_has_the_reference_stack_capacity():
 
 @pytest.mark.parametrize("seed", range(4))
 def test_match_and_all_modes_on_the_gpu(seed):
-    """-m / -ma / -a (trre_nft.c:635-648, 782-797) through trre_prog_set_mode: GPU DFS vs the oracle on random
-    expressions and inputs; trre_dft -m prints a bare newline per record (trre_dft.c:1287-1292)."""
-    from oracle_util import MATCH, SCAN
+    """-m / -ma / -a (trre_nft.c:635-648, 782-797) through trre_prog_set_mode: GPU DFS vs the reference on random
+    expressions whose enumeration is finite, lines of at most 8 bytes; the expected output comes from a CHILD process
+    under CPU / memory / output limits (oracle_util.bounded_run) - `-ma` is allowed to print gigabytes."""
+    from oracle_util import MATCH, SCAN, bounded_run
+    from patgen import rand_finite_expr
     rng = random.Random(7000 + seed)
     ran = 0
-    for _ in range(50):
-        pat = rand_expr(rng, 2)
-        data = rand_input(rng, nlines=rng.randint(0, 40), maxlen=12, final_newline=rng.random() < 0.8)
+    for _ in range(40):
+        pat = rand_finite_expr(rng)
+        data = rand_input(rng, nlines=rng.randint(0, 30), alphabet="abc ", maxlen=8, final_newline=rng.random() < 0.8)
         for flavor, mode, all_ in ((NFT, SCAN, True), (NFT, MATCH, False), (NFT, MATCH, True), (DFT, MATCH, False)):
-            rc, want, err = oracle_run(pat if isinstance(pat, bytes) else pat.encode("latin1"), data, flavor=flavor, mode=mode, all_=all_)
-            if len(want) > (1 << 20):
+            ref = bounded_run(pat.encode("latin1"), data, flavor=flavor, mode=mode, all_=all_, cpu_s=2, out_mb=4)
+            if ref is None or ref[0] != 0:
                 continue
             try:
                 prog = T.compile(pat, flavor).set_mode(match=mode == MATCH, all_=all_)
             except T.TrreError:
                 continue
-            if rc != 0:
-                with pytest.raises(T.TrreError):
-                    prog.scan(data)
-                continue
             got = prog.scan(data)
-            assert got == want, (pat, flavor, mode, all_, data[:80], got[:80], want[:80])
+            assert got == ref[1], (pat, flavor, mode, all_, data[:80], got[:80], ref[1][:80])
             if flavor == NFT:
-                assert prog.match(data, all_=all_, scan=mode == SCAN) == want
+                assert prog.match(data, all_=all_, scan=mode == SCAN) == ref[1]
             ran += 1
     assert ran > 60, ran
 
@@ -447,3 +445,38 @@ def test_modes_on_config_text():
         assert rc == 0
         assert T.compile(expr, NFT).set_mode(match=mode == MATCH, all_=all_).scan(text) == want, expr
     assert T.compile("cat:dog", DFT).set_mode(match=True).scan(text) == b"\n" * text.count(b"\n")
+
+
+def test_literal_words_kernel(monkeypatch):
+    """k_lit (lit_kernel.cuh): fixed words compared in registers - against the oracle on random word programs, buffer
+    sizes around the kernel's 16-byte vectors, 30-vector warp windows and 15 360-byte CTAs, words across every such
+    boundary, high bytes, and the irregular cases (NUL, no final newline) that must take the general path."""
+    from patgen import rand_word_expr
+    rng = random.Random(4242)
+    served = 0
+    for _ in range(60):
+        pat = rand_word_expr(rng)
+        n = rng.choice([1, 2, 5, 15, 16, 17, 31, 33, 479, 480, 481, 500, 1000, 15359, 15360, 15361, 15376, 30720, 100000])
+        body = bytes(rng.choice(b"abcdefgh  \n") for _k in range(n))
+        data = body[:-1] + b"\n"
+        for flavor in (NFT, DFT):
+            prog = check(pat, flavor, data)
+            if prog is not None and prog.info["literal_words"]:
+                served += 1
+                assert prog.launches() == 1
+    assert served > 30, served
+    text = bytes(T.synth_text(0x72726511, 3 << 20, ["cat", "dog", "catdog", "dogcat", "ca", "do", "cot", "dig"], 0.3))
+    for expr in ("cat:dog", "(cat:dog|dog:cat)", "(ca):(xy)|(do):(zw)|(ig):(ab)|(ut):(cd)", "(catd):(DOGC)", "c(a:o)t|dog:cat"):
+        for flavor in (NFT, DFT):
+            prog = check(expr, flavor, text)
+            assert prog.info["literal_words"] >= 1
+            for cut in (1, 15, 16, 17, 480 * 16, 480 * 16 + 5):                # ragged ends, every one a final newline
+                piece = text[:len(text) - cut]
+                piece = piece[:piece.rfind(b"\n") + 1]
+                check(expr, flavor, piece)
+            check(expr, flavor, text[:70000] + b"c\xe1t \xff dog\0cat\n" + text[:5000])      # high bytes, a NUL
+            check(expr, flavor, text[:70001].rstrip(b"\n"))                                 # no final newline
+    monkeypatch.setenv("TRRE_NO_LIT", "1")                 # the same programs on k_gram: same bytes
+    for expr in ("cat:dog", "(cat:dog|dog:cat)"):
+        q = T.compile(expr, NFT)
+        assert q.scan(text) == oracle_run(expr.encode(), text, flavor=NFT)[1]

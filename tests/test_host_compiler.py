@@ -231,6 +231,81 @@ def test_gram_tables_reproduce_the_scan():
             assert rc == 0 and b.scan_gram(data) == want, (pat, fl, data)
 
 
+def test_literal_word_form():
+    """BlobHeader::lit (k_lit): programs whose matches are <= 4 fixed words of 2..4 byte ranges that cannot overlap.  The
+    form must reproduce the scan WITHOUT any bookkeeping of earlier matches; whatever could overlap must not get it."""
+    text = bytes(T.synth_text(3, 30000, ["cat", "dog", "catdog", "dogcat", "ca", "do", "cot", "dig", "abab", "aa"], 0.4))
+    yes = [("cat:dog", 1, 3), ("(cat:dog|dog:cat)", 2, 3), ("c(a:o)t", 1, 3), ("c(a:o)t|dog:cat", 2, 3), ("[a-c][x-z]:pq", 1, 2),
+           ("ca:xy|do:zw|ig:ab|ut:cd", 4, 2), ("catd:dogc", 1, 4), ("[c-d]og:xyz|cat:CAT", 3, 3), ("[e-f]og:xyz|cat:CAT", 2, 3)]
+    for expr, nw, L in yes:
+        for flavor in (NFT, DFT):
+            p = T.compile(expr, flavor)
+            b = Blob(p.blob())
+            if flavor == NFT:                          # (trre_dft's tables may split a range into its bytes: more words)
+                assert (b.h["lit_words"], b.h["lit_len"], p.info["literal_words"]) == (nw, L, nw), (expr, flavor, b.h["lit_words"], b.h["lit_len"])
+            elif not b.h["lit_words"]:
+                continue
+            rc, want, _ = oracle_run(expr.encode(), text, flavor=flavor)
+            assert rc == 0 and b.scan_lit(text) == want, (expr, flavor)
+    no = ["aba:xyz",             # overlaps itself: ababa -> xyzba
+          "aa:bc",               # overlaps itself
+          "ab:xy|bc:zw",         # b ends one word and starts another
+          "cat:dog|ca:xy",       # what follows `ca` decides
+          "a:b|cat:dog",         # two lengths
+          "cat:do",              # not length preserving
+          "ab:xy|cd:xy|ef:xy|gh:xy|ij:xy",   # five words
+          "c\xe9:xy",            # a byte >= 0x80: still the form (k_lit itself declines it at run time) - checked below
+          "[a-c]:x",             # one byte: a byte map
+          "cat+:dog"]            # cyclic
+    for expr in no:
+        for flavor in (NFT, DFT):
+            try:
+                p = T.compile(expr.encode("latin1"), flavor)
+            except T.TrreError:
+                continue
+            if expr.startswith("c\xe9"):
+                assert p.info["literal_words"] == 1
+                continue
+            if flavor == DFT and p.info["literal_words"]:          # shortest-match semantics can make it a word form after all
+                assert Blob(p.blob()).scan_lit(text) == oracle_run(expr.encode("latin1"), text, flavor=DFT)[1], expr
+                continue
+            assert p.info["literal_words"] == 0, (expr, flavor, p.info)
+    rng = random.Random(99)
+    got = 0
+    for _ in range(300):                                   # whatever the generator produces: the form, when granted, is exact
+        pat = rand_expr(rng, 2).encode()
+        for fl in (NFT, DFT):
+            try:
+                p = T.compile(pat, fl)
+            except T.TrreError:
+                continue
+            b = Blob(p.blob())
+            if not b.h["lit_words"]:
+                continue
+            data = b"".join(rand_input(rng, nlines=6, maxlen=14, final_newline=True).replace(b"\0", b"x") for _ in range(3))
+            if not data.endswith(b"\n"):
+                data += b"\n"
+            rc, want, _ = oracle_run(pat, data, flavor=fl)
+            assert rc == 0 and b.scan_lit(data) == want, (pat, fl, data)
+            got += 1
+    from patgen import rand_word_expr
+    for _ in range(150):
+        pat = rand_word_expr(rng).encode()
+        for fl in (NFT, DFT):
+            try:
+                p = T.compile(pat, fl)
+            except T.TrreError:
+                continue
+            b = Blob(p.blob())
+            if not b.h["lit_words"]:
+                continue
+            data = b"\n".join(bytes(rng.choice(b"abcdefgh ") for _k in range(rng.randint(0, 60))) for _l in range(8)) + b"\n"
+            rc, want, _ = oracle_run(pat, data, flavor=fl)
+            assert rc == 0 and b.scan_lit(data) == want, (pat, fl, data)
+            got += 1
+    assert got > 40, got
+
+
 def test_gram_tables_of_the_dictionary():
     rng = random.Random(7)
     words = set()

@@ -28,7 +28,8 @@ class TrreError(RuntimeError):
 class _Info(ctypes.Structure):
     _fields_ = [(n, ctypes.c_uint32) for n in (
         "abi_version", "flavor", "exec_kind", "nft_states", "dsa_states", "byte_classes",
-        "max_depth", "length_preserving", "can_match_empty", "table_bytes", "fast_path", "gram_tables")]
+        "max_depth", "length_preserving", "can_match_empty", "table_bytes", "fast_path", "gram_tables",
+        "literal_words")]
 
 
 _L = None

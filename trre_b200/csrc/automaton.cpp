@@ -702,6 +702,57 @@ bool build_grams(const Program &P, GramTables &G) {
     return true;
 }
 
+// The literal form of a gram program (BlobHeader::lit): every match consumes and prints L = 2..4 bytes, whether an
+// attempt matches depends on its first L byte classes only, there are at most 4 matching class words, every class in
+// them is one byte range inside one half of the byte space, every printed byte is non-zero, and no proper suffix of a
+// word is the prefix of a word (then an attempt that starts inside a match can never match, so the set of matches is
+// simply the set of candidates - no chain to resolve).
+bool build_lit(const Program &P, const GramTables &G, uint32_t *n_words, uint32_t *len, uint32_t (&lit)[16]) {
+    const uint32_t L = G.uniform_len, D = G.depth, ncls = P.n_classes;
+    if (!(G.flags & GRAM_DIRECT_FLAG) || L < 2 || L > 4 || D < L) return false;
+    uint64_t prefixes = 1, completions = 1;
+    for (uint32_t i = 0; i < L; ++i) prefixes *= ncls;
+    for (uint32_t i = L; i < D; ++i) completions *= ncls;
+    struct Word { uint32_t prefix, out; uint64_t seen; };
+    std::vector<Word> words;
+    for (uint64_t idx = 0; idx < G.entries; ++idx) {
+        if (!(G.bits[idx >> 5] >> (idx & 31) & 1u)) continue;
+        const uint32_t pre = (uint32_t)(idx % prefixes);
+        size_t k = 0;
+        while (k < words.size() && words[k].prefix != pre) ++k;
+        if (k == words.size()) {
+            if (words.size() == 4) return false;
+            words.push_back(Word{pre, G.out[idx], 0});
+        }
+        if (words[k].out != G.out[idx]) return false;                 // what follows the word changes what it prints
+        ++words[k].seen;
+    }
+    if (words.empty()) return false;
+    for (const Word &w : words)
+        if (w.seen != completions) return false;                      // what follows the word decides whether it matches
+    auto cls_at = [&](const Word &w, uint32_t k) { uint32_t v = w.prefix; for (uint32_t i = 0; i < k; ++i) v /= ncls; return v % ncls; };
+    for (size_t a = 0; a < words.size(); ++a) {
+        for (uint32_t k = 0; k < L; ++k) {
+            const uint32_t c = cls_at(words[a], k);
+            int lo = -1, hi = -1, members = 0;
+            for (int b = 0; b < 256; ++b)
+                if (P.classmap[b] == c) { if (lo < 0) lo = b; hi = b; ++members; }
+            if (lo <= 0 || members != hi - lo + 1 || (lo < 0x80) != (hi < 0x80) || (lo <= '\n' && hi >= '\n')) return false;
+            const uint32_t printed = (words[a].out >> (8 * k)) & 0xFFu;
+            if (!printed) return false;
+            lit[a * L + k] = (uint32_t)lo | ((uint32_t)hi << 8) | (printed << 16);
+        }
+        for (size_t b = 0; b < words.size(); ++b)
+            for (uint32_t s = 1; s < L; ++s) {                         // words[b] starting s bytes into words[a]
+                bool fits = true;
+                for (uint32_t k = 0; k + s < L && fits; ++k) fits = cls_at(words[a], s + k) == cls_at(words[b], k);
+                if (fits) return false;
+            }
+    }
+    *n_words = (uint32_t)words.size();
+    *len = L;
+    return true;
+}
 
 std::vector<uint8_t> assemble(const Program &P, const Nft &g) {
     BlobHeader h;
@@ -755,6 +806,7 @@ std::vector<uint8_t> assemble(const Program &P, const Nft &g) {
         h.off_gout = (uint32_t)off; off += G.out.size() * 4; off = align16(off);
         h.off_gpool = (uint32_t)off; h.gpool_bytes = (uint32_t)G.pool.size(); off += G.pool.size(); off = align16(off);
         h.gram_depth = G.depth; h.gram_entries = G.entries; h.gram_len = G.uniform_len; h.gram_flags = G.flags;
+        if (matchable && !build_lit(P, G, &h.lit_words, &h.lit_len, h.lit)) { h.lit_words = h.lit_len = 0; std::memset(h.lit, 0, sizeof h.lit); }
     }
     if (off >= (1ull << 31)) throw PatternError{TRRE_E_UNSUPPORTED, "error: compiled tables exceed 2 GiB\n"};
     h.magic = 0x32425254u;  // "TRB2"
@@ -1050,6 +1102,13 @@ bool blob_is_valid(const void *blob, size_t nbytes, std::string *why) {
             const uint32_t *go = reinterpret_cast<const uint32_t *>(b + h.off_gout);
             for (uint64_t k = 0; k < e; ++k)
                 if ((uint64_t)(go[k] & 0xFFFFFu) + ((go[k] >> 20) & 0xFFu) > h.gpool_bytes && go[k]) return bad("gram output reference");
+        }
+    }
+    if (h.lit_words) {
+        if (h.lit_words > 4 || h.lit_len < 2 || h.lit_len > 4 || !(h.flags & PF_GRAM) || !(h.flags & PF_MATCHABLE)) return bad("literal word form");
+        for (uint32_t k = 0; k < h.lit_words * h.lit_len; ++k) {
+            const uint32_t lo = h.lit[k] & 0xFFu, hi = (h.lit[k] >> 8) & 0xFFu;
+            if (!lo || lo > hi || (lo < 0x80u) != (hi < 0x80u) || !((h.lit[k] >> 16) & 0xFFu)) return bad("literal word range");
         }
     }
     // table contents: every class < n_classes, every next state < dsa_states (or DEAD), every string inside the pool

@@ -101,6 +101,13 @@ struct BlobHeader {
                                // printed length(8) << 20 | (consumed - 1) << 28
     uint32_t off_gpool;
     uint32_t gpool_bytes;
+    // (lit_words > 0) the matches are lit_words <= 4 WORDS of lit_len = 2..4 bytes; position k of word w accepts one byte
+    // range and prints one byte: lit[w * lit_len + k] = lo | hi << 8 | printed << 16; no suffix of a word can be the
+    // prefix of a word, so every candidate is a real match and the scan needs no tables and no line structure at all:
+    // k_lit compares in registers (lit_kernel.cuh).  cat:dog is one word, (cat:dog|dog:cat) two.
+    uint32_t lit_words;
+    uint32_t lit_len;
+    uint32_t lit[16];
 };
 
 struct NftFlat {               // 12 bytes, device layout of trre_nft.c:334-340

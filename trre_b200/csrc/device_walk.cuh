@@ -18,8 +18,15 @@ enum : uint32_t {
     ST_OBUF        = 8u,    // per-attempt output buffer of the backtracking executor overflowed
     ST_NOSPACE     = 16u,   // d_out too small
     ST_MISS        = 32u,   // lazy tables: a row the input needs has not been built yet (see LazyDev)
-    ST_RUNAWAY     = 64u    // lazy tables: the input leads into a closure that does not terminate (LAZY_POISON)
+    ST_RUNAWAY     = 64u,   // lazy tables: the input leads into a closure that does not terminate (LAZY_POISON)
+    ST_BUDGET      = 128u   // DFS executor: one attempt went past kDfsStepBudget steps or kDfsPrintBudget printed bytes
 };
+
+// One attempt of the reference's DFS may backtrack exponentially ((a*)*b on aaaa...) and, with -a, print without bound
+// (generators): the reference then simply runs for hours.  A GPU thread gets a budget per RECORD instead; beyond it the
+// scan fails with its own error text (status_to_rc), never with wrong bytes.
+constexpr uint32_t kDfsStepBudget  = 1u << 26;
+constexpr uint32_t kDfsPrintBudget = 1u << 24;
 
 // TRRE_EXEC_LAZY: rows by raw byte, built on demand by the host between passes (automaton.hpp, LazyDsa)
 struct LazyDev {
@@ -175,6 +182,7 @@ struct BtScratch {
     uint32_t *stk_o;      // [cap]
     uint8_t  *obuf;       // [ocap]
     uint32_t  cap, ocap;
+    mutable uint32_t steps, printed;   // spent by the current RECORD (run_record resets them): see kDfsStepBudget
 };
 
 // What one attempt of the DFS does at a FINAL state (trre_nft.c:635-648):
@@ -199,6 +207,7 @@ __device__ __forceinline__ long attempt_backtrack(const DevProg &P, const BtScra
             s = B.stk_s[top]; i = B.stk_i[top]; w = B.stk_o[top];
             if (s < 0) continue;
         }
+        if (++B.steps > kDfsStepBudget) { status |= ST_BUDGET; return -1; }
         NftFlat n = P.nft[s];
         switch (n.op) {
             case N_CONS:
@@ -229,6 +238,10 @@ __device__ __forceinline__ long attempt_backtrack(const DevProg &P, const BtScra
                     if (i < len) { const uint8_t c = __ldg(in + p + i); accept = (c == 0 || c == '\n'); }
                 }
                 if (accept) {
+                    if (AMODE != AM_FIRST && AMODE != AM_MATCH) {
+                        B.printed += w + 1;
+                        if (B.printed > kDfsPrintBudget) { status |= ST_BUDGET; return -1; }
+                    }
                     for (uint32_t k = 0; k < w; ++k) {
                         uint8_t b = B.obuf[k];
                         if (!b) break;

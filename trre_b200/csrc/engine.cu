@@ -17,6 +17,7 @@
 #include "kernels.cuh"
 #include "match_kernel.cuh"
 #include "gram_kernel.cuh"
+#include "lit_kernel.cuh"
 #include "lines_staged.cuh"
 #include "bmv_kernel.cuh"
 #include "pattern.hpp"
@@ -99,6 +100,8 @@ struct DeviceState {
     bool gram_small = false;
     const void *gram_fn = nullptr;
     SwarMap swar{};                // table-free byte map (n == 0: not of that form)
+    LitMap lit{};                  // table-free word matcher (lit_words == 0: not of that form)
+    uint32_t lit_words = 0, lit_len = 0;
     // TRRE_EXEC_LAZY: device copies of the rows built so far (automaton.hpp, LazyDsa)
     uint64_t *lz_rows = nullptr, *lz_sinfo = nullptr;
     uint8_t *lz_pool = nullptr;
@@ -286,6 +289,17 @@ int get_state(const trre_prog *cp, int device, DeviceState **out) {
             d->swar.half[k] = lo < 0x80u ? 0x80808080u : 0u;
             d->swar.delta[k] = delta;
         }
+    }
+    if (h.lit_words >= 1 && h.lit_words <= 4 && h.lit_len >= 2 && h.lit_len <= 4 && (h.flags & PF_MATCHABLE) && !std::getenv("TRRE_NO_LIT")) {
+        d->lit_words = h.lit_words; d->lit_len = h.lit_len;
+        for (uint32_t k = 0; k < h.lit_words * h.lit_len; ++k) {
+            const uint32_t lo = h.lit[k] & 0xFFu, hi = (h.lit[k] >> 8) & 0xFFu;
+            d->lit.add_lo[k] = (0x80u - (lo & 0x7Fu)) * 0x01010101u;
+            d->lit.add_hi[k] = (0x7Fu - (hi & 0x7Fu)) * 0x01010101u;
+            d->lit.printed[k / h.lit_len] |= ((h.lit[k] >> 16) & 0xFFu) << (8 * (k % h.lit_len));
+            if (hi >= 0x80u) d->lit_words = 0;                     // k_lit tests 7-bit ranges below 0x80 only: k_gram serves
+        }
+        d->lit.one = 1;
     }
     if (h.flags & PF_MATCHABLE) {
         int rc2 = plan_match(h, (size_t)kMatchWarps * kWarpSmem, 108 * 1024, d->sm_count, OP_INPLACE, &d->mp);
@@ -484,6 +498,18 @@ int launch_fast(const trre_prog *p, DeviceState *d, const uint8_t *d_in, size_t 
         }
     } else if (h.exec_kind == TRRE_EXEC_BYTEMAP && aligned && d->P.pairlut) {
         k_bytemap<<<d->sm_count, kBmThreads, kPairLutBytes, st>>>(d_in, d_out, n, d->P.pairlut, d->P.lut, status);
+    } else if (d->lit_words && aligned && (reinterpret_cast<uintptr_t>(d_in) & 15) == 0) {
+        const size_t nvec = (n + 15) / 16;
+        const int grid = (int)((nvec + kLitVecPerCta - 1) / kLitVecPerCta);
+#define LIT_CASE(NW, L) case (NW) * 8 + (L): k_lit<NW, L><<<grid, kLitThreads, 0, st>>>(d_in, d_out, n, d->lit, status); break;
+        switch (d->lit_words * 8 + d->lit_len) {
+            LIT_CASE(1, 2) LIT_CASE(1, 3) LIT_CASE(1, 4)
+            LIT_CASE(2, 2) LIT_CASE(2, 3) LIT_CASE(2, 4)
+            LIT_CASE(3, 2) LIT_CASE(3, 3) LIT_CASE(3, 4)
+            LIT_CASE(4, 2) LIT_CASE(4, 3) LIT_CASE(4, 4)
+            default: g_last_error = "internal: literal word form out of range"; return TRRE_E_ARG;
+        }
+#undef LIT_CASE
     } else if (d->gram.entries && aligned && (reinterpret_cast<uintptr_t>(d_in) & 15) == 0 && !std::getenv("TRRE_NO_GRAM")) {
         GramArgs g = d->gram;
         g.in = d_in; g.out = d_out; g.n = n; g.status = status;
@@ -734,6 +760,10 @@ int status_to_rc(uint32_t s) {
     if (s & ST_OBUF) { g_last_error = "error: one match attempt produced more than 1 MiB of output (limit of the GPU DFS executor, not of trre)\n"; return TRRE_E_UNSUPPORTED; }
     if (s & ST_RUNAWAY) {
         g_last_error = "error: the input leads into an epsilon cycle of the transducer (trre_dft recurses for ever there)\n";
+        return TRRE_E_UNSUPPORTED;
+    }
+    if (s & ST_BUDGET) {
+        g_last_error = "error: one match attempt went past 2^26 backtracking steps or 16 MiB of printed paths (limit of the GPU DFS executor, not of trre)\n";
         return TRRE_E_UNSUPPORTED;
     }
     if (s & ST_NOSPACE) { g_last_error = "output buffer too small"; return TRRE_E_NOSPACE; }
@@ -1087,6 +1117,7 @@ int trre_prog_get_info(const trre_prog *p, trre_prog_info *info) {
                       : ((h.flags & PF_LENGTH_PRESERVING) && h.exec_kind == TRRE_EXEC_TABLE) ? TRRE_FAST_INPLACE
                                                         : TRRE_FAST_NONE;
     info->gram_tables = (h.flags & PF_GRAM) ? 1 : 0;
+    info->literal_words = h.lit_words;
     return TRRE_OK;
 }
 

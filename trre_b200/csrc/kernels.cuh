@@ -285,6 +285,7 @@ enum { EXEC_TABLE = 0, EXEC_DFS = 1, EXEC_LAZY = 2 };   // which per-attempt exe
 template <int EXEC, int AMODE = AM_FIRST>
 __device__ __forceinline__ size_t run_record(const DevProg &P, const BtScratch &B, const LazyDev &L, const uint8_t *__restrict__ in,
                                              size_t p, size_t lim, size_t n, Sink &o, uint32_t &status) {
+    if (EXEC == EXEC_DFS) { B.steps = 0; B.printed = 0; }
     if (AMODE == AM_MATCH || AMODE == AM_MATCH_ALL || AMODE == AM_NEWLINES) {
         // match mode: one attempt over the whole record, nothing copied, no newline of its own (trre_nft.c:792-796);
         // trre_dft prints a bare newline per record instead (trre_dft.c:1288-1292)
@@ -298,7 +299,7 @@ __device__ __forceinline__ size_t run_record(const DevProg &P, const BtScratch &
                  : EXEC == EXEC_LAZY ? attempt_lazy(L, in, p, lim, o, status)
                                      : attempt_table(P, in, p, lim, o, status);
         if (EXEC == EXEC_LAZY && k == -2) break;          // a row is missing: this pass is void, leave the record
-        if (status & (ST_STACK | ST_OBUF | ST_DIVERGE | ST_RUNAWAY)) break;   // the scan has failed (the reference exits here):
+        if (status & (ST_STACK | ST_OBUF | ST_DIVERGE | ST_RUNAWAY | ST_BUDGET)) break;   // the scan has failed (the reference exits here):
                                                           // do not grind through the rest of the record
         if (at_end) break;                                // that was the attempt on the empty tail
         if (k > 0) p += (size_t)k;
@@ -324,7 +325,7 @@ k_lines(LineArgs a) {
         if (threadIdx.x == 0 && blockIdx.x == 0) atomicOr(a.status, ST_NOSPACE);
         return;
     }
-    BtScratch B;
+    BtScratch B{};
     if (EXEC == EXEC_DFS) {
         size_t slot = (size_t)blockIdx.x * kLineThreads + threadIdx.x;
         B.stk_s = a.bt_s + slot * a.bt_cap; B.stk_i = a.bt_i + slot * a.bt_cap; B.stk_o = a.bt_o + slot * a.bt_cap;
