@@ -18,7 +18,7 @@ FIELDS = ("magic abi total_bytes flavor exec_kind flags nft_states nft_start dsa
 # header words beyond FIELDS (automaton.hpp BlobHeader): index -> name
 EXT = {28: "swar_n", 29: "swar0", 30: "swar1", 31: "swar2", 32: "swar3", 33: "gram_depth", 34: "gram_entries",
        35: "gram_len", 36: "gram_flags", 37: "off_gbits", 38: "off_gout", 39: "off_gpool", 40: "gpool_bytes",
-       41: "lit_words", 42: "lit_len"}
+       41: "lit_words", 42: "lit_len", 59: "vrun_classes", 23: "off_vent", 25: "off_vpool", 26: "vpool_bytes"}
 EXT.update({43 + k: "lit%d" % k for k in range(16)})
 PF_MATCHABLE, PF_GRAM = 64, 512
 
@@ -42,7 +42,7 @@ class Blob:
         self.sinfo = struct.unpack_from("<%dQ" % ns, raw, h["off_sinfo"]) if ns else ()
         self.pool = raw[h["off_pool"]:h["off_pool"] + h["pool_bytes"]]
         self.nft = [struct.unpack_from("<BBBBii", raw, h["off_nft"] + 12 * k) for k in range(h["nft_states"])]
-        words = struct.unpack_from("<59I", raw, 0)
+        words = struct.unpack_from("<60I", raw, 0)
         for k, name in EXT.items():
             h[name] = words[k]
 
@@ -63,6 +63,29 @@ class Blob:
         return bytes(lut)
 
     # ---- gram tables (k_gram): position-parallel form of the scan over a REGULAR buffer ----------------------
+    def scan_vmap(self, data: bytes) -> bytes:
+        """What k_bmv_* compute (bmv_kernel.cuh): every byte prints the string of its vent entry - except, in the RUN form,
+        a byte whose predecessor has the same non-zero run class (bits 28..31): it is swallowed by the match that started
+        the run.  Regular buffers only."""
+        h = self.h
+        assert h["off_vent"] and data.endswith(b"\n") and b"\0" not in data
+        vent = struct.unpack_from("<256I", self.raw, h["off_vent"])
+        run = h["vrun_classes"] > 0
+        out = bytearray()
+        prev_rc = 0
+        for c in data:
+            e = vent[c]
+            rc = (e >> 28) if run else 0
+            if not (rc and rc == prev_rc):
+                ln = e & 0xFF
+                if ln == 1:
+                    out.append((e >> 8) & 0xFF)
+                elif ln > 1:
+                    off = h["off_vpool"] + (((e >> 16) & 0xFFF) if run else (e >> 16))
+                    out += self.raw[off:off + ln]
+            prev_rc = rc
+        return bytes(out)
+
     def scan_lit(self, data: bytes) -> bytes:
         """What k_lit computes (lit_kernel.cuh): wherever one of the lit_words words stands - position k of a word accepts
         one byte range - its lit_len bytes are replaced by what it prints.  No line structure, no "inside an earlier

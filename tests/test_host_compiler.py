@@ -231,6 +231,43 @@ def test_gram_tables_reproduce_the_scan():
             assert rc == 0 and b.scan_gram(data) == want, (pat, fl, data)
 
 
+def test_run_form_of_variable_byte_maps():
+    """BlobHeader::vrun_classes (k_bmv_*<RUN>): `X+:s` - the first byte decides, the match swallows the rest of the run.
+    Position parallel with one byte of left context; validated here against the oracle through the table interpreter."""
+    rng = random.Random(5)
+    lines = []
+    for _ in range(300):
+        lines.append("".join(rng.choice(["a", "aa", "aaaa", "b", "bb", "7", "42", "2026", " ", "   ", "c", "x1", "d"]) for _k in range(rng.randint(0, 12))))
+    text = ("\n".join(lines) + "\n").encode()
+    yes = [("[0-9]+:#", 1), ("a+:x", 1), ("a+:", 1), ("( +): ", 1), ("a+:xyz|b:", 1), ("a+:x|b+:yy", 2), ("[a-b]+:Q|[0-9]+:#|c:", 2),
+           ("(a|b)+:x", 1), ("a+:x|[0-9]:n", 1)]
+    for expr, classes in yes:
+        p = T.compile(expr, NFT)
+        b = Blob(p.blob())
+        assert p.info["fast_path"] == 3 and b.h["vrun_classes"] == classes, (expr, p.info, b.h["vrun_classes"])
+        rc, want, _ = oracle_run(expr.encode(), text, flavor=NFT)
+        assert rc == 0 and b.scan_vmap(text) == want, expr
+    for expr in ("a:", "a:xy|b:", "a+?:xy", "[0-9]:##"):            # plain variable byte maps: no run class
+        p = T.compile(expr, NFT)
+        b = Blob(p.blob())
+        assert p.info["fast_path"] == 3 and b.h["vrun_classes"] == 0, (expr, p.info)
+        assert b.scan_vmap(text) == oracle_run(expr.encode(), text, flavor=NFT)[1], expr
+    for expr in ("ab*:x", "a+b:x", "(a:x)+", "a*:x", "(ab)+:x", "ab:y|a+:x"):   # the run is not the first byte's own set / prints
+        p = T.compile(expr, NFT)
+        b = Blob(p.blob())
+        assert b.h["vrun_classes"] == 0, (expr, p.info)
+        if p.info["fast_path"] == 3:
+            assert b.scan_vmap(text) == oracle_run(expr.encode(), text, flavor=NFT)[1], expr
+    p = T.compile("a+:x|ab:y", NFT)                                 # the first alternative always wins: a run after all
+    assert Blob(p.blob()).scan_vmap(text) == oracle_run(b"a+:x|ab:y", text, flavor=NFT)[1]
+    for expr in ("[0-9]+:#", "a+:x"):                               # trre_dft: shortest match - a plain byte map
+        p = T.compile(expr, DFT)
+        b = Blob(p.blob())
+        assert b.h["vrun_classes"] == 0
+        if p.info["fast_path"] == 3:
+            assert b.scan_vmap(text) == oracle_run(expr.encode(), text, flavor=DFT)[1], expr
+
+
 def test_literal_word_form():
     """BlobHeader::lit (k_lit): programs whose matches are <= 4 fixed words of 2..4 byte ranges that cannot overlap.  The
     form must reproduce the scan WITHOUT any bookkeeping of earlier matches; whatever could overlap must not get it."""

@@ -397,6 +397,8 @@ struct Program {
     std::vector<uint32_t> eout;      // see BlobHeader::off_eout
     bool vmap = false;               // PF_BYTEMAP_VAR
     std::string vstr[256];           // what an attempt starting with this byte prints (raw copy: the byte itself)
+    uint8_t vrun[256] = {};          // > 0: the match then swallows every following byte of the same run class (X+:s)
+    uint32_t vrun_classes = 0;
 };
 
 class PoolWriter {
@@ -597,22 +599,55 @@ void analyse_and_pack(const std::vector<RawState> &st, const StringPool &sp, int
         if (bm && (P.flags & PF_LENGTH_PRESERVING)) P.exec_kind = TRRE_EXEC_BYTEMAP;
     }
     // variable-length byte map: every attempt is still decided by its first byte, but prints 0..255 bytes
-    // (deletions `a:`, expansions `a:xy`, tr-like maps mixed with them)
+    // (deletions `a:`, expansions `a:xy`, tr-like maps mixed with them).  RUNS (`[0-9]+:#`, `a+:x`, ` +: `): the first byte
+    // decides as well, but the match then greedily swallows every following byte of its own set - the first edge leads to
+    // a state with a pending FINAL whose only edges are unprinting marked self-loops on exactly the bytes that lead there
+    // from the start.  A byte is then covered by an earlier match iff its predecessor is of the same run class: still
+    // position parallel, with one byte of left context (k_bmv_*<RUN>).
     if (P.exec_kind != TRRE_EXEC_BYTEMAP) {
         bool vm = !(st[0].flags & (DSA_S_HAS_FINAL | DSA_S_DIVERGE));
         for (int c = 0; c < 256; ++c) P.vstr[c].assign(1, (char)c);
         size_t pool = 0;
+        std::vector<uint32_t> run_states;
         for (const RawEdge &e : st[0].edges) {
             if (!vm) break;
             const RawState &t = st[e.next];
             bool ok = (t.flags & DSA_S_DECIDED) && (t.flags & DSA_S_HAS_FINAL) && !(t.flags & DSA_S_DIVERGE) &&
                       (flavor == TRRE_FLAVOR_DFT || e.mark);
+            if (!ok && flavor == TRRE_FLAVOR_NFT && e.mark && e.next != 0 && (t.flags & DSA_S_HAS_FINAL) &&
+                !(t.flags & (DSA_S_DECIDED | DSA_S_DIVERGE))) {
+                size_t k = 0;
+                while (k < run_states.size() && run_states[k] != e.next) ++k;
+                if (k == run_states.size()) run_states.push_back(e.next);
+                if (run_states.size() <= 15) { P.vrun[e.byte] = (uint8_t)(k + 1); ok = true; }
+            }
             if (!ok) { vm = false; break; }
             P.vstr[e.byte] = sp.get(e.out_id) + sp.get(t.fin_id);
             if (P.vstr[e.byte].size() > 255) { vm = false; break; }
             if (P.vstr[e.byte].size() > 1) pool += P.vstr[e.byte].size();
         }
-        if (vm && pool < 60000 && !st[0].edges.empty()) P.vmap = true;
+        for (size_t k = 0; k < run_states.size() && vm; ++k) {
+            // the run state loops silently on exactly its own bytes; any other byte (read ahead, not consumed: no mark) ends
+            // the match with what the end of the payload would print
+            const RawState &t = st[run_states[k]];
+            size_t members = 0, loops = 0;
+            for (int c = 0; c < 256; ++c) members += P.vrun[c] == k + 1;
+            for (const RawEdge &e2 : t.edges) {
+                if (P.vrun[e2.byte] == k + 1) {
+                    ++loops;
+                    if (e2.next != run_states[k] || !e2.mark || !sp.get(e2.out_id).empty()) vm = false;
+                } else {
+                    const RawState &t2 = st[e2.next];
+                    if (e2.mark || !(t2.flags & DSA_S_DECIDED) || !(t2.flags & DSA_S_HAS_FINAL) || (t2.flags & DSA_S_DIVERGE) ||
+                        sp.get(e2.out_id) + sp.get(t2.fin_id) != sp.get(t.fin_id))
+                        vm = false;
+                }
+            }
+            if (loops != members) vm = false;
+        }
+        if (!run_states.empty() && pool >= 4000) vm = false;          // run class bits share the entry with the pool offset
+        if (vm && pool < 60000 && !st[0].edges.empty()) { P.vmap = true; P.vrun_classes = (uint32_t)run_states.size(); }
+        else { std::memset(P.vrun, 0, sizeof P.vrun); P.vrun_classes = 0; }
     }
 }
 
@@ -781,7 +816,7 @@ std::vector<uint8_t> assemble(const Program &P, const Nft &g) {
             const std::string &str = P.vstr[c];
             uint32_t ent = (uint32_t)str.size() | ((str.empty() ? 0u : (uint32_t)(uint8_t)str[0]) << 8);
             if (str.size() > 1) { ent |= (uint32_t)vpool.size() << 16; vpool.insert(vpool.end(), str.begin(), str.end()); }
-            vent[c] = ent;
+            vent[c] = ent | ((uint32_t)P.vrun[c] << 28);              // (vrun_classes > 0 implies a pool below 4 KB)
         }
         while (vpool.size() & 15) vpool.push_back(0);
         h.off_vent = (uint32_t)off; off += 1024;
@@ -823,6 +858,7 @@ std::vector<uint8_t> assemble(const Program &P, const Nft &g) {
     h.max_depth = P.max_depth;
     h.start_info = P.sinfo.empty() ? 0 : (uint32_t)(P.sinfo[0] & 0xFFFFFFFFu);
     h.pool_bytes = (uint32_t)P.pool.size();
+    h.vrun_classes = P.vrun_classes;
     if (P.exec_kind == TRRE_EXEC_BYTEMAP) {
         // maximal runs of bytes that move by the same non-zero delta, cut at 0x80 (k_bytemap_swar tests 7-bit ranges)
         std::vector<uint32_t> runs;
@@ -1104,6 +1140,15 @@ bool blob_is_valid(const void *blob, size_t nbytes, std::string *why) {
                 if ((uint64_t)(go[k] & 0xFFFFFu) + ((go[k] >> 20) & 0xFFu) > h.gpool_bytes && go[k]) return bad("gram output reference");
         }
     }
+    if (h.off_vent) {
+        const uint32_t *ve = reinterpret_cast<const uint32_t *>(b + h.off_vent);
+        for (int c = 0; c < 256; ++c) {
+            const uint32_t len = ve[c] & 0xFFu, off = h.vrun_classes ? ((ve[c] >> 16) & 0xFFFu) : (ve[c] >> 16);
+            if (len > 1 && (uint64_t)off + len > h.vpool_bytes) return bad("byte-map string out of range");
+            if (!h.vrun_classes ? false : (ve[c] >> 28) > h.vrun_classes) return bad("run class out of range");
+        }
+    }
+    if (h.vrun_classes > 15 || (h.vrun_classes && (!(h.flags & PF_BYTEMAP_VAR) || h.vpool_bytes > 4096))) return bad("run form");
     if (h.lit_words) {
         if (h.lit_words > 4 || h.lit_len < 2 || h.lit_len > 4 || !(h.flags & PF_GRAM) || !(h.flags & PF_MATCHABLE)) return bad("literal word form");
         for (uint32_t k = 0; k < h.lit_words * h.lit_len; ++k) {

@@ -108,6 +108,10 @@ struct BlobHeader {
     uint32_t lit_words;
     uint32_t lit_len;
     uint32_t lit[16];
+    // (PF_BYTEMAP_VAR) > 0: RUN form - bits 28..31 of a vent entry are the byte's run class (1..15, 0 = none): a match that
+    // starts with such a byte swallows every following byte of the same class ([0-9]+:#), i.e. a byte whose predecessor has
+    // its run class prints nothing; the pool offset of an entry is then 12 bits
+    uint32_t vrun_classes;
 };
 
 struct NftFlat {               // 12 bytes, device layout of trre_nft.c:334-340

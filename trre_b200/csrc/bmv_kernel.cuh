@@ -10,6 +10,11 @@
 //                lane-local prefix + warp scan, bytes placed into the warp's shared-memory window, which
 //                leaves in aligned 16-byte vectors; the < 16 leftover bytes carry into the next tile
 //
+// RUN form (BlobHeader::vrun_classes: `[0-9]+:#`, `a+:x`, ` +: `): a match that starts with a byte of run class r swallows
+// every following byte of class r, so a byte prints nothing iff its predecessor has its own (non-zero) run class - one
+// byte of left context (the neighbour lane's last byte by shuffle, the previous tile's by one load), still no state:
+//   k_bmv_count_run / k_bmv_write<true>
+//
 // NUL bytes / a missing final newline raise ST_IRREGULAR (the general path reruns the buffer).
 #pragma once
 #include <cstdint>
@@ -102,6 +107,68 @@ k_bmv_count(BmvArgs a) {
     }
 }
 
+// the byte before tile position `pos` (lane 0's left context); a buffer starts where a record starts
+__device__ __forceinline__ uint32_t bmv_byte_before(const uint8_t *__restrict__ in, size_t pos) {
+    return pos ? (uint32_t)__ldg(in + pos - 1) : (uint32_t)'\n';
+}
+
+// RUN form: per-byte entries (the pair-length table cannot see the left context), otherwise k_bmv_count
+__global__ void __launch_bounds__(kBmvCountThreads, 1)
+k_bmv_count_run(BmvArgs a) {
+    extern __shared__ __align__(16) uint8_t smem[];
+    uint32_t *vent_s = reinterpret_cast<uint32_t *>(smem);                       // [256][32], bank == lane
+    for (uint32_t k = threadIdx.x; k < 256u * 32u; k += blockDim.x) vent_s[k] = __ldg(a.vent + (k >> 5));
+    __syncthreads();
+    const uint32_t lane = threadIdx.x & 31;
+    const uint32_t *vent_lane = vent_s + lane;
+    const size_t n = a.n;
+    const size_t n_tiles = (n + kBmvTile - 1) / kBmvTile;
+    const size_t warps_total = (size_t)gridDim.x * (blockDim.x / 32);
+    uint32_t nul = 0;
+    for (size_t span = (size_t)blockIdx.x * (blockDim.x / 32) + (threadIdx.x >> 5); span < a.n_spans; span += warps_total) {
+        const size_t t0 = span * a.tiles_per_span;
+        size_t t1 = t0 + a.tiles_per_span;
+        if (t1 > n_tiles) t1 = n_tiles;
+        unsigned long long sum = 0;
+        for (size_t t = t0; t < t1; ++t) {
+            const size_t pos = t * (size_t)kBmvTile + lane * 16;
+            uint4 x = make_uint4(0x0A0A0A0Au, 0x0A0A0A0Au, 0x0A0A0A0Au, 0x0A0A0A0Au);
+            uint32_t valid = 0;
+            if (pos + 16 <= n) { x = ld_stream(reinterpret_cast<const uint4 *>(a.in + pos)); valid = 16; }
+            else if (pos < n) {
+                uint32_t w[4] = {0, 0, 0, 0};
+                valid = (uint32_t)(n - pos);
+                for (uint32_t k = 0; k < valid; ++k) w[k >> 2] |= (uint32_t)a.in[pos + k] << ((k & 3) * 8);
+                for (uint32_t k = valid; k < 16; ++k) w[k >> 2] |= 0x0Au << ((k & 3) * 8);
+                x = make_uint4(w[0], w[1], w[2], w[3]);
+            }
+            nul |= ((x.x - 0x01010101u) & ~x.x) | ((x.y - 0x01010101u) & ~x.y) | ((x.z - 0x01010101u) & ~x.z) | ((x.w - 0x01010101u) & ~x.w);
+            uint32_t before = __shfl_up_sync(0xFFFFFFFFu, x.w >> 24, 1);
+            if (lane == 0) before = bmv_byte_before(a.in, pos);
+            uint32_t rc_prev = vent_lane[before << 5] >> 28;
+            const uint32_t w[4] = {x.x, x.y, x.z, x.w};
+            uint32_t mine = 0;
+#pragma unroll
+            for (int j = 0; j < 16; ++j) {
+                const uint32_t c = (w[j >> 2] >> ((j & 3) * 8)) & 0xFFu;
+                const uint32_t e = vent_lane[c << 5], rc = e >> 28;
+                if ((uint32_t)j < valid && !(rc && rc == rc_prev)) mine += e & 0xFFu;
+                rc_prev = rc;
+            }
+            sum += mine;
+        }
+#pragma unroll
+        for (int d = 16; d; d >>= 1) sum += __shfl_xor_sync(0xFFFFFFFFu, sum, d);
+        if (lane == 0) a.gsum[span] = sum;
+    }
+    nul &= 0x80808080u;
+    if (blockIdx.x == 0 && threadIdx.x == 0 && n && a.in[n - 1] != '\n') nul = 1;
+    if (__any_sync(0xFFFFFFFFu, nul != 0)) {
+        if (lane == 0) atomicOr(a.status, ST_IRREGULAR);
+    }
+}
+
+template <bool RUN>
 __global__ void __launch_bounds__(kBmvWriteThreads)
 k_bmv_write(BmvArgs a) {
     extern __shared__ __align__(16) uint8_t smem[];
@@ -146,10 +213,21 @@ k_bmv_write(BmvArgs a) {
             }
             const uint32_t w[4] = {x.x, x.y, x.z, x.w};
             uint32_t ent[16], mine = 0;
+            uint32_t rc_prev = 0;
+            if (RUN) {
+                uint32_t before = __shfl_up_sync(0xFFFFFFFFu, x.w >> 24, 1);       // (lanes past the end hold zeros: class 0)
+                if (lane == 0) before = bmv_byte_before(a.in, pos);
+                rc_prev = vent_lane[before << 5] >> 28;
+            }
 #pragma unroll
             for (int j = 0; j < 16; ++j) {
                 const uint32_t c = (w[j >> 2] >> ((j & 3) * 8)) & 0xFFu;
                 ent[j] = (uint32_t)j < valid ? vent_lane[c << 5] : 0u;
+                if (RUN) {
+                    const uint32_t rc = ent[j] >> 28;
+                    ent[j] = (rc && rc == rc_prev) ? 0u : (ent[j] & 0x0FFFFFFFu);   // swallowed by the run it continues
+                    rc_prev = rc;
+                }
                 mine += ent[j] & 0xFFu;
             }
             uint32_t incl = mine;

@@ -645,7 +645,8 @@ int launch_bmv(const trre_prog *p, DeviceState *d, const uint8_t *d_in, size_t n
     if (!d->bmv_attr) {
         d->bmv_smem = 256 * 32 * 4 + ((d->vpool_bytes + 15) & ~15u) + (size_t)(kBmvWriteThreads / 32) * kBmvWarpSmem;
         CUDA_TRY(cudaFuncSetAttribute(k_bmv_count, cudaFuncAttributeMaxDynamicSharedMemorySize, kPairLutBytes));
-        CUDA_TRY(cudaFuncSetAttribute(k_bmv_write, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)d->bmv_smem));
+        CUDA_TRY(cudaFuncSetAttribute(k_bmv_write<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)d->bmv_smem));
+        CUDA_TRY(cudaFuncSetAttribute(k_bmv_write<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)d->bmv_smem));
         d->bmv_attr = true;
     }
     BmvArgs a{};
@@ -654,7 +655,8 @@ int launch_bmv(const trre_prog *p, DeviceState *d, const uint8_t *d_in, size_t n
     a.gsum = ws ? ws->gsum : d->d_gsum; a.total = ws ? ws->total : d->d_total; a.status = ws ? ws->status : d->d_status;
     a.n_spans = n_spans; a.tiles_per_span = tiles_per_span;
     if (phase != PH_WRITE) {
-        k_bmv_count<<<d->sm_count, kBmvCountThreads, kPairLutBytes, st>>>(a);
+        if (p->hdr.vrun_classes) k_bmv_count_run<<<d->sm_count, kBmvCountThreads, 256 * 32 * 4, st>>>(a);
+        else k_bmv_count<<<d->sm_count, kBmvCountThreads, kPairLutBytes, st>>>(a);
         k_scan_groups<<<1, kScanThreads, 0, st>>>(a.gsum, n_spans, const_cast<unsigned long long *>(a.total));
         *launches += 2;
         if (!ws) d->counts_kind = 2;
@@ -662,7 +664,8 @@ int launch_bmv(const trre_prog *p, DeviceState *d, const uint8_t *d_in, size_t n
     if (phase != PH_SIZE) {
         const size_t per = kBmvWriteThreads / 32;
         int grid = (int)std::min<size_t>((n_spans + per - 1) / per, (size_t)d->sm_count * 2);
-        k_bmv_write<<<grid < 1 ? 1 : grid, kBmvWriteThreads, d->bmv_smem, st>>>(a);
+        if (p->hdr.vrun_classes) k_bmv_write<true><<<grid < 1 ? 1 : grid, kBmvWriteThreads, d->bmv_smem, st>>>(a);
+        else k_bmv_write<false><<<grid < 1 ? 1 : grid, kBmvWriteThreads, d->bmv_smem, st>>>(a);
         *launches += 1;
     }
     CUDA_TRY(cudaGetLastError());
