@@ -175,7 +175,8 @@ def test_fast_path_classification():
         ("a:", NFT, "bytemap_var"), ("a:xy", DFT, "bytemap_var"), ("[a-c]:|d:DD", NFT, "bytemap_var"),
         ("cat:mouse", NFT, "match_var"), ("(cat):", DFT, "match_var"), ("ab:X|abc:Y|a:Z", NFT, "match_var"),
         ("(a:b)+", NFT, "match"),                       # cyclic: attempts capped at 16 bytes, longer ones fall back
-        ("a+:x", NFT, "match_var"), ("[0-9]+:#", NFT, "match_var"),
+        ("a+:x", NFT, "bytemap_var"), ("[0-9]+:#", NFT, "bytemap_var"),   # RUN form: one byte of left context
+        ("a+b:x", NFT, "match_var"),                    # cyclic, not a run of the first byte's own set
         ("(a:b)*", NFT, "inplace"),                     # length preserving, but matches empty
         (":=", NFT, "none"), ("(a:x)*b|a", NFT, "none"),
     ]
