@@ -64,6 +64,11 @@ WORKLOADS["cfg5"] = ("|".join("%s:%s" % (w, w.upper()) for w in _DICT), 1, 8 * G
 WORKLOADS["del"] = ("a:", 0, 1 * GiB, None, 0.0, False, 0x72726506, "trre")
 WORKLOADS["num"] = ("[0-9]+:#", 0, 1 * GiB, None, 0.0, False, 0x72726508, "trre")
 WORKLOADS["sub"] = ("cat:mouse|dog:d", 0, 1 * GiB, ["cat", "dog", "catdog", "dogcat", "ca", "do", "cot", "dig"], 0.25, False, 0x72726507, "trre")
+# the reference's DFS itself on the GPU (one record per thread): the executor of last resort, and the CLI's -a / -m modes
+_CATS = ["cat", "dog", "catdog", "dogcat", "ca", "do", "cot", "dig"]
+WORKLOADS["dfs"] = ("(a:x)*b|a", 0, 64 * MiB, None, 0.0, False, 0x72726509, "trre")
+WORKLOADS["mode_a"] = ("(cat:dog|dog:cat|cat:CAT)", 0, 64 * MiB, _CATS, 0.25, False, 0x7272650A, "trre", (0, 1))
+WORKLOADS["mode_m"] = ("[a-zA-Z0-9.,; ]*(cat:dog)[a-zA-Z0-9.,; ]*", 0, 16 * MiB, _CATS, 0.25, False, 0x7272650B, "trre", (1, 0))
 
 DESCR = {
     "cfg1": "'cat:dog' over 1 MB ASCII (NFT flavour)",
@@ -74,6 +79,9 @@ DESCR = {
     "num": "'[0-9]+:#' (collapse digit runs: cyclic automaton, per-line kernels) over 1 GiB synthetic ASCII, NFT flavour",
     "sub": "'cat:mouse|dog:d' (matches print more / fewer bytes than they consume) over 1 GiB synthetic text, NFT flavour",
     "del": "'a:' (delete every a; NOT length preserving: count + scan + write path) over 1 GiB synthetic ASCII, NFT flavour",
+    "dfs": "'(a:x)*b|a' (not subsequential: the reference's backtracking DFS on the GPU, one record per thread) over 64 MiB, NFT flavour",
+    "mode_a": "`trre -a '(cat:dog|dog:cat|cat:CAT)'` (every accepting path at every position; DFS executor) over 64 MiB",
+    "mode_m": "`trre -m '[a-zA-Z0-9.,; ]*(cat:dog)[a-zA-Z0-9.,; ]*'` (whole-record match; DFS executor) over 16 MiB",
 }
 METRIC = "input GB/s (scan mode)"
 KERNELS = {0: "k_lines_s<count> + k_scan_groups + k_lines_s<write>", 1: "k_bytemap", 2: "k_match",
@@ -222,7 +230,7 @@ def run_reference(args, name, spec):
         return 0
     sys.path.insert(0, os.path.join(ROOT, "tests"))
     from oracle_util import oracle_run, oracle_synth_text
-    pattern, flavor, nbytes, words, p_hit, lower, seed, refbin = spec
+    pattern, flavor, nbytes, words, p_hit, lower, seed, refbin = spec[:8]
     exe = os.path.join(ROOT, "oracle", "_ref", refbin)
     kind = "reference"
     sample_n = min(nbytes, 64 * MiB)
@@ -272,7 +280,7 @@ def run_reference(args, name, spec):
 
 def cpu_baseline(T, spec):
     """The reference binary on a bounded sample of the same workload (rank 0, N=1 only)."""
-    pattern, flavor, nbytes, words, p_hit, lower, seed, refbin = spec
+    pattern, flavor, nbytes, words, p_hit, lower, seed, refbin = spec[:8]
     exe = os.path.join(ROOT, "oracle", "_ref", refbin)
     # ~10 s of CPU work: trre_dft runs near 50 MB/s whatever the pattern, trre (NFT) 12-165 MB/s
     sample_n = min(nbytes, 256 * MiB if refbin == "trre_dft" else 128 * MiB)
@@ -308,7 +316,7 @@ def cli_end_to_end(T, name, spec):
     """What a user of the drop-in feels: `bin/trre_dft EXPR FILE > /dev/null` on a file in /dev/shm, wall clock of the
     whole process (CUDA context creation, compilation, streaming read -> GPU -> write), next to the reference binary on a
     sample of the same file."""
-    pattern, flavor, nbytes, words, p_hit, lower, seed, refbin = spec
+    pattern, flavor, nbytes, words, p_hit, lower, seed, refbin = spec[:8]
     exe = os.path.join(ROOT, "bin", refbin)
     ref = os.path.join(ROOT, "oracle", "_ref", refbin)
     if not os.access(exe, os.X_OK):
@@ -433,9 +441,12 @@ def measure(ctx, name, nbytes, steps, warmup, collectives=False, tile_rank=None,
     """One workload, device resident: build the input from the rank's synthetic tile, time `steps` scans with CUDA
     events on the launching stream, verify against the reference's hash.  Returns a dict; buffers are released."""
     T, torch = ctx.T, ctx.torch
-    pattern, flavor, _, words, p_hit, lower, seed, refbin = WORKLOADS[name]
+    pattern, flavor, _, words, p_hit, lower, seed, refbin = WORKLOADS[name][:8]
+    mode = WORKLOADS[name][8] if len(WORKLOADS[name]) > 8 else None
     prog = ctx.broadcast_program(pattern, flavor)
-    info = prog.info
+    if mode:
+        prog.set_mode(match=bool(mode[0]), all_=bool(mode[1]))     # (not part of the blob: every rank sets it)
+    info = dict(prog.info, mode=mode)
     rank_tile = ctx.rank if tile_rank is None else tile_rank
     tile_n = min(TILE, nbytes)
     tile = T.synth_text(seed + rank_tile, tile_n, words, p_hit, lower)
@@ -445,7 +456,7 @@ def measure(ctx, name, nbytes, steps, warmup, collectives=False, tile_rank=None,
     d_in = d_tile.repeat(reps) if reps > 1 else d_tile
     if reps > 1:
         del d_tile
-    out_cap = n + 64 if info["length_preserving"] else 2 * n + 64      # expanding programs: room for 2x
+    out_cap = n + 64 if info["length_preserving"] and not mode else 2 * n + 64      # expanding programs: room for 2x
     d_out = torch.empty(out_cap, dtype=torch.uint8, device=ctx.dev)
     sizes = torch.zeros(1, dtype=torch.int64, device=ctx.dev)
     gathered = [torch.zeros_like(sizes) for _ in range(ctx.world)]
@@ -528,6 +539,8 @@ def measure(ctx, name, nbytes, steps, warmup, collectives=False, tile_rank=None,
 
 
 def kernel_label(T, info):
+    if info.get("mode"):
+        return "k_lines<dfs, %s> count + k_scan_groups + k_lines<dfs, %s> write" % (("-m" if info["mode"][0] else "") + ("-a" if info["mode"][1] else ""),) * 2
     if info["exec_kind"] == T.EXEC_BACKTRACK:
         return "k_lines<dfs> count + k_scan_groups + k_lines<dfs> write"
     if info["exec_kind"] == T.EXEC_LAZY:
@@ -646,7 +659,7 @@ def main():
     ctx = Ctx(args)
     T, torch = ctx.T, ctx.torch
     world, rank = ctx.world, ctx.rank
-    pattern, flavor, nbytes, words, p_hit, lower, seed, refbin = spec
+    pattern, flavor, nbytes, words, p_hit, lower, seed, refbin = spec[:8]
 
     # ---- headline: device-resident timing ------------------------------------------------------------------------------
     r = measure(ctx, name, nbytes, args.steps, args.warmup, clocks=True)
@@ -769,6 +782,8 @@ def main():
                 ("cfg5_1GiB", 1 * GiB, False)]
         if world == 1:
             plan += [("cfg3", 8 * GiB, False), ("cfg5_64GiB", 64 * GiB, False)]
+            # off-BASELINE programs: what the other kernel families and the DFS executor do (sizes: WORKLOADS)
+            plan += [(w, WORKLOADS[w][2], False) for w in ("del", "num", "sub", "dfs", "mode_a", "mode_m")]
         else:
             plan += [("cfg4", 8 * GiB, True), ("cfg5_64GiB_split", 64 * GiB // world, True)]
         free = torch.cuda.mem_get_info()[0]

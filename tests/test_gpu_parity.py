@@ -476,6 +476,11 @@ def test_literal_words_kernel(monkeypatch):
                 check(expr, flavor, piece)
             check(expr, flavor, text[:70000] + b"c\xe1t \xff dog\0cat\n" + text[:5000])      # high bytes, a NUL
             check(expr, flavor, text[:70001].rstrip(b"\n"))                                 # no final newline
+    monkeypatch.setenv("TRRE_LIT_NO_EQ", "1")              # plain strings through the range form of k_lit: same bytes
+    for expr in ("cat:dog", "(cat:dog|dog:cat)", "(catd):(DOGC)"):
+        q = T.compile(expr, NFT)
+        assert q.info["literal_words"] and q.scan(text) == oracle_run(expr.encode(), text, flavor=NFT)[1]
+    monkeypatch.delenv("TRRE_LIT_NO_EQ")
     monkeypatch.setenv("TRRE_NO_LIT", "1")                 # the same programs on k_gram: same bytes
     for expr in ("cat:dog", "(cat:dog|dog:cat)"):
         q = T.compile(expr, NFT)

@@ -102,6 +102,7 @@ struct DeviceState {
     SwarMap swar{};                // table-free byte map (n == 0: not of that form)
     LitMap lit{};                  // table-free word matcher (lit_words == 0: not of that form)
     uint32_t lit_words = 0, lit_len = 0;
+    bool lit_eq = false;           // every position of every word accepts exactly one byte
     // TRRE_EXEC_LAZY: device copies of the rows built so far (automaton.hpp, LazyDsa)
     uint64_t *lz_rows = nullptr, *lz_sinfo = nullptr;
     uint8_t *lz_pool = nullptr;
@@ -292,14 +293,20 @@ int get_state(const trre_prog *cp, int device, DeviceState **out) {
     }
     if (h.lit_words >= 1 && h.lit_words <= 4 && h.lit_len >= 2 && h.lit_len <= 4 && (h.flags & PF_MATCHABLE) && !std::getenv("TRRE_NO_LIT")) {
         d->lit_words = h.lit_words; d->lit_len = h.lit_len;
+        d->lit_eq = true;
         for (uint32_t k = 0; k < h.lit_words * h.lit_len; ++k) {
             const uint32_t lo = h.lit[k] & 0xFFu, hi = (h.lit[k] >> 8) & 0xFFu;
+            if (lo != hi) d->lit_eq = false;
+            d->lit.eq[k] = lo * 0x01010101u;
             d->lit.add_lo[k] = (0x80u - (lo & 0x7Fu)) * 0x01010101u;
             d->lit.add_hi[k] = (0x7Fu - (hi & 0x7Fu)) * 0x01010101u;
             d->lit.printed[k / h.lit_len] |= ((h.lit[k] >> 16) & 0xFFu) << (8 * (k % h.lit_len));
-            if (hi >= 0x80u) d->lit_words = 0;                     // k_lit tests 7-bit ranges below 0x80 only: k_gram serves
         }
         d->lit.one = 1;
+        if (std::getenv("TRRE_LIT_NO_EQ")) d->lit_eq = false;     // (test switch: the range form on plain strings)
+        if (!d->lit_eq)                                            // the range form tests 7-bit ranges below 0x80 only: k_gram serves
+            for (uint32_t k = 0; k < h.lit_words * h.lit_len; ++k)
+                if (((h.lit[k] >> 8) & 0xFFu) >= 0x80u) d->lit_words = 0;
     }
     if (h.flags & PF_MATCHABLE) {
         int rc2 = plan_match(h, (size_t)kMatchWarps * kWarpSmem, 108 * 1024, d->sm_count, OP_INPLACE, &d->mp);
@@ -501,7 +508,10 @@ int launch_fast(const trre_prog *p, DeviceState *d, const uint8_t *d_in, size_t 
     } else if (d->lit_words && aligned && (reinterpret_cast<uintptr_t>(d_in) & 15) == 0) {
         const size_t nvec = (n + 15) / 16;
         const int grid = (int)((nvec + kLitVecPerCta - 1) / kLitVecPerCta);
-#define LIT_CASE(NW, L) case (NW) * 8 + (L): k_lit<NW, L><<<grid, kLitThreads, 0, st>>>(d_in, d_out, n, d->lit, status); break;
+#define LIT_CASE(NW, L) case (NW) * 8 + (L):                                                             \
+        if (d->lit_eq) k_lit<NW, L, true><<<grid, kLitThreads, 0, st>>>(d_in, d_out, n, d->lit, status); \
+        else k_lit<NW, L, false><<<grid, kLitThreads, 0, st>>>(d_in, d_out, n, d->lit, status);          \
+        break;
         switch (d->lit_words * 8 + d->lit_len) {
             LIT_CASE(1, 2) LIT_CASE(1, 3) LIT_CASE(1, 4)
             LIT_CASE(2, 2) LIT_CASE(2, 3) LIT_CASE(2, 4)

@@ -32,6 +32,7 @@ constexpr int kLitVecPerCta = (kLitThreads / 32) * kLitIters * kLitVecPerWarpIte
 struct LitMap {
     uint32_t add_lo[16];     // slot = w * L + k; the 7-bit range test of k_bytemap_swar (SwarMap), ranges below 0x80 only
     uint32_t add_hi[16];
+    uint32_t eq[16];         // EQ form (every position accepts exactly one byte): that byte in all four byte lanes
     uint32_t printed[4];     // word w prints these L bytes (byte k = position k)
     uint32_t one;            // 1 at run time: `l * one + c` is an IMAD - the adds of the range tests go to the FMA pipe,
                              // which this kernel leaves idle, instead of the ALU pipe, which bounds it (LOP3 / SHF)
@@ -58,16 +59,23 @@ __device__ __forceinline__ uint4 lit_load(const uint8_t *__restrict__ in, long l
 // and k, whatever the number of words), so the L position masks of a word line up at its start byte and one LOP3 ANDs
 // them.  A start (0x01 in its byte) times the word's printed bytes, as a 64-bit product, IS the printed text at its place:
 // the low half lands in this data word, the high half in the next one (a neighbour lane's for the last word: shuffle).
-template <int NW, int L>
+// EQ (every position of every word accepts exactly one byte - plain strings, the common case): the L comparisons of a word
+// collapse into ONE zero-byte test: byte b of (D0 ^ c0) | (D1 ^ c1) | .. is zero iff the word stands at b (3 LOP3 for the
+// chain, 3 more for an exact zero-byte test) - 6 instructions per word and data word instead of 3 per position.
+template <int NW, int L, bool EQ>
 __device__ __forceinline__ uint4 lit_vec(const uint4 &x, const LitMap &M, uint32_t &nul) {
     uint32_t W[5] = {x.x, x.y, x.z, x.w, 0};
     W[4] = __shfl_down_sync(0xFFFFFFFFu, x.x, 1);                    // the next lane's first data word
-    uint32_t l[L][4];                                                // low 7 bits of every byte, data shifted down by k bytes
+    uint32_t D[L][4];                                                // the data shifted down by k bytes
+    uint32_t l[L][4];                                                // ... its low 7 bits per byte
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
-        nul |= (W[i] - 0x01010101u) & ~W[i];
+        nul |= (EQ ? W[i] * M.one - 0x01010101u : W[i] - 0x01010101u) & ~W[i];   // (EQ: the ALU pipe is the busier one)
 #pragma unroll
-        for (int k = 0; k < L; ++k) l[k][i] = (k == 0 ? W[i] : __funnelshift_r(W[i], W[i + 1], 8 * k)) & 0x7F7F7F7Fu;
+        for (int k = 0; k < L; ++k) {
+            D[k][i] = k == 0 ? W[i] : __funnelshift_r(W[i], W[i + 1], 8 * k);
+            l[k][i] = D[k][i] & 0x7F7F7F7Fu;
+        }
     }
     // bytes >= 0x80 stand in no word: bit 7 of byte b of ok[i] = none of the L bytes from b on has bit 7 set
     uint32_t ok[4];
@@ -84,12 +92,21 @@ __device__ __forceinline__ uint4 lit_vec(const uint4 &x, const LitMap &M, uint32
     for (int w = 0; w < NW; ++w) {
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
-            uint32_t m = ok[i];
+            uint32_t m;
+            if (EQ) {
+                uint32_t t = D[0][i] ^ M.eq[w * L];
 #pragma unroll
-            for (int k = 0; k < L; ++k) {
-                const int s = w * L + k;
-                const uint32_t ge = l[k][i] * M.one + M.add_lo[s], gt = l[k][i] * M.one + M.add_hi[s];
-                m &= ge & ~gt;                                       // bit 7 of a byte: position k of w can stand k bytes on
+                for (int k = 1; k < L; ++k) t |= D[k][i] ^ M.eq[w * L + k];
+                const uint32_t nz = (t & 0x7F7F7F7Fu) * M.one + 0x7F7F7F7Fu;     // bit 7 of a byte: its low 7 bits are not all zero
+                m = ~(nz | t) & 0x80808080u;
+            } else {
+                m = ok[i];
+#pragma unroll
+                for (int k = 0; k < L; ++k) {
+                    const int s = w * L + k;
+                    const uint32_t ge = l[k][i] * M.one + M.add_lo[s], gt = l[k][i] * M.one + M.add_hi[s];
+                    m &= ge & ~gt;                                   // bit 7 of a byte: position k of w can stand k bytes on
+                }
             }
             const uint32_t start = __umulhi(m, 1u << 25);            // 0x01 where word w starts (IMAD.HI: FMA pipe)
             any[i] |= start;
@@ -115,7 +132,7 @@ __device__ __forceinline__ uint4 lit_vec(const uint4 &x, const LitMap &M, uint32
 }
 
 // one CTA's 960 vectors; GUARD = false when all of them (and both halo vectors) lie inside the buffer: no bounds checks
-template <int NW, int L, bool GUARD>
+template <int NW, int L, bool EQ, bool GUARD>
 __device__ __forceinline__ uint32_t lit_cta(const uint8_t *__restrict__ in, uint8_t *__restrict__ out, size_t n, const LitMap &M,
                                             uint32_t lane, long long first) {
     const long long nvec = (long long)((n + 15) / 16);
@@ -131,7 +148,7 @@ __device__ __forceinline__ uint32_t lit_cta(const uint8_t *__restrict__ in, uint
     for (int u = 0; u < kLitIters; ++u) {
         const long long vi = first + u * kLitVecPerWarpIter - 1 + (long long)lane;
         uint32_t nul_v = 0;
-        const uint4 y = lit_vec<NW, L>(x[u], M, nul_v);
+        const uint4 y = lit_vec<NW, L, EQ>(x[u], M, nul_v);
         if (!GUARD) {
             if (stores) { nul |= nul_v; st_stream(reinterpret_cast<uint4 *>(out) + vi, y); }
         } else if (stores && vi < nvec) {
@@ -147,13 +164,13 @@ __device__ __forceinline__ uint32_t lit_cta(const uint8_t *__restrict__ in, uint
     return nul & 0x80808080u;
 }
 
-template <int NW, int L>
-__global__ void __launch_bounds__(kLitThreads)
+template <int NW, int L, bool EQ>
+__global__ void __launch_bounds__(kLitThreads, EQ ? (NW <= 2 ? 6 : 5) : 4)
 k_lit(const uint8_t *__restrict__ in, uint8_t *__restrict__ out, size_t n, const LitMap M, uint32_t *__restrict__ status) {
     const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const long long first = ((long long)blockIdx.x * (kLitThreads / 32) + warp) * (kLitIters * kLitVecPerWarpIter);
     const bool interior = blockIdx.x > 0 && ((size_t)blockIdx.x + 1) * kLitVecPerCta * 16 + 16 <= n;
-    uint32_t nul = interior ? lit_cta<NW, L, false>(in, out, n, M, lane, first) : lit_cta<NW, L, true>(in, out, n, M, lane, first);
+    uint32_t nul = interior ? lit_cta<NW, L, EQ, false>(in, out, n, M, lane, first) : lit_cta<NW, L, EQ, true>(in, out, n, M, lane, first);
     if (blockIdx.x == 0 && threadIdx.x == 0 && n && in[n - 1] != '\n') nul = 1;   // the last record would lose its last byte
     if (__any_sync(0xFFFFFFFFu, nul != 0)) {
         if (lane == 0) atomicOr(status, ST_IRREGULAR);
