@@ -550,6 +550,10 @@ def kernel_label(T, info):
     label = KERNELS[info["fast_path"]]
     if info.get("literal_words") and info["fast_path"] == 2 and os.environ.get("TRRE_NO_LIT") is None:
         return "k_lit"
+    if info.get("literal_words") and info["fast_path"] == 4 and os.environ.get("TRRE_NO_LIT") is None:
+        return "k_litv_count + k_scan_groups + k_bmv_write<lit>"
+    if info["fast_path"] == 3 and info.get("run_classes"):
+        return "k_bmv_count_run + k_scan_groups + k_bmv_write<run>"
     if info.get("gram_tables") and os.environ.get("TRRE_NO_GRAM") is None:
         label = label.replace("k_match", "k_gram_var") if info["fast_path"] == 4 else label.replace("k_match", "k_gram")
     return label

@@ -20,6 +20,7 @@ EXT = {28: "swar_n", 29: "swar0", 30: "swar1", 31: "swar2", 32: "swar3", 33: "gr
        35: "gram_len", 36: "gram_flags", 37: "off_gbits", 38: "off_gout", 39: "off_gpool", 40: "gpool_bytes",
        41: "lit_words", 42: "lit_len", 59: "vrun_classes", 23: "off_vent", 25: "off_vpool", 26: "vpool_bytes"}
 EXT.update({43 + k: "lit%d" % k for k in range(16)})
+EXT.update({60 + k: "lit_out%d" % k for k in range(4)})
 PF_MATCHABLE, PF_GRAM = 64, 512
 
 
@@ -42,7 +43,7 @@ class Blob:
         self.sinfo = struct.unpack_from("<%dQ" % ns, raw, h["off_sinfo"]) if ns else ()
         self.pool = raw[h["off_pool"]:h["off_pool"] + h["pool_bytes"]]
         self.nft = [struct.unpack_from("<BBBBii", raw, h["off_nft"] + 12 * k) for k in range(h["nft_states"])]
-        words = struct.unpack_from("<60I", raw, 0)
+        words = struct.unpack_from("<64I", raw, 0)
         for k, name in EXT.items():
             h[name] = words[k]
 
@@ -84,6 +85,31 @@ class Blob:
                     off = h["off_vpool"] + (((e >> 16) & 0xFFF) if run else (e >> 16))
                     out += self.raw[off:off + ln]
             prev_rc = rc
+        return bytes(out)
+
+    def scan_litv(self, data: bytes) -> bytes:
+        """What k_litv_count / k_bmv_write<BMV_LIT> compute: wherever a word stands its lit_len bytes are replaced by the
+        word's string (gpool, any length); every other byte prints itself.  Regular buffers only."""
+        h = self.h
+        nw, L = h["lit_words"], h["lit_len"]
+        assert nw and data.endswith(b"\n") and b"\0" not in data
+        out = bytearray()
+        p = 0
+        while p < len(data):
+            hit = None
+            if p + L <= len(data):
+                for w in range(nw):
+                    slots = [h["lit%d" % (w * L + k)] for k in range(L)]
+                    if all((s & 0xFF) <= data[p + k] <= ((s >> 8) & 0xFF) for k, s in enumerate(slots)):
+                        hit = w
+            if hit is None:
+                out.append(data[p])
+                p += 1
+            else:
+                o = h["lit_out%d" % hit]
+                off = h["off_gpool"] + (o & 0xFFFFF)
+                out += self.raw[off:off + ((o >> 20) & 0xFF)]
+                p += L
         return bytes(out)
 
     def scan_lit(self, data: bytes) -> bytes:

@@ -504,3 +504,31 @@ def test_run_form_kernels():
             assert rc == 0 and prog.scan(buf) == want, (expr, len(buf))
         check(expr, NFT, data[:3000] + b"a\0a\n" + data[:100])          # a NUL: the general path
         check(expr, NFT, data[:3000].rstrip(b"\n") + b"aa")              # no final newline
+
+
+def test_literal_words_with_outputs_of_any_length():
+    """k_litv_count / k_bmv_write<BMV_LIT> (`cat:mouse|dog:d`): k_lit's comparison, k_bmv's placement.  Matches across lanes
+    (16 B), tiles (512 B) and spans; deletions, expansions; irregular buffers go to the general path."""
+    from patgen import rand_word_expr
+    rng = random.Random(777)
+    served = 0
+    for _ in range(40):
+        pat = rand_word_expr(rng)
+        pat = "|".join(part[:part.index(":(")] + ":(" + rng.choice(["", "Q", "longer output", part[part.index(":(") + 2:-1] + "x"]) + ")"
+                       for part in pat.split("|"))
+        n = rng.choice([1, 2, 15, 16, 17, 33, 511, 512, 513, 1000, 8191, 8192, 8193, 100000, 300000])
+        body = bytes(rng.choice(b"abcdefgh  \n") for _k in range(n))
+        data = body[:-1] + b"\n"
+        for flavor in (NFT, DFT):
+            prog = check(pat, flavor, data)
+            if prog is not None and prog.info["literal_words"] and prog.info["fast_path"] == 4:
+                served += 1
+    assert served > 15, served
+    text = bytes(T.synth_text(0x72726515, 3 << 20, ["cat", "dog", "catdog", "dogcat", "ca", "do", "cot", "dig"], 0.3))
+    for expr in ("cat:mouse|dog:d", "(cat):", "cat:mouse", "(ca):(xyz)|(do):|(ig):(0123456789)", "(catd):(!)", "[c-d]at:(hello)"):
+        prog = check(expr, NFT, text)
+        assert prog.info["literal_words"] >= 1 and prog.info["fast_path"] == 4
+        check(expr, NFT, text[:70000] + b"cat\0dog\n" + text[:5000])
+        check(expr, NFT, text[:70001].rstrip(b"\n"))
+        dense = (b"catdog" * 200 + b"\n") * 50                    # every byte inside a match: tiles that shrink / grow 3x
+        check(expr, NFT, dense)

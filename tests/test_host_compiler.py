@@ -290,7 +290,6 @@ def test_literal_word_form():
           "ab:xy|bc:zw",         # b ends one word and starts another
           "cat:dog|ca:xy",       # what follows `ca` decides
           "a:b|cat:dog",         # two lengths
-          "cat:do",              # not length preserving
           "ab:xy|cd:xy|ef:xy|gh:xy|ij:xy",   # five words
           "c\xe9:xy",            # a byte >= 0x80: still the form (k_lit itself declines it at run time) - checked below
           "[a-c]:x",             # one byte: a byte map
@@ -324,7 +323,7 @@ def test_literal_word_form():
             if not data.endswith(b"\n"):
                 data += b"\n"
             rc, want, _ = oracle_run(pat, data, flavor=fl)
-            assert rc == 0 and b.scan_lit(data) == want, (pat, fl, data)
+            assert rc == 0 and (b.scan_lit(data) if b.h["flags"] & 64 else b.scan_litv(data)) == want, (pat, fl, data)
             got += 1
     from patgen import rand_word_expr
     for _ in range(150):
@@ -339,9 +338,45 @@ def test_literal_word_form():
                 continue
             data = b"\n".join(bytes(rng.choice(b"abcdefgh ") for _k in range(rng.randint(0, 60))) for _l in range(8)) + b"\n"
             rc, want, _ = oracle_run(pat, data, flavor=fl)
-            assert rc == 0 and b.scan_lit(data) == want, (pat, fl, data)
+            assert rc == 0 and (b.scan_lit(data) if b.h["flags"] & 64 else b.scan_litv(data)) == want, (pat, fl, data)
             got += 1
     assert got > 40, got
+
+
+def test_literal_word_form_with_outputs_of_any_length():
+    """BlobHeader::lit_out (k_litv_count / k_bmv_write<BMV_LIT>): the words of `cat:mouse|dog:d` found by comparison, their
+    strings placed by k_bmv's machinery.  The table interpreter against the oracle."""
+    from patgen import rand_word_expr
+    text = bytes(T.synth_text(3, 30000, ["cat", "dog", "catdog", "dogcat", "ca", "do", "cot", "dig", "abab"], 0.4))
+    for expr, nw, L in [("cat:mouse|dog:d", 2, 3), ("(cat):", 1, 3), ("cat:mouse", 1, 3), ("(ca):(xyz)|(do):|(ig):(0123456789)", 3, 2),
+                        ("(catd):(!)", 1, 4), ("[c-d]at:(hello)", 1, 3)]:
+        p = T.compile(expr, NFT)
+        b = Blob(p.blob())
+        assert p.info["fast_path"] == 4 and (b.h["lit_words"], b.h["lit_len"]) == (nw, L), (expr, p.info, b.h["lit_words"], b.h["lit_len"])
+        rc, want, _ = oracle_run(expr.encode(), text, flavor=NFT)
+        assert rc == 0 and b.scan_litv(text) == want, expr
+    for expr in ("aba:x", "ab:xyz|bc:q", "cat:mouse|ca:x", "a:xy|cat:mouse"):       # overlaps / look-ahead / two lengths
+        assert Blob(T.compile(expr, NFT).blob()).h["lit_words"] == 0, expr
+    rng = random.Random(31)
+    got = 0
+    for _ in range(200):
+        pat = rand_word_expr(rng)
+        # give the words outputs of other lengths: (w):(out) -> (w):(out + extra) or (w):()
+        pat = "|".join(part[:part.index(":(")] + ":(" + rng.choice(["", "Q", "longer output", part[part.index(":(") + 2:-1] + "x"]) + ")"
+                       for part in pat.split("|"))
+        for fl in (NFT, DFT):
+            try:
+                p = T.compile(pat, fl)
+            except T.TrreError:
+                continue
+            b = Blob(p.blob())
+            if not b.h["lit_words"] or p.info["fast_path"] != 4:
+                continue
+            data = b"\n".join(bytes(rng.choice(b"abcdefgh ") for _k in range(rng.randint(0, 60))) for _l in range(8)) + b"\n"
+            rc, want, _ = oracle_run(pat.encode(), data, flavor=fl)
+            assert rc == 0 and b.scan_litv(data) == want, (pat, fl, data)
+            got += 1
+    assert got > 30, got
 
 
 def test_gram_tables_of_the_dictionary():

@@ -742,9 +742,10 @@ bool build_grams(const Program &P, GramTables &G) {
 // them is one byte range inside one half of the byte space, every printed byte is non-zero, and no proper suffix of a
 // word is the prefix of a word (then an attempt that starts inside a match can never match, so the set of matches is
 // simply the set of candidates - no chain to resolve).
-bool build_lit(const Program &P, const GramTables &G, uint32_t *n_words, uint32_t *len, uint32_t (&lit)[16]) {
+bool build_lit(const Program &P, const GramTables &G, uint32_t *n_words, uint32_t *len, uint32_t (&lit)[16], uint32_t (&lit_out)[4]) {
     const uint32_t L = G.uniform_len, D = G.depth, ncls = P.n_classes;
-    if (!(G.flags & GRAM_DIRECT_FLAG) || L < 2 || L > 4 || D < L) return false;
+    const bool direct = (G.flags & GRAM_DIRECT_FLAG) != 0;            // else: G.out = pool offset(20) | printed length(8) << 20 | ..
+    if (L < 2 || L > 4 || D < L) return false;
     uint64_t prefixes = 1, completions = 1;
     for (uint32_t i = 0; i < L; ++i) prefixes *= ncls;
     for (uint32_t i = L; i < D; ++i) completions *= ncls;
@@ -767,14 +768,16 @@ bool build_lit(const Program &P, const GramTables &G, uint32_t *n_words, uint32_
         if (w.seen != completions) return false;                      // what follows the word decides whether it matches
     auto cls_at = [&](const Word &w, uint32_t k) { uint32_t v = w.prefix; for (uint32_t i = 0; i < k; ++i) v /= ncls; return v % ncls; };
     for (size_t a = 0; a < words.size(); ++a) {
+        if (!direct && (words[a].out >> 28) + 1 != L) return false;   // (consumed - 1) of the variable form
+        lit_out[a] = direct ? 0u : (words[a].out & 0x0FFFFFFFu);
         for (uint32_t k = 0; k < L; ++k) {
             const uint32_t c = cls_at(words[a], k);
             int lo = -1, hi = -1, members = 0;
             for (int b = 0; b < 256; ++b)
                 if (P.classmap[b] == c) { if (lo < 0) lo = b; hi = b; ++members; }
             if (lo <= 0 || members != hi - lo + 1 || (lo < 0x80) != (hi < 0x80) || (lo <= '\n' && hi >= '\n')) return false;
-            const uint32_t printed = (words[a].out >> (8 * k)) & 0xFFu;
-            if (!printed) return false;
+            const uint32_t printed = direct ? (words[a].out >> (8 * k)) & 0xFFu : 0u;
+            if (direct && !printed) return false;
             lit[a * L + k] = (uint32_t)lo | ((uint32_t)hi << 8) | (printed << 16);
         }
         for (size_t b = 0; b < words.size(); ++b)
@@ -841,7 +844,14 @@ std::vector<uint8_t> assemble(const Program &P, const Nft &g) {
         h.off_gout = (uint32_t)off; off += G.out.size() * 4; off = align16(off);
         h.off_gpool = (uint32_t)off; h.gpool_bytes = (uint32_t)G.pool.size(); off += G.pool.size(); off = align16(off);
         h.gram_depth = G.depth; h.gram_entries = G.entries; h.gram_len = G.uniform_len; h.gram_flags = G.flags;
-        if (matchable && !build_lit(P, G, &h.lit_words, &h.lit_len, h.lit)) { h.lit_words = h.lit_len = 0; std::memset(h.lit, 0, sizeof h.lit); }
+        // the literal word form: length preserving (k_lit) or with outputs of any length (k_litv_*: same comparison,
+        // k_bmv's placement)
+        const bool want_lit = (matchable && (G.flags & GRAM_DIRECT_FLAG)) || (matchable_var && !(G.flags & GRAM_DIRECT_FLAG));
+        if (!want_lit || !build_lit(P, G, &h.lit_words, &h.lit_len, h.lit, h.lit_out)) {
+            h.lit_words = h.lit_len = 0;
+            std::memset(h.lit, 0, sizeof h.lit);
+            std::memset(h.lit_out, 0, sizeof h.lit_out);
+        }
     }
     if (off >= (1ull << 31)) throw PatternError{TRRE_E_UNSUPPORTED, "error: compiled tables exceed 2 GiB\n"};
     h.magic = 0x32425254u;  // "TRB2"
@@ -1150,11 +1160,15 @@ bool blob_is_valid(const void *blob, size_t nbytes, std::string *why) {
     }
     if (h.vrun_classes > 15 || (h.vrun_classes && (!(h.flags & PF_BYTEMAP_VAR) || h.vpool_bytes > 4096))) return bad("run form");
     if (h.lit_words) {
-        if (h.lit_words > 4 || h.lit_len < 2 || h.lit_len > 4 || !(h.flags & PF_GRAM) || !(h.flags & PF_MATCHABLE)) return bad("literal word form");
+        const bool var = (h.flags & PF_MATCHABLE_VAR) != 0;
+        if (h.lit_words > 4 || h.lit_len < 2 || h.lit_len > 4 || !(h.flags & PF_GRAM) || !(h.flags & (PF_MATCHABLE | PF_MATCHABLE_VAR)))
+            return bad("literal word form");
         for (uint32_t k = 0; k < h.lit_words * h.lit_len; ++k) {
             const uint32_t lo = h.lit[k] & 0xFFu, hi = (h.lit[k] >> 8) & 0xFFu;
-            if (!lo || lo > hi || (lo < 0x80u) != (hi < 0x80u) || !((h.lit[k] >> 16) & 0xFFu)) return bad("literal word range");
+            if (!lo || lo > hi || (lo < 0x80u) != (hi < 0x80u) || (!var && !((h.lit[k] >> 16) & 0xFFu))) return bad("literal word range");
         }
+        for (uint32_t w = 0; var && w < h.lit_words; ++w)
+            if ((uint64_t)(h.lit_out[w] & 0xFFFFFu) + ((h.lit_out[w] >> 20) & 0xFFu) > h.gpool_bytes) return bad("literal word output");
     }
     // table contents: every class < n_classes, every next state < dsa_states (or DEAD), every string inside the pool
     const uint8_t *cm = b + h.off_classmap;

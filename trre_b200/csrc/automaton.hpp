@@ -112,6 +112,9 @@ struct BlobHeader {
     // starts with such a byte swallows every following byte of the same class ([0-9]+:#), i.e. a byte whose predecessor has
     // its run class prints nothing; the pool offset of an entry is then 12 bits
     uint32_t vrun_classes;
+    // (lit_words > 0 on a PF_MATCHABLE_VAR program) the words print strings of any length instead: gpool offset(20) |
+    // printed length(8) << 20 per word (k_litv_count / k_litv_write: k_lit's comparison, k_bmv's placement)
+    uint32_t lit_out[4];
 };
 
 struct NftFlat {               // 12 bytes, device layout of trre_nft.c:334-340

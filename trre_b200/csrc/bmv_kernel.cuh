@@ -20,8 +20,53 @@
 #include <cstdint>
 
 #include "kernels.cuh"
+#include "lit_kernel.cuh"
 
 namespace trre {
+
+enum { BMV_PLAIN = 0, BMV_RUN = 1, BMV_LIT = 2 };    // where k_bmv_write takes a position's entry from
+
+// BMV_LIT: the literal word form of a program whose matches print strings of any length (BlobHeader::lit_out:
+// cat:mouse|dog:d): k_lit's comparison finds the word starts, a start prints its word's string, the L - 1 bytes behind it
+// nothing, every other byte itself - k_bmv's placement does the rest.
+struct LitvArgs {
+    LitMap M;
+    uint32_t nw, len, eq;
+    uint32_t ent[4];          // per word: printed length | first byte << 8 | offset into the staged pool << 16
+    int32_t  delta[4];        // printed length - len: what a start adds to the output size
+};
+
+// Word starts in one lane's vector: code[i] byte b = 1 + w where word w starts at byte b of data word i (0: none).
+// W[4] = the data word after the vector.
+__device__ __forceinline__ void litv_starts(const uint32_t (&W)[5], const LitvArgs &A, uint32_t (&code)[4]) {
+#pragma unroll
+    for (int i = 0; i < 4; ++i) code[i] = 0;
+#pragma unroll
+    for (int w = 0; w < 4; ++w) {
+        if ((uint32_t)w >= A.nw) break;
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            uint32_t m = 0x80808080u;
+            if (A.eq) {
+                uint32_t t = 0;
+#pragma unroll
+                for (int k = 0; k < 4; ++k)
+                    if ((uint32_t)k < A.len) t |= (k == 0 ? W[i] : __funnelshift_r(W[i], W[i + 1], 8 * k)) ^ A.M.eq[w * A.len + k];
+                const uint32_t nz = (t & 0x7F7F7F7Fu) + 0x7F7F7F7Fu;
+                m = ~(nz | t) & 0x80808080u;
+            } else {
+#pragma unroll
+                for (int k = 0; k < 4; ++k)
+                    if ((uint32_t)k < A.len) {
+                        const uint32_t d = k == 0 ? W[i] : __funnelshift_r(W[i], W[i + 1], 8 * k);
+                        const uint32_t l = d & 0x7F7F7F7Fu;
+                        m &= (l + A.M.add_lo[w * A.len + k]) & ~(l + A.M.add_hi[w * A.len + k]) & ~d;
+                    }
+            }
+            code[i] += (m >> 7) * (uint32_t)(w + 1);                  // words cannot start at the same byte
+        }
+    }
+}
 
 constexpr int kBmvCountThreads = 1024;
 constexpr int kBmvWriteThreads = 512;
@@ -168,9 +213,91 @@ k_bmv_count_run(BmvArgs a) {
     }
 }
 
-template <bool RUN>
+// the data word after the vector at `pos` (lane 31's right context); what lies past the buffer reads as '\n'
+__device__ __forceinline__ uint32_t bmv_word_after(const uint8_t *__restrict__ in, size_t pos, size_t n) {
+    uint32_t w = 0x0A0A0A0Au;
+    if (pos + 20 <= n) w = __ldg(reinterpret_cast<const uint32_t *>(in + pos + 16));
+    else
+        for (uint32_t k = 0; k < 4 && pos + 16 + k < n; ++k) w = (w & ~(0xFFu << (8 * k))) | ((uint32_t)in[pos + 16 + k] << (8 * k));
+    return w;
+}
+
+// one lane's 16 bytes at `pos` (bytes past the buffer read as '\n') and how many of them exist
+__device__ __forceinline__ uint4 bmv_load(const uint8_t *__restrict__ in, size_t pos, size_t n, uint32_t &valid) {
+    uint4 x = make_uint4(0x0A0A0A0Au, 0x0A0A0A0Au, 0x0A0A0A0Au, 0x0A0A0A0Au);
+    valid = 0;
+    if (pos + 16 <= n) { x = ld_stream(reinterpret_cast<const uint4 *>(in + pos)); valid = 16; }
+    else if (pos < n) {
+        uint32_t w[4] = {x.x, x.y, x.z, x.w};
+        valid = (uint32_t)(n - pos);
+        for (uint32_t k = 0; k < valid; ++k) w[k >> 2] = (w[k >> 2] & ~(0xFFu << ((k & 3) * 8))) | ((uint32_t)in[pos + k] << ((k & 3) * 8));
+        x = make_uint4(w[0], w[1], w[2], w[3]);
+    }
+    return x;
+}
+
+// how far a match that starts in the last L - 1 bytes of a vector reaches into the next one
+__device__ __forceinline__ uint32_t litv_reach(const uint32_t (&code)[4], uint32_t len) {
+    uint32_t reach = 0;
+#pragma unroll
+    for (int b = 1; b < 4; ++b) {                                     // a start at byte 16 - b swallows len - b bytes beyond
+        const uint32_t c = (code[3] >> (8 * (4 - b))) & 0xFFu;
+        if (c && len > (uint32_t)b) reach = len - (uint32_t)b;
+    }
+    return reach;
+}
+
+// BMV_LIT: output size per span = bytes + sum over the word starts of (printed - consumed)
+__global__ void __launch_bounds__(kBmvCountThreads, 1)
+k_litv_count(BmvArgs a, LitvArgs A) {
+    const uint32_t lane = threadIdx.x & 31;
+    const size_t n = a.n;
+    const size_t n_tiles = (n + kBmvTile - 1) / kBmvTile;
+    const size_t warps_total = (size_t)gridDim.x * (blockDim.x / 32);
+    uint32_t nul = 0;
+    for (size_t span = (size_t)blockIdx.x * (blockDim.x / 32) + (threadIdx.x >> 5); span < a.n_spans; span += warps_total) {
+        const size_t t0 = span * a.tiles_per_span;
+        size_t t1 = t0 + a.tiles_per_span;
+        if (t1 > n_tiles) t1 = n_tiles;
+        long long sum = 0;
+        for (size_t t = t0; t < t1; ++t) {
+            const size_t pos = t * (size_t)kBmvTile + lane * 16;
+            uint32_t valid;
+            const uint4 x = bmv_load(a.in, pos, n, valid);
+            nul |= ((x.x - 0x01010101u) & ~x.x) | ((x.y - 0x01010101u) & ~x.y) | ((x.z - 0x01010101u) & ~x.z) | ((x.w - 0x01010101u) & ~x.w);
+            uint32_t W[5] = {x.x, x.y, x.z, x.w, __shfl_down_sync(0xFFFFFFFFu, x.x, 1)};
+            if (lane == 31) W[4] = bmv_word_after(a.in, pos, n);
+            uint32_t code[4];
+            litv_starts(W, A, code);
+            long long mine = (long long)valid;
+#pragma unroll
+            for (int w = 0; w < 4; ++w) {
+                if ((uint32_t)w >= A.nw) break;
+                uint32_t cnt = 0;
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                    const uint32_t z = code[i] ^ ((uint32_t)(w + 1) * 0x01010101u);           // zero bytes = starts of word w
+                    cnt += __popc(~(((z & 0x7F7F7F7Fu) + 0x7F7F7F7Fu) | z) & 0x80808080u);
+                }
+                mine += (long long)cnt * A.delta[w];
+            }
+            sum += mine;
+        }
+#pragma unroll
+        for (int d = 16; d; d >>= 1) sum += __shfl_xor_sync(0xFFFFFFFFu, sum, d);
+        if (lane == 0) a.gsum[span] = (unsigned long long)sum;
+    }
+    nul &= 0x80808080u;
+    if (blockIdx.x == 0 && threadIdx.x == 0 && n && a.in[n - 1] != '\n') nul = 1;
+    if (__any_sync(0xFFFFFFFFu, nul != 0)) {
+        if (lane == 0) atomicOr(a.status, ST_IRREGULAR);
+    }
+}
+
+template <int SRC>
 __global__ void __launch_bounds__(kBmvWriteThreads)
-k_bmv_write(BmvArgs a) {
+k_bmv_write(BmvArgs a, LitvArgs A) {
+    constexpr bool RUN = SRC == BMV_RUN;
     extern __shared__ __align__(16) uint8_t smem[];
     const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     uint32_t *vent_s = reinterpret_cast<uint32_t *>(smem);                       // [256][32], bank == lane
@@ -181,7 +308,8 @@ k_bmv_write(BmvArgs a) {
         if (threadIdx.x == 0 && blockIdx.x == 0) atomicOr(a.status, ST_NOSPACE);
         return;
     }
-    for (uint32_t k = threadIdx.x; k < 256u * 32u; k += blockDim.x) vent_s[k] = __ldg(a.vent + (k >> 5));
+    if (SRC != BMV_LIT)
+        for (uint32_t k = threadIdx.x; k < 256u * 32u; k += blockDim.x) vent_s[k] = __ldg(a.vent + (k >> 5));
     for (uint32_t k = threadIdx.x; k < a.vpool_bytes; k += blockDim.x) vpool_s[k] = __ldg(a.vpool + k);
     __syncthreads();
     const uint32_t *vent_lane = vent_s + lane;
@@ -200,19 +328,43 @@ k_bmv_write(BmvArgs a) {
         uint32_t foreign = (uint32_t)((reinterpret_cast<uintptr_t>(a.out) + span_off) & 15);
         unsigned long long gpos = span_off - foreign;
         uint32_t fill = foreign;                                                   // bytes present in the window
+        uint32_t carry_left = 0;       // BMV_LIT: bytes at the start of the next tile that a match of this tile swallows
+        if (SRC == BMV_LIT && t0 > 0) {                                            // ... and of the tile before the span
+            const size_t before = t0 * (size_t)kBmvTile - 16;                      // its last vector
+            uint32_t valid;
+            const uint4 y = bmv_load(a.in, before, n, valid);
+            const uint32_t W[5] = {y.x, y.y, y.z, y.w, bmv_word_after(a.in, before, n)};
+            uint32_t code[4];
+            litv_starts(W, A, code);
+            carry_left = litv_reach(code, A.len);
+        }
         for (size_t t = t0; t < t1; ++t) {
             const size_t pos = t * (size_t)kBmvTile + lane * 16;
-            uint4 x = make_uint4(0, 0, 0, 0);
-            uint32_t valid = 0;
-            if (pos + 16 <= n) { x = ld_stream(reinterpret_cast<const uint4 *>(a.in + pos)); valid = 16; }
-            else if (pos < n) {
-                uint32_t w[4] = {0, 0, 0, 0};
-                valid = (uint32_t)(n - pos);
-                for (uint32_t k = 0; k < valid; ++k) w[k >> 2] |= (uint32_t)a.in[pos + k] << ((k & 3) * 8);
-                x = make_uint4(w[0], w[1], w[2], w[3]);
-            }
+            uint32_t valid;
+            const uint4 x = bmv_load(a.in, pos, n, valid);
             const uint32_t w[4] = {x.x, x.y, x.z, x.w};
             uint32_t ent[16], mine = 0;
+            if (SRC == BMV_LIT) {
+                uint32_t W[5] = {x.x, x.y, x.z, x.w, __shfl_down_sync(0xFFFFFFFFu, x.x, 1)};
+                if (lane == 31) W[4] = bmv_word_after(a.in, pos, n);
+                uint32_t code[4];
+                litv_starts(W, A, code);
+                // bytes behind a start print nothing - also the next lane's (next tile's: carry_left) first ones
+                const uint32_t reach = litv_reach(code, A.len);
+                uint32_t left = __shfl_up_sync(0xFFFFFFFFu, reach, 1);   // bytes of an earlier match still to swallow
+                if (lane == 0) left = carry_left;
+                carry_left = __shfl_sync(0xFFFFFFFFu, reach, 31);
+#pragma unroll
+                for (int j = 0; j < 16; ++j) {
+                    const uint32_t c = (code[j >> 2] >> ((j & 3) * 8)) & 0xFFu;
+                    uint32_t e = 1u | (((w[j >> 2] >> ((j & 3) * 8)) & 0xFFu) << 8);
+                    if (c) { e = A.ent[c - 1]; left = A.len; }
+                    else if (left) e = 0;
+                    if (left) --left;
+                    ent[j] = (uint32_t)j < valid ? e : 0u;
+                    mine += ent[j] & 0xFFu;
+                }
+            }
             uint32_t rc_prev = 0;
             if (RUN) {
                 uint32_t before = __shfl_up_sync(0xFFFFFFFFu, x.w >> 24, 1);       // (lanes past the end hold zeros: class 0)
@@ -221,6 +373,7 @@ k_bmv_write(BmvArgs a) {
             }
 #pragma unroll
             for (int j = 0; j < 16; ++j) {
+                if (SRC == BMV_LIT) break;
                 const uint32_t c = (w[j >> 2] >> ((j & 3) * 8)) & 0xFFu;
                 ent[j] = (uint32_t)j < valid ? vent_lane[c << 5] : 0u;
                 if (RUN) {

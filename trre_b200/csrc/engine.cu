@@ -103,6 +103,8 @@ struct DeviceState {
     LitMap lit{};                  // table-free word matcher (lit_words == 0: not of that form)
     uint32_t lit_words = 0, lit_len = 0;
     bool lit_eq = false;           // every position of every word accepts exactly one byte
+    LitvArgs litv{};               // the same words printing strings of any length (k_litv_count / k_bmv_write<BMV_LIT>)
+    bool litv_ok = false;
     // TRRE_EXEC_LAZY: device copies of the rows built so far (automaton.hpp, LazyDsa)
     uint64_t *lz_rows = nullptr, *lz_sinfo = nullptr;
     uint8_t *lz_pool = nullptr;
@@ -290,6 +292,29 @@ int get_state(const trre_prog *cp, int device, DeviceState **out) {
             d->swar.half[k] = lo < 0x80u ? 0x80808080u : 0u;
             d->swar.delta[k] = delta;
         }
+    }
+    if (h.lit_words >= 1 && h.lit_words <= 4 && h.lit_len >= 2 && h.lit_len <= 4 && (h.flags & PF_MATCHABLE_VAR) && !(h.flags & PF_MATCHABLE) &&
+        h.gpool_bytes <= 16384 && !std::getenv("TRRE_NO_LIT")) {
+        LitvArgs &A = d->litv;
+        A.nw = h.lit_words; A.len = h.lit_len; A.eq = 1;
+        bool ok = true;
+        for (uint32_t k = 0; k < h.lit_words * h.lit_len; ++k) {
+            const uint32_t lo = h.lit[k] & 0xFFu, hi = (h.lit[k] >> 8) & 0xFFu;
+            if (lo != hi) A.eq = 0;
+            A.M.eq[k] = lo * 0x01010101u;
+            A.M.add_lo[k] = (0x80u - (lo & 0x7Fu)) * 0x01010101u;
+            A.M.add_hi[k] = (0x7Fu - (hi & 0x7Fu)) * 0x01010101u;
+        }
+        for (uint32_t k = 0; k < h.lit_words * h.lit_len && !A.eq; ++k)
+            if (((h.lit[k] >> 8) & 0xFFu) >= 0x80u) ok = false;        // the range form tests 7-bit ranges below 0x80 only
+        A.M.one = 1;
+        const uint8_t *gp = p->blob.data() + h.off_gpool;
+        for (uint32_t w = 0; w < h.lit_words; ++w) {
+            const uint32_t off = h.lit_out[w] & 0xFFFFFu, len = (h.lit_out[w] >> 20) & 0xFFu;
+            A.ent[w] = len | ((len ? (uint32_t)gp[off] : 0u) << 8) | (off << 16);
+            A.delta[w] = (int32_t)len - (int32_t)h.lit_len;
+        }
+        d->litv_ok = ok;
     }
     if (h.lit_words >= 1 && h.lit_words <= 4 && h.lit_len >= 2 && h.lit_len <= 4 && (h.flags & PF_MATCHABLE) && !std::getenv("TRRE_NO_LIT")) {
         d->lit_words = h.lit_words; d->lit_len = h.lit_len;
@@ -640,7 +665,7 @@ int launch_general(const trre_prog *p, DeviceState *d, const uint8_t *d_in, size
 }
 
 bool bmv_capable(const trre_prog *p, const DeviceState *d, const uint8_t *d_in) {
-    return (p->hdr.flags & PF_BYTEMAP_VAR) && d->vent && (reinterpret_cast<uintptr_t>(d_in) & 15) == 0 &&
+    return (((p->hdr.flags & PF_BYTEMAP_VAR) && d->vent) || d->litv_ok) && (reinterpret_cast<uintptr_t>(d_in) & 15) == 0 &&
            !std::getenv("TRRE_NO_BMV");
 }
 
@@ -652,20 +677,25 @@ int launch_bmv(const trre_prog *p, DeviceState *d, const uint8_t *d_in, size_t n
     const size_t tiles_per_span = (n_tiles + n_spans - 1) / n_spans;
     n_spans = (n_tiles + tiles_per_span - 1) / tiles_per_span;
     if (!ws) { int rc = ensure_workspace(d, 0, n_spans, false, 0); if (rc != TRRE_OK) return rc; }
+    const int src = d->litv_ok ? BMV_LIT : p->hdr.vrun_classes ? BMV_RUN : BMV_PLAIN;
+    const uint32_t pool_bytes = src == BMV_LIT ? p->hdr.gpool_bytes : d->vpool_bytes;
     if (!d->bmv_attr) {
-        d->bmv_smem = 256 * 32 * 4 + ((d->vpool_bytes + 15) & ~15u) + (size_t)(kBmvWriteThreads / 32) * kBmvWarpSmem;
+        d->bmv_smem = 256 * 32 * 4 + ((pool_bytes + 15) & ~15u) + (size_t)(kBmvWriteThreads / 32) * kBmvWarpSmem;
         CUDA_TRY(cudaFuncSetAttribute(k_bmv_count, cudaFuncAttributeMaxDynamicSharedMemorySize, kPairLutBytes));
-        CUDA_TRY(cudaFuncSetAttribute(k_bmv_write<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)d->bmv_smem));
-        CUDA_TRY(cudaFuncSetAttribute(k_bmv_write<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)d->bmv_smem));
+        CUDA_TRY(cudaFuncSetAttribute(k_bmv_write<BMV_PLAIN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)d->bmv_smem));
+        CUDA_TRY(cudaFuncSetAttribute(k_bmv_write<BMV_RUN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)d->bmv_smem));
+        CUDA_TRY(cudaFuncSetAttribute(k_bmv_write<BMV_LIT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)d->bmv_smem));
         d->bmv_attr = true;
     }
     BmvArgs a{};
     a.in = d_in; a.out = d_out; a.n = n; a.out_cap = out_cap;
     a.vent = d->vent; a.vpairlen = d->vpairlen; a.vpool = d->vpool; a.vpool_bytes = d->vpool_bytes;
+    if (src == BMV_LIT) { a.vpool = d->d_blob + p->hdr.off_gpool; a.vpool_bytes = p->hdr.gpool_bytes; }
     a.gsum = ws ? ws->gsum : d->d_gsum; a.total = ws ? ws->total : d->d_total; a.status = ws ? ws->status : d->d_status;
     a.n_spans = n_spans; a.tiles_per_span = tiles_per_span;
     if (phase != PH_WRITE) {
-        if (p->hdr.vrun_classes) k_bmv_count_run<<<d->sm_count, kBmvCountThreads, 256 * 32 * 4, st>>>(a);
+        if (src == BMV_LIT) k_litv_count<<<d->sm_count, kBmvCountThreads, 0, st>>>(a, d->litv);
+        else if (src == BMV_RUN) k_bmv_count_run<<<d->sm_count, kBmvCountThreads, 256 * 32 * 4, st>>>(a);
         else k_bmv_count<<<d->sm_count, kBmvCountThreads, kPairLutBytes, st>>>(a);
         k_scan_groups<<<1, kScanThreads, 0, st>>>(a.gsum, n_spans, const_cast<unsigned long long *>(a.total));
         *launches += 2;
@@ -674,8 +704,9 @@ int launch_bmv(const trre_prog *p, DeviceState *d, const uint8_t *d_in, size_t n
     if (phase != PH_SIZE) {
         const size_t per = kBmvWriteThreads / 32;
         int grid = (int)std::min<size_t>((n_spans + per - 1) / per, (size_t)d->sm_count * 2);
-        if (p->hdr.vrun_classes) k_bmv_write<true><<<grid < 1 ? 1 : grid, kBmvWriteThreads, d->bmv_smem, st>>>(a);
-        else k_bmv_write<false><<<grid < 1 ? 1 : grid, kBmvWriteThreads, d->bmv_smem, st>>>(a);
+        if (src == BMV_LIT) k_bmv_write<BMV_LIT><<<grid < 1 ? 1 : grid, kBmvWriteThreads, d->bmv_smem, st>>>(a, d->litv);
+        else if (src == BMV_RUN) k_bmv_write<BMV_RUN><<<grid < 1 ? 1 : grid, kBmvWriteThreads, d->bmv_smem, st>>>(a, d->litv);
+        else k_bmv_write<BMV_PLAIN><<<grid < 1 ? 1 : grid, kBmvWriteThreads, d->bmv_smem, st>>>(a, d->litv);
         *launches += 1;
     }
     CUDA_TRY(cudaGetLastError());
