@@ -30,41 +30,40 @@ enum { BMV_PLAIN = 0, BMV_RUN = 1, BMV_LIT = 2 };    // where k_bmv_write takes 
 // cat:mouse|dog:d): k_lit's comparison finds the word starts, a start prints its word's string, the L - 1 bytes behind it
 // nothing, every other byte itself - k_bmv's placement does the rest.
 struct LitvArgs {
-    LitMap M;
-    uint32_t nw, len, eq;
+    LitMap M;                 // M.eq: the bytes of the words (plain strings only: every position accepts exactly one byte)
     uint32_t ent[4];          // per word: printed length | first byte << 8 | offset into the staged pool << 16
-    int32_t  delta[4];        // printed length - len: what a start adds to the output size
 };
 
-// Word starts in one lane's vector: code[i] byte b = 1 + w where word w starts at byte b of data word i (0: none).
-// W[4] = the data word after the vector.
-__device__ __forceinline__ void litv_starts(const uint32_t (&W)[5], const LitvArgs &A, uint32_t (&code)[4]) {
+// Word starts in one lane's vector (k_lit's EQ comparison): code[i] byte b = 1 + w where word w starts at byte b of data
+// word i (0: none).  W[4] = the data word after the vector.
+template <int NW, int L>
+__device__ __forceinline__ void litv_starts(const uint32_t (&W)[5], const LitMap &M, uint32_t (&code)[4]) {
 #pragma unroll
-    for (int i = 0; i < 4; ++i) code[i] = 0;
+    for (int i = 0; i < 4; ++i) {
+        uint32_t D[L];
 #pragma unroll
-    for (int w = 0; w < 4; ++w) {
-        if ((uint32_t)w >= A.nw) break;
+        for (int k = 0; k < L; ++k) D[k] = k == 0 ? W[i] : __funnelshift_r(W[i], W[i + 1], 8 * k);
+        code[i] = 0;
 #pragma unroll
-        for (int i = 0; i < 4; ++i) {
-            uint32_t m = 0x80808080u;
-            if (A.eq) {
-                uint32_t t = 0;
+        for (int w = 0; w < NW; ++w) {
+            uint32_t t = D[0] ^ M.eq[w * L];
 #pragma unroll
-                for (int k = 0; k < 4; ++k)
-                    if ((uint32_t)k < A.len) t |= (k == 0 ? W[i] : __funnelshift_r(W[i], W[i + 1], 8 * k)) ^ A.M.eq[w * A.len + k];
-                const uint32_t nz = (t & 0x7F7F7F7Fu) + 0x7F7F7F7Fu;
-                m = ~(nz | t) & 0x80808080u;
-            } else {
-#pragma unroll
-                for (int k = 0; k < 4; ++k)
-                    if ((uint32_t)k < A.len) {
-                        const uint32_t d = k == 0 ? W[i] : __funnelshift_r(W[i], W[i + 1], 8 * k);
-                        const uint32_t l = d & 0x7F7F7F7Fu;
-                        m &= (l + A.M.add_lo[w * A.len + k]) & ~(l + A.M.add_hi[w * A.len + k]) & ~d;
-                    }
-            }
-            code[i] += (m >> 7) * (uint32_t)(w + 1);                  // words cannot start at the same byte
+            for (int k = 1; k < L; ++k) t |= D[k] ^ M.eq[w * L + k];
+            const uint32_t nz = (t & 0x7F7F7F7Fu) + 0x7F7F7F7Fu;
+            code[i] += ((~(nz | t) & 0x80808080u) >> 7) * (uint32_t)(w + 1);      // words cannot start at the same byte
         }
+    }
+}
+
+// 0xFF over every byte of a match: low half in the start's own data word, high half in the next one
+template <int L>
+__device__ __forceinline__ void litv_cover(const uint32_t (&code)[4], uint32_t (&lo)[4], uint32_t (&hi)[4]) {
+    constexpr uint32_t kSpan = L == 4 ? 0xFFFFFFFFu : ((1u << (8 * L)) - 1u);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const uint32_t any = (code[i] | (code[i] >> 1) | (code[i] >> 2)) & 0x01010101u;      // codes are 1..4
+        lo[i] = any * kSpan;
+        hi[i] = __umulhi(any, kSpan);
     }
 }
 
@@ -236,18 +235,9 @@ __device__ __forceinline__ uint4 bmv_load(const uint8_t *__restrict__ in, size_t
     return x;
 }
 
-// how far a match that starts in the last L - 1 bytes of a vector reaches into the next one
-__device__ __forceinline__ uint32_t litv_reach(const uint32_t (&code)[4], uint32_t len) {
-    uint32_t reach = 0;
-#pragma unroll
-    for (int b = 1; b < 4; ++b) {                                     // a start at byte 16 - b swallows len - b bytes beyond
-        const uint32_t c = (code[3] >> (8 * (4 - b))) & 0xFFu;
-        if (c && len > (uint32_t)b) reach = len - (uint32_t)b;
-    }
-    return reach;
-}
-
-// BMV_LIT: output size per span = bytes + sum over the word starts of (printed - consumed)
+// BMV_LIT: output size per span, position by position as k_bmv_write<BMV_LIT> will place it: a start counts its word's
+// string, a byte a match covers nothing (also when the match started in the previous lane, tile or span), others 1
+template <int NW, int L>
 __global__ void __launch_bounds__(kBmvCountThreads, 1)
 k_litv_count(BmvArgs a, LitvArgs A) {
     const uint32_t lane = threadIdx.x & 31;
@@ -260,6 +250,17 @@ k_litv_count(BmvArgs a, LitvArgs A) {
         size_t t1 = t0 + a.tiles_per_span;
         if (t1 > n_tiles) t1 = n_tiles;
         long long sum = 0;
+        uint32_t carry_cov = 0;
+        if (t0 > 0 && t0 < t1) {                                                   // a match that reaches in from the tile before the span
+            const size_t before = t0 * (size_t)kBmvTile - 16;
+            uint32_t valid;
+            const uint4 y = bmv_load(a.in, before, n, valid);
+            const uint32_t W[5] = {y.x, y.y, y.z, y.w, bmv_word_after(a.in, before, n)};
+            uint32_t code[4], lo[4], hi[4];
+            litv_starts<NW, L>(W, A.M, code);
+            litv_cover<L>(code, lo, hi);
+            carry_cov = hi[3];
+        }
         for (size_t t = t0; t < t1; ++t) {
             const size_t pos = t * (size_t)kBmvTile + lane * 16;
             uint32_t valid;
@@ -267,19 +268,24 @@ k_litv_count(BmvArgs a, LitvArgs A) {
             nul |= ((x.x - 0x01010101u) & ~x.x) | ((x.y - 0x01010101u) & ~x.y) | ((x.z - 0x01010101u) & ~x.z) | ((x.w - 0x01010101u) & ~x.w);
             uint32_t W[5] = {x.x, x.y, x.z, x.w, __shfl_down_sync(0xFFFFFFFFu, x.x, 1)};
             if (lane == 31) W[4] = bmv_word_after(a.in, pos, n);
-            uint32_t code[4];
-            litv_starts(W, A, code);
-            long long mine = (long long)valid;
+            uint32_t code[4], lo[4], hi[4];
+            litv_starts<NW, L>(W, A.M, code);
+            litv_cover<L>(code, lo, hi);
+            uint32_t cov_in = __shfl_up_sync(0xFFFFFFFFu, hi[3], 1);
+            if (lane == 0) cov_in = carry_cov;
+            carry_cov = __shfl_sync(0xFFFFFFFFu, hi[3], 31);
+            // covered bytes (never padding: '\n' stands in no word)
+            int mine = (int)valid - __popc((lo[0] | cov_in) & 0x01010101u) - __popc((lo[1] | hi[0]) & 0x01010101u) -
+                       __popc((lo[2] | hi[1]) & 0x01010101u) - __popc((lo[3] | hi[2]) & 0x01010101u);
 #pragma unroll
-            for (int w = 0; w < 4; ++w) {
-                if ((uint32_t)w >= A.nw) break;
+            for (int w = 0; w < NW; ++w) {
                 uint32_t cnt = 0;
 #pragma unroll
                 for (int i = 0; i < 4; ++i) {
                     const uint32_t z = code[i] ^ ((uint32_t)(w + 1) * 0x01010101u);           // zero bytes = starts of word w
                     cnt += __popc(~(((z & 0x7F7F7F7Fu) + 0x7F7F7F7Fu) | z) & 0x80808080u);
                 }
-                mine += (long long)cnt * A.delta[w];
+                mine += (int)(cnt * (A.ent[w] & 0xFFu));
             }
             sum += mine;
         }
@@ -294,7 +300,7 @@ k_litv_count(BmvArgs a, LitvArgs A) {
     }
 }
 
-template <int SRC>
+template <int SRC, int NW = 1, int L = 2>
 __global__ void __launch_bounds__(kBmvWriteThreads)
 k_bmv_write(BmvArgs a, LitvArgs A) {
     constexpr bool RUN = SRC == BMV_RUN;
@@ -328,15 +334,16 @@ k_bmv_write(BmvArgs a, LitvArgs A) {
         uint32_t foreign = (uint32_t)((reinterpret_cast<uintptr_t>(a.out) + span_off) & 15);
         unsigned long long gpos = span_off - foreign;
         uint32_t fill = foreign;                                                   // bytes present in the window
-        uint32_t carry_left = 0;       // BMV_LIT: bytes at the start of the next tile that a match of this tile swallows
+        uint32_t carry_cov = 0;        // BMV_LIT: bytes at the start of the next tile that a match of this tile covers
         if (SRC == BMV_LIT && t0 > 0) {                                            // ... and of the tile before the span
             const size_t before = t0 * (size_t)kBmvTile - 16;                      // its last vector
             uint32_t valid;
             const uint4 y = bmv_load(a.in, before, n, valid);
             const uint32_t W[5] = {y.x, y.y, y.z, y.w, bmv_word_after(a.in, before, n)};
-            uint32_t code[4];
-            litv_starts(W, A, code);
-            carry_left = litv_reach(code, A.len);
+            uint32_t code[4], lo[4], hi[4];
+            litv_starts<NW, L>(W, A.M, code);
+            litv_cover<L>(code, lo, hi);
+            carry_cov = hi[3];
         }
         for (size_t t = t0; t < t1; ++t) {
             const size_t pos = t * (size_t)kBmvTile + lane * 16;
@@ -347,20 +354,20 @@ k_bmv_write(BmvArgs a, LitvArgs A) {
             if (SRC == BMV_LIT) {
                 uint32_t W[5] = {x.x, x.y, x.z, x.w, __shfl_down_sync(0xFFFFFFFFu, x.x, 1)};
                 if (lane == 31) W[4] = bmv_word_after(a.in, pos, n);
-                uint32_t code[4];
-                litv_starts(W, A, code);
-                // bytes behind a start print nothing - also the next lane's (next tile's: carry_left) first ones
-                const uint32_t reach = litv_reach(code, A.len);
-                uint32_t left = __shfl_up_sync(0xFFFFFFFFu, reach, 1);   // bytes of an earlier match still to swallow
-                if (lane == 0) left = carry_left;
-                carry_left = __shfl_sync(0xFFFFFFFFu, reach, 31);
+                uint32_t code[4], lo[4], hi[4];
+                litv_starts<NW, L>(W, A.M, code);
+                litv_cover<L>(code, lo, hi);
+                uint32_t cov_in = __shfl_up_sync(0xFFFFFFFFu, hi[3], 1);   // what the previous lane's (tile's) last match covers here
+                if (lane == 0) cov_in = carry_cov;
+                carry_cov = __shfl_sync(0xFFFFFFFFu, hi[3], 31);
+                const uint32_t cov[4] = {lo[0] | cov_in, lo[1] | hi[0], lo[2] | hi[1], lo[3] | hi[2]};
 #pragma unroll
                 for (int j = 0; j < 16; ++j) {
                     const uint32_t c = (code[j >> 2] >> ((j & 3) * 8)) & 0xFFu;
-                    uint32_t e = 1u | (((w[j >> 2] >> ((j & 3) * 8)) & 0xFFu) << 8);
-                    if (c) { e = A.ent[c - 1]; left = A.len; }
-                    else if (left) e = 0;
-                    if (left) --left;
+                    uint32_t e = ((cov[j >> 2] >> ((j & 3) * 8)) & 0xFFu) ? 0u : (1u | (((w[j >> 2] >> ((j & 3) * 8)) & 0xFFu) << 8));
+#pragma unroll
+                    for (int k = 0; k < NW; ++k)
+                        if (c == (uint32_t)(k + 1)) e = A.ent[k];       // a start prints its word's string
                     ent[j] = (uint32_t)j < valid ? e : 0u;
                     mine += ent[j] & 0xFFu;
                 }
@@ -397,6 +404,8 @@ k_bmv_write(BmvArgs a, LitvArgs A) {
                     const uint32_t len = ent[j] & 0xFFu;
                     if (len == 1) s_out[at] = (uint8_t)(ent[j] >> 8);
                     else if (len > 1) {
+                        // (measured and rejected for BMV_LIT: one copy loop per word with a warp-uniform trip count and a
+                        // broadcast source behind a ballot - cat:mouse|dog:d 3.4 -> 5.9 ms per GiB)
                         const uint8_t *src = vpool_s + (ent[j] >> 16);
                         for (uint32_t k = 0; k < len; ++k) s_out[at + k] = src[k];
                     }

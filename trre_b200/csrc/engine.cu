@@ -296,23 +296,17 @@ int get_state(const trre_prog *cp, int device, DeviceState **out) {
     if (h.lit_words >= 1 && h.lit_words <= 4 && h.lit_len >= 2 && h.lit_len <= 4 && (h.flags & PF_MATCHABLE_VAR) && !(h.flags & PF_MATCHABLE) &&
         h.gpool_bytes <= 16384 && !std::getenv("TRRE_NO_LIT")) {
         LitvArgs &A = d->litv;
-        A.nw = h.lit_words; A.len = h.lit_len; A.eq = 1;
         bool ok = true;
         for (uint32_t k = 0; k < h.lit_words * h.lit_len; ++k) {
             const uint32_t lo = h.lit[k] & 0xFFu, hi = (h.lit[k] >> 8) & 0xFFu;
-            if (lo != hi) A.eq = 0;
+            if (lo != hi) ok = false;                                  // plain strings only (a range keeps k_gram_var)
             A.M.eq[k] = lo * 0x01010101u;
-            A.M.add_lo[k] = (0x80u - (lo & 0x7Fu)) * 0x01010101u;
-            A.M.add_hi[k] = (0x7Fu - (hi & 0x7Fu)) * 0x01010101u;
         }
-        for (uint32_t k = 0; k < h.lit_words * h.lit_len && !A.eq; ++k)
-            if (((h.lit[k] >> 8) & 0xFFu) >= 0x80u) ok = false;        // the range form tests 7-bit ranges below 0x80 only
         A.M.one = 1;
         const uint8_t *gp = p->blob.data() + h.off_gpool;
         for (uint32_t w = 0; w < h.lit_words; ++w) {
             const uint32_t off = h.lit_out[w] & 0xFFFFFu, len = (h.lit_out[w] >> 20) & 0xFFu;
             A.ent[w] = len | ((len ? (uint32_t)gp[off] : 0u) << 8) | (off << 16);
-            A.delta[w] = (int32_t)len - (int32_t)h.lit_len;
         }
         d->litv_ok = ok;
     }
@@ -684,7 +678,10 @@ int launch_bmv(const trre_prog *p, DeviceState *d, const uint8_t *d_in, size_t n
         CUDA_TRY(cudaFuncSetAttribute(k_bmv_count, cudaFuncAttributeMaxDynamicSharedMemorySize, kPairLutBytes));
         CUDA_TRY(cudaFuncSetAttribute(k_bmv_write<BMV_PLAIN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)d->bmv_smem));
         CUDA_TRY(cudaFuncSetAttribute(k_bmv_write<BMV_RUN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)d->bmv_smem));
-        CUDA_TRY(cudaFuncSetAttribute(k_bmv_write<BMV_LIT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)d->bmv_smem));
+#define LITV_ATTR(NW, L) CUDA_TRY(cudaFuncSetAttribute(k_bmv_write<BMV_LIT, NW, L>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)d->bmv_smem));
+        LITV_ATTR(1, 2) LITV_ATTR(1, 3) LITV_ATTR(1, 4) LITV_ATTR(2, 2) LITV_ATTR(2, 3) LITV_ATTR(2, 4)
+        LITV_ATTR(3, 2) LITV_ATTR(3, 3) LITV_ATTR(3, 4) LITV_ATTR(4, 2) LITV_ATTR(4, 3) LITV_ATTR(4, 4)
+#undef LITV_ATTR
         d->bmv_attr = true;
     }
     BmvArgs a{};
@@ -694,8 +691,15 @@ int launch_bmv(const trre_prog *p, DeviceState *d, const uint8_t *d_in, size_t n
     a.gsum = ws ? ws->gsum : d->d_gsum; a.total = ws ? ws->total : d->d_total; a.status = ws ? ws->status : d->d_status;
     a.n_spans = n_spans; a.tiles_per_span = tiles_per_span;
     if (phase != PH_WRITE) {
-        if (src == BMV_LIT) k_litv_count<<<d->sm_count, kBmvCountThreads, 0, st>>>(a, d->litv);
-        else if (src == BMV_RUN) k_bmv_count_run<<<d->sm_count, kBmvCountThreads, 256 * 32 * 4, st>>>(a);
+        if (src == BMV_LIT) {
+#define LITV_COUNT(NW, L) case (NW) * 8 + (L): k_litv_count<NW, L><<<d->sm_count, kBmvCountThreads, 0, st>>>(a, d->litv); break;
+            switch (p->hdr.lit_words * 8 + p->hdr.lit_len) {
+                LITV_COUNT(1, 2) LITV_COUNT(1, 3) LITV_COUNT(1, 4) LITV_COUNT(2, 2) LITV_COUNT(2, 3) LITV_COUNT(2, 4)
+                LITV_COUNT(3, 2) LITV_COUNT(3, 3) LITV_COUNT(3, 4) LITV_COUNT(4, 2) LITV_COUNT(4, 3) LITV_COUNT(4, 4)
+                default: g_last_error = "internal: literal word form out of range"; return TRRE_E_ARG;
+            }
+#undef LITV_COUNT
+        } else if (src == BMV_RUN) k_bmv_count_run<<<d->sm_count, kBmvCountThreads, 256 * 32 * 4, st>>>(a);
         else k_bmv_count<<<d->sm_count, kBmvCountThreads, kPairLutBytes, st>>>(a);
         k_scan_groups<<<1, kScanThreads, 0, st>>>(a.gsum, n_spans, const_cast<unsigned long long *>(a.total));
         *launches += 2;
@@ -704,8 +708,15 @@ int launch_bmv(const trre_prog *p, DeviceState *d, const uint8_t *d_in, size_t n
     if (phase != PH_SIZE) {
         const size_t per = kBmvWriteThreads / 32;
         int grid = (int)std::min<size_t>((n_spans + per - 1) / per, (size_t)d->sm_count * 2);
-        if (src == BMV_LIT) k_bmv_write<BMV_LIT><<<grid < 1 ? 1 : grid, kBmvWriteThreads, d->bmv_smem, st>>>(a, d->litv);
-        else if (src == BMV_RUN) k_bmv_write<BMV_RUN><<<grid < 1 ? 1 : grid, kBmvWriteThreads, d->bmv_smem, st>>>(a, d->litv);
+        if (src == BMV_LIT) {
+#define LITV_WRITE(NW, L) case (NW) * 8 + (L): k_bmv_write<BMV_LIT, NW, L><<<grid < 1 ? 1 : grid, kBmvWriteThreads, d->bmv_smem, st>>>(a, d->litv); break;
+            switch (p->hdr.lit_words * 8 + p->hdr.lit_len) {
+                LITV_WRITE(1, 2) LITV_WRITE(1, 3) LITV_WRITE(1, 4) LITV_WRITE(2, 2) LITV_WRITE(2, 3) LITV_WRITE(2, 4)
+                LITV_WRITE(3, 2) LITV_WRITE(3, 3) LITV_WRITE(3, 4) LITV_WRITE(4, 2) LITV_WRITE(4, 3) LITV_WRITE(4, 4)
+                default: g_last_error = "internal: literal word form out of range"; return TRRE_E_ARG;
+            }
+#undef LITV_WRITE
+        } else if (src == BMV_RUN) k_bmv_write<BMV_RUN><<<grid < 1 ? 1 : grid, kBmvWriteThreads, d->bmv_smem, st>>>(a, d->litv);
         else k_bmv_write<BMV_PLAIN><<<grid < 1 ? 1 : grid, kBmvWriteThreads, d->bmv_smem, st>>>(a, d->litv);
         *launches += 1;
     }
