@@ -14,5 +14,4 @@ print('cli', d.get('cli_e2e')); print('cpu', d.get('cpu_baseline'))
 for k,v in (d.get('others') or {}).items(): print(k, {a:(round(b,4) if isinstance(b,float) else b) for a,b in v.items() if a not in ('pattern','verified_how')})
 PY
 ncu --metrics gpu__time_duration.sum --clock-control none -c 120 --csv --log-file gpurun_out/launches_$TAG.csv python bench.py --steps 5 --warmup 3 --no-cpu-baseline --e2e-steps 0 --no-others > /dev/null 2>&1
-for w in num sub del; do python bench.py --workload $w --steps 5 --warmup 3 --no-cpu-baseline --e2e-steps 1 2>/dev/null | tail -1 > gpurun_out/bench_${w}_$TAG.json; python -c "
-import json,sys; d=json.loads(open('gpurun_out/bench_${w}_$TAG.json').read()); print('$w', round(d['value'],1), round(d['roofline']['frac'],4), d['config_detail']['exec'], d['verified'], 'e2e', round(d['e2e']['value'],1))"; done
+# (the off-BASELINE workloads - del, num, sub, dfs, mode_a, mode_m - are part of `others` of the default line since r2)
