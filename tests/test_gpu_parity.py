@@ -181,6 +181,27 @@ def test_dictionary_on_gpu():
         assert rc == 0 and prog.scan(data) == want, flavor
 
 
+def test_dictionary_outputs_by_delta_and_by_table(monkeypatch):
+    """word:WORD prints the matched bytes moved by one constant: k_gram<.., 2> adds it under a byte mask spread from the
+    real-start bits (no output table).  Same bytes as the table emission (TRRE_GRAM_NO_MAP) and as the oracle; words back to
+    back, across lanes and tiles, 3- and 2-letter dictionaries (other match lengths)."""
+    rng = random.Random(11)
+    for L, nwords in ((4, 1500), (3, 900), (2, 300)):
+        words = set()
+        while len(words) < nwords:
+            words.add("".join(rng.choice("abcdefghijklmnopqrstuvwxyz") for _ in range(L)))
+        words = sorted(words)
+        expr = "|".join("%s:%s" % (w, w.upper()) for w in words)
+        dense = ("".join(rng.choice(words) for _ in range(3000)) + "\n").encode() * 3          # nothing but matches
+        text = bytes(T.synth_text(0x72726517, 2 << 20, words, 0.5, True)) + dense
+        want = oracle_run(expr.encode(), text, flavor=DFT)[1]
+        prog = T.compile(expr, DFT)
+        assert prog.info["gram_tables"] and prog.scan(text) == want, L
+        monkeypatch.setenv("TRRE_GRAM_NO_MAP", "1")
+        assert T.compile(expr, DFT).scan(text) == want, L
+        monkeypatch.delenv("TRRE_GRAM_NO_MAP")
+
+
 # ---- the general path: shared-memory staged kernels against the plain ones and the oracle -----------
 
 @pytest.mark.parametrize("expr,flavor", [("a:", NFT), (":=", NFT), ("a:xy", DFT), ("a+:x", NFT), ("(cat)*:dog", NFT),

@@ -391,7 +391,13 @@ def test_gram_tables_of_the_dictionary():
     assert b.h["flags"] & 512 and b.h["gram_depth"] == 4 and b.h["gram_len"] == 4 and b.h["gram_flags"] & 1
     assert b.h["gram_entries"] == b.ncls ** 4
     text = bytes(T.synth_text(12, 6000, words[:80], 0.3, True))
-    assert b.scan_gram(text) == oracle_run(expr.encode(), text, flavor=DFT)[1]
+    want = oracle_run(expr.encode(), text, flavor=DFT)[1]
+    assert b.scan_gram(text) == want
+    # word:WORD prints the matched bytes moved by one constant: k_gram's delta emission needs no output table
+    assert b.h["gram_flags"] & 2 and b.h["gram_delta"] == 0xE0
+    assert all(o == i or o == (i + 0xE0) & 0xFF for i, o in zip(text, want))
+    for other in ("|".join("%s:%s" % (w, w[::-1]) for w in words[:600]), "|".join("%s:%s" % (w, w.upper()[:3] + "x") for w in words[:600])):
+        assert not Blob(T.compile(other, DFT).blob()).h["gram_flags"] & 2           # no common delta
 
 
 def test_lazy_tables_for_automata_too_large_to_build_ahead():

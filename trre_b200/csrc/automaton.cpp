@@ -654,8 +654,9 @@ void analyse_and_pack(const std::vector<RawState> &st, const StringPool &sp, int
 // Gram tables (k_gram): the outcome of an attempt of an acyclic program is a function of the byte classes of its first
 // D = max_depth bytes.  Walk every combination here, once: bit = the attempt matches; out = what it prints, how much
 // it consumes.  Mirrors walk_from() in match_kernel.cuh (itself the table form of infer_dft / infer_backtrack).
+constexpr uint32_t GRAM_MAPDELTA_FLAG = 2u; // = GRAM_MAPDELTA in gram_kernel.cuh
 struct GramTables {
-    uint32_t depth = 0, entries = 0, uniform_len = 0, flags = 0;
+    uint32_t depth = 0, entries = 0, uniform_len = 0, flags = 0, delta = 0;
     std::vector<uint32_t> bits, out;
     std::vector<uint8_t> pool;
 };
@@ -712,6 +713,31 @@ bool build_grams(const Program &P, GramTables &G) {
     G.uniform_len = uniform ? common : 0;
     const bool direct = uniform && all_short && lp;
     if (direct) G.flags |= GRAM_DIRECT_FLAG;
+    if (direct) {
+        // do all matches print their own bytes moved by ONE constant (word:WORD dictionaries: -32)?  Then the device needs
+        // no output table at all: matched bytes + delta (k_gram REG = 2)
+        int single[256];
+        for (uint32_t c = 0; c < ncls; ++c) single[c] = -1;
+        {
+            int members[256] = {};
+            for (int b = 0; b < 256; ++b) { ++members[P.classmap[b]]; single[P.classmap[b]] = b; }
+            for (uint32_t c = 0; c < ncls; ++c) if (members[c] != 1) single[c] = -1;
+        }
+        bool map = true;
+        int delta = -1;
+        for (uint64_t idx = 0; idx < entries && map; ++idx) {
+            if (!consumed[idx]) continue;
+            uint64_t rest = idx;
+            for (uint32_t k = 0; k < common; ++k) {
+                const int b = single[rest % ncls];
+                rest /= ncls;
+                if (b < 0) { map = false; break; }
+                const int d = ((int)(uint8_t)strs[idx][k] - b) & 0xFF;
+                if (delta < 0) delta = d; else if (delta != d) { map = false; break; }
+            }
+        }
+        if (map && delta > 0) { G.flags |= GRAM_MAPDELTA_FLAG; G.delta = (uint32_t)delta; }
+    }
     for (uint64_t idx = 0; idx < entries; ++idx) {
         if (!consumed[idx]) continue;
         const std::string &o = strs[idx];
@@ -844,6 +870,7 @@ std::vector<uint8_t> assemble(const Program &P, const Nft &g) {
         h.off_gout = (uint32_t)off; off += G.out.size() * 4; off = align16(off);
         h.off_gpool = (uint32_t)off; h.gpool_bytes = (uint32_t)G.pool.size(); off += G.pool.size(); off = align16(off);
         h.gram_depth = G.depth; h.gram_entries = G.entries; h.gram_len = G.uniform_len; h.gram_flags = G.flags;
+        h.gram_delta = G.delta;
         // the literal word form: length preserving (k_lit) or with outputs of any length (k_litv_*: same comparison,
         // k_bmv's placement)
         const bool want_lit = (matchable && (G.flags & GRAM_DIRECT_FLAG)) || (matchable_var && !(G.flags & GRAM_DIRECT_FLAG));

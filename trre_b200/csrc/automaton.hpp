@@ -115,6 +115,9 @@ struct BlobHeader {
     // (lit_words > 0 on a PF_MATCHABLE_VAR program) the words print strings of any length instead: gpool offset(20) |
     // printed length(8) << 20 per word (k_litv_count / k_litv_write: k_lit's comparison, k_bmv's placement)
     uint32_t lit_out[4];
+    // (gram_flags & 2) every match prints its own bytes moved by this constant mod 256 (word:WORD dictionaries: 0xE0):
+    // k_gram then needs no output table
+    uint32_t gram_delta;
 };
 
 struct NftFlat {               // 12 bytes, device layout of trre_nft.c:334-340

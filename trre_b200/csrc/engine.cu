@@ -214,9 +214,9 @@ const void *gram_var_kernel(uint32_t depth, bool small, int op) {
 #undef GV
 }
 
-const void *gram_kernel(uint32_t depth, bool small, bool reg) {
-#define GK(D) (small ? (reg ? (const void *)k_gram<D, true, true> : (const void *)k_gram<D, true, false>) \
-                     : (reg ? (const void *)k_gram<D, false, true> : (const void *)k_gram<D, false, false>))
+const void *gram_kernel(uint32_t depth, bool small, int reg) {      // reg: 0 staged, 1 registers, 2 registers + delta outputs
+#define GK(D) (small ? (reg ? (const void *)k_gram<D, true, 1> : (const void *)k_gram<D, true, 0>) \
+                     : (reg == 2 ? (const void *)k_gram<D, false, 2> : reg ? (const void *)k_gram<D, false, 1> : (const void *)k_gram<D, false, 0>))
     switch (depth) {
         case 1: return GK(1);
         case 2: return GK(2);
@@ -357,7 +357,9 @@ int get_state(const trre_prog *cp, int device, DeviceState **out) {
         d->gram_smem = 256 * 32 * 4 + (d->gram_small ? (size_t)h.gram_entries * 128 : (size_t)((words + 3) & ~3u) * 4) +
                        (g.gout_in_smem ? (size_t)((h.gram_entries + 3) & ~3u) * 4 : 0) +
                        (g.pool_in_smem ? ((h.gpool_bytes + 15) & ~15u) : 0) + (reg ? 8 * 256 * 2 : (size_t)kGramWarps * kGramWarpSmem);
-        d->gram_fn = gram_kernel(h.gram_depth, d->gram_small, reg);
+        const bool map = reg && !d->gram_small && (h.gram_flags & GRAM_MAPDELTA) && !std::getenv("TRRE_GRAM_NO_MAP");
+        g.map_delta = h.gram_delta & 0xFFu;
+        d->gram_fn = gram_kernel(h.gram_depth, d->gram_small, map ? 2 : reg ? 1 : 0);
         if (d->gram_fn && d->gram_smem <= 220 * 1024) {
             CUDA_TRY(cudaFuncSetAttribute(d->gram_fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)d->gram_smem));
         } else {

@@ -38,6 +38,7 @@ constexpr uint32_t kGramSmallEntries = 512;          // up to here: one u32 per 
 
 enum : uint32_t {
     GRAM_DIRECT = 1u,       // gout holds the output bytes themselves (every match prints <= 4 bytes, one common length)
+    GRAM_MAPDELTA = 2u,     // ... and they are the matched bytes moved by ONE constant (word:WORD dictionaries): no gout at all
 };
 
 struct GramArgs {
@@ -58,6 +59,7 @@ struct GramArgs {
     uint32_t gout_in_smem;
     uint32_t pool_in_smem;
     uint32_t len_mask;           // REG form: 0xFF in the low uniform_len bytes
+    uint32_t map_delta;          // REG form 2 (GRAM_MAPDELTA): added mod 256 to every matched byte
 };
 
 struct GramTables {
@@ -182,7 +184,10 @@ __device__ __forceinline__ uint32_t bitsel(uint32_t a, uint32_t b, uint32_t m) {
 // shared-memory staging at all.  After the chain is resolved the real matches are merged into the lane's four output
 // words position by position (compile-time byte offsets, predicated on the `real` bit); the up to three bytes a match
 // at positions 13..15 prints past the lane's end travel to the next lane (next tile: carry_sp / carry_sm) by shuffle.
-template <int D, bool SMALL, bool STORE>
+// MAP (GRAM_MAPDELTA): what a match prints is its own bytes plus a constant - the emission is SWAR arithmetic on the lane's
+// four words under a byte mask spread from the real-start bits (no output table, no load per match: on the 10 000-word
+// dictionary that load, from a 2.1 MB table in L2, was the top stall).
+template <int D, bool SMALL, bool STORE, bool MAP>
 __device__ __forceinline__ void gram_tile_reg(const GramArgs &a, const GramTables &T, size_t base, bool full, uint4 x, uint4 x_next,
                                               uint32_t lane, uint32_t first_valid, uint32_t &carry_e, uint32_t &carry_sp,
                                               uint32_t &carry_sm, uint32_t &nul_acc) {
@@ -195,6 +200,32 @@ __device__ __forceinline__ void gram_tile_reg(const GramArgs &a, const GramTable
     const uint32_t M = a.len_mask;                                  // 0xFF in the low L bytes
     uint32_t o[5] = {x.x, x.y, x.z, x.w, 0u};
     uint32_t sm = 0;                                                // which bytes of o[4] (positions 16..19) are written
+    if (MAP) {
+        const uint32_t L = a.uniform_len;
+        uint32_t cov = f.real;                                      // bit p: position p lies inside a real match
+        if (L > 1) cov |= f.real << 1;
+        if (L > 2) cov |= f.real << 2;
+        if (L > 3) cov |= f.real << 3;
+        uint32_t cov_in = __shfl_up_sync(0xFFFFFFFFu, cov >> 16, 1);    // what the previous lane's last match covers here
+        if (lane == 0) cov_in = carry_sm;
+        carry_sm = __shfl_sync(0xFFFFFFFFu, cov >> 16, 31);
+        cov |= cov_in;
+#pragma unroll
+        for (int w = 0; w < 4; ++w) {
+            const uint32_t m01 = (((cov >> (4 * w)) & 0xFu) * 0x00204081u) & 0x01010101u;   // 4 bits -> 0x01 in 4 bytes
+            const uint32_t d = m01 * a.map_delta;
+            o[w] = ((o[w] & 0x7F7F7F7Fu) + (d & 0x7F7F7F7Fu)) ^ ((o[w] ^ d) & 0x80808080u);   // byte-wise add, carries cut
+        }
+        if (STORE) {
+            const size_t my = base + (size_t)lane * 16;
+            if (full || my + 16 <= a.n) {
+                *reinterpret_cast<uint4 *>(a.out + my) = make_uint4(o[0], o[1], o[2], o[3]);
+            } else if (my < a.n) {
+                for (int k = 0; k < 16 && my + k < a.n; ++k) a.out[my + k] = (uint8_t)(o[k >> 2] >> ((k & 3) * 8));
+            }
+        }
+        carry_e = __shfl_sync(0xFFFFFFFFu, f.e_out, 31);
+    } else {
 #pragma unroll
     for (int j = 0; j < 16; ++j) {
         if (f.real & (1u << j)) {
@@ -224,6 +255,7 @@ __device__ __forceinline__ void gram_tile_reg(const GramArgs &a, const GramTable
     carry_e = __shfl_sync(0xFFFFFFFFu, f.e_out, 31);
     carry_sp = __shfl_sync(0xFFFFFFFFu, o[4], 31);
     carry_sm = __shfl_sync(0xFFFFFFFFu, sm, 31);
+    }
 }
 
 // The general form: tile staged in shared memory, real matches write their span there (any length, pool strings).
@@ -399,9 +431,11 @@ k_gram_var(MatchArgs m, GramArgs g) {
     span_loop<OP>(m, GramFE<D, SMALL>{g, T}, cur + warp * kVarWarpSmem, lane);
 }
 
-template <int D, bool SMALL, bool REG>
+template <int D, bool SMALL, int REGF>       // REGF: 0 staged tile, 1 tile in registers, 2 ... and outputs by a constant delta
 __global__ void __launch_bounds__(kGramThreads, 1)
 k_gram(GramArgs a) {
+    constexpr bool REG = REGF != 0;
+    constexpr bool MAP = REGF == 2;
     extern __shared__ __align__(16) uint8_t smem[];
     const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     GramTables T;
@@ -454,8 +488,8 @@ k_gram(GramArgs a) {
             const bool full = base + 2 * (size_t)kTile <= n;
             const uint4 x_next = full ? ldg_vec(a.in + base + kTile + lane * 16) : load_padded(a.in, base + kTile + lane * 16, n);
             if (REG) {
-                if (t < t0) gram_tile_reg<D, SMALL, false>(a, T, base, full, x, x_next, lane, first_valid, carry_e, carry_sp, carry_sm, nul_acc);
-                else        gram_tile_reg<D, SMALL, true>(a, T, base, full, x, x_next, lane, first_valid, carry_e, carry_sp, carry_sm, nul_acc);
+                if (t < t0) gram_tile_reg<D, SMALL, false, MAP>(a, T, base, full, x, x_next, lane, first_valid, carry_e, carry_sp, carry_sm, nul_acc);
+                else        gram_tile_reg<D, SMALL, true, MAP>(a, T, base, full, x, x_next, lane, first_valid, carry_e, carry_sp, carry_sm, nul_acc);
             } else {
                 if (t < t0) gram_tile<D, SMALL, false>(a, T, s_in, s_out, base, full, x, x_next, lane, first_valid, carry_e, carry_halo, nul_acc);
                 else        gram_tile<D, SMALL, true>(a, T, s_in, s_out, base, full, x, x_next, lane, first_valid, carry_e, carry_halo, nul_acc);
