@@ -540,7 +540,8 @@ def measure(ctx, name, nbytes, steps, warmup, collectives=False, tile_rank=None,
 
 def kernel_label(T, info):
     if info.get("mode"):
-        return "k_lines<dfs, %s> count + k_scan_groups + k_lines<dfs, %s> write" % (("-m" if info["mode"][0] else "") + ("-a" if info["mode"][1] else ""),) * 2
+        flags = ("-m" if info["mode"][0] else "") + ("-a" if info["mode"][1] else "")
+        return "k_lines<dfs, %s> count + k_scan_groups + k_lines<dfs, %s> write" % (flags, flags)
     if info["exec_kind"] == T.EXEC_BACKTRACK:
         return "k_lines<dfs> count + k_scan_groups + k_lines<dfs> write"
     if info["exec_kind"] == T.EXEC_LAZY:
@@ -792,7 +793,7 @@ def main():
             plan += [("cfg4", 8 * GiB, True), ("cfg5_64GiB_split", 64 * GiB // world, True)]
         free = torch.cuda.mem_get_info()[0]
         for label, per_gpu, coll in plan:
-            wl = label.split("_")[0]
+            wl = label if label in WORKLOADS else label.split("_")[0]
             if 2 * per_gpu + (1 << 30) > free:
                 others[label] = {"skipped": "needs %d GiB of HBM" % ((2 * per_gpu) >> 30)}
                 continue
