@@ -826,6 +826,10 @@ def main():
                 tj = json.load(f)
             traffic = tj.get("dram_bytes_per_launch")
             traffic_src = tj.get("source", "ncu --set full capture committed under profiles/ (not measured in this run)")
+            cap_n = tj.get("bytes_per_launch_input")
+            if traffic and cap_n and cap_n != n:                  # captured on another size: the traffic is linear in it
+                traffic = traffic * n / cap_n
+                traffic_src += " - scaled from a %d MiB capture" % (cap_n // MiB)
         except Exception:
             pass
     kernel = kernel_label(T, info)
