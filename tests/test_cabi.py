@@ -68,6 +68,20 @@ def test_scan_fails_loudly_without_a_gpu():
     assert ei.value.code == 3 and "no CPU fallback" in str(ei.value)
 
 
+def test_set_mode_is_host_state_of_the_program_not_of_the_blob():
+    """trre_prog_set_mode (the CLI's -m / -a, trre_nft.c:728-741): accepted without a GPU; trre_dft -a is the reference's
+    "Not supported yet" (trre_dft.c:1226); a program rebuilt from a broadcast blob starts in scan mode and takes the call."""
+    p = T.compile("cat:dog", NFT)
+    assert p.set_mode(match=True, all_=True) is p and p.set_mode() is p
+    q = T.from_blob(p.blob())
+    q.set_mode(match=False, all_=True)
+    d = T.compile("cat:dog", DFT)
+    d.set_mode(match=True)
+    with pytest.raises(T.TrreError) as ei:
+        d.set_mode(match=False, all_=True)
+    assert ei.value.code == 2 and "Not supported yet" in ei.value.text
+
+
 def gpu_present():
     try:
         import torch
