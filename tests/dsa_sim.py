@@ -22,6 +22,8 @@ EXT = {28: "swar_n", 29: "swar0", 30: "swar1", 31: "swar2", 32: "swar3", 33: "gr
 EXT.update({43 + k: "lit%d" % k for k in range(16)})
 EXT.update({60 + k: "lit_out%d" % k for k in range(4)})
 EXT[64] = "gram_delta"
+EXT[65] = "vrun_swar_n"
+EXT.update({66 + k: "vrun_swar%d" % k for k in range(4)})
 PF_MATCHABLE, PF_GRAM = 64, 512
 
 
@@ -44,7 +46,7 @@ class Blob:
         self.sinfo = struct.unpack_from("<%dQ" % ns, raw, h["off_sinfo"]) if ns else ()
         self.pool = raw[h["off_pool"]:h["off_pool"] + h["pool_bytes"]]
         self.nft = [struct.unpack_from("<BBBBii", raw, h["off_nft"] + 12 * k) for k in range(h["nft_states"])]
-        words = struct.unpack_from("<65I", raw, 0)
+        words = struct.unpack_from("<70I", raw, 0)
         for k, name in EXT.items():
             h[name] = words[k]
 

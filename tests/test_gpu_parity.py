@@ -508,7 +508,7 @@ def test_literal_words_kernel(monkeypatch):
         assert q.scan(text) == oracle_run(expr.encode(), text, flavor=NFT)[1]
 
 
-def test_run_form_kernels():
+def test_run_form_kernels(monkeypatch):
     """k_bmv_count_run / k_bmv_write<RUN> (`X+:s`: one byte of left context): runs across lanes (16 B), tiles (512 B), spans
     and pipeline chunks; runs at the start and the end of the buffer; runs longer than a tile; several run classes."""
     rng = random.Random(99)
@@ -517,7 +517,8 @@ def test_run_form_kernels():
     body = "".join(rng.choice(pieces) for _ in range(6000))
     data = ("aaa" + body + "aaaa\n").encode()
     text = bytes(T.synth_text(0x72726513, 2 << 20, ["1", "22", "333", "4444", "a", "aa"], 0.3))
-    for expr in ("[0-9]+:#", "a+:x", "a+:", "( +): ", "a+:xyz|b:", "a+:x|b+:yy", "[a-b]+:Q|[0-9]+:#|c:", "(a|b)+:x"):
+    for expr in ("[0-9]+:#", "a+:x", "a+:", "( +): ", "a+:xyz|b:", "a+:x|b+:yy", "[a-b]+:Q|[0-9]+:#|c:", "(a|b)+:x",
+                 "(a|7)+:x"):                                     # (a set that is not one range: counted byte by byte)
         prog = T.compile(expr, NFT)
         assert prog.info["fast_path"] == 3                         # TRRE_FAST_BYTEMAP_VAR
         for buf in (data, text, data[:1], b"a\n", b"aaaa\n", b"\n", data[:511] + b"\n", data[:512] + b"\n", data[:513] + b"\n"):
@@ -525,6 +526,9 @@ def test_run_form_kernels():
             assert rc == 0 and prog.scan(buf) == want, (expr, len(buf))
         check(expr, NFT, data[:3000] + b"a\0a\n" + data[:100])          # a NUL: the general path
         check(expr, NFT, data[:3000].rstrip(b"\n") + b"aa")              # no final newline
+    monkeypatch.setenv("TRRE_RUN_PER_BYTE", "1")                   # the count pass without the SWAR range form: same bytes
+    for expr in ("[0-9]+:#", "a+:x|b+:yy"):
+        assert T.compile(expr, NFT).scan(data) == oracle_run(expr.encode(), data, flavor=NFT)[1]
 
 
 def test_literal_words_with_outputs_of_any_length():

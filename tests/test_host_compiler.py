@@ -246,6 +246,7 @@ def test_run_form_of_variable_byte_maps():
         p = T.compile(expr, NFT)
         b = Blob(p.blob())
         assert p.info["fast_path"] == 3 and b.h["vrun_classes"] == classes, (expr, p.info, b.h["vrun_classes"])
+        assert b.h["vrun_swar_n"] == classes                       # all of these are ranges that print one length
         rc, want, _ = oracle_run(expr.encode(), text, flavor=NFT)
         assert rc == 0 and b.scan_vmap(text) == want, expr
     for expr in ("a:", "a:xy|b:", "a+?:xy", "[0-9]:##"):            # plain variable byte maps: no run class
@@ -259,6 +260,8 @@ def test_run_form_of_variable_byte_maps():
         assert b.h["vrun_classes"] == 0, (expr, p.info)
         if p.info["fast_path"] == 3:
             assert b.scan_vmap(text) == oracle_run(expr.encode(), text, flavor=NFT)[1], expr
+    b = Blob(T.compile("(a|c)+:x", NFT).blob())                     # a run class that is not one range: counted per byte
+    assert b.h["vrun_classes"] == 1 and b.h["vrun_swar_n"] == 0 and b.scan_vmap(text) == oracle_run(b"(a|c)+:x", text, flavor=NFT)[1]
     p = T.compile("a+:x|ab:y", NFT)                                 # the first alternative always wins: a run after all
     assert Blob(p.blob()).scan_vmap(text) == oracle_run(b"a+:x|ab:y", text, flavor=NFT)[1]
     for expr in ("[0-9]+:#", "a+:x"):                               # trre_dft: shortest match - a plain byte map

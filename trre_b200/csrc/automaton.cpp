@@ -896,6 +896,23 @@ std::vector<uint8_t> assemble(const Program &P, const Nft &g) {
     h.start_info = P.sinfo.empty() ? 0 : (uint32_t)(P.sinfo[0] & 0xFFFFFFFFu);
     h.pool_bytes = (uint32_t)P.pool.size();
     h.vrun_classes = P.vrun_classes;
+    if (P.vmap && P.vrun_classes >= 1 && P.vrun_classes <= 4) {
+        bool ok = true;
+        for (uint32_t k = 1; k <= P.vrun_classes && ok; ++k) {
+            int lo = -1, hi = -1, members = 0;
+            size_t len = 0;
+            for (int c = 0; c < 256; ++c)
+                if (P.vrun[c] == k) {
+                    if (lo < 0) { lo = c; len = P.vstr[c].size(); }
+                    hi = c; ++members;
+                    if (P.vstr[c].size() != len) ok = false;
+                }
+            if (lo < 0 || members != hi - lo + 1 || (lo < 0x80) != (hi < 0x80) || len > 255) ok = false;
+            if (ok) h.vrun_swar[k - 1] = (uint32_t)lo | ((uint32_t)hi << 8) | ((uint32_t)len << 16);
+        }
+        if (ok) h.vrun_swar_n = P.vrun_classes;
+        else std::memset(h.vrun_swar, 0, sizeof h.vrun_swar);
+    }
     if (P.exec_kind == TRRE_EXEC_BYTEMAP) {
         // maximal runs of bytes that move by the same non-zero delta, cut at 0x80 (k_bytemap_swar tests 7-bit ranges)
         std::vector<uint32_t> runs;
@@ -1184,6 +1201,11 @@ bool blob_is_valid(const void *blob, size_t nbytes, std::string *why) {
             if (len > 1 && (uint64_t)off + len > h.vpool_bytes) return bad("byte-map string out of range");
             if (!h.vrun_classes ? false : (ve[c] >> 28) > h.vrun_classes) return bad("run class out of range");
         }
+    }
+    if (h.vrun_swar_n && (h.vrun_swar_n != h.vrun_classes || h.vrun_swar_n > 4)) return bad("run ranges");
+    for (uint32_t k = 0; k < h.vrun_swar_n; ++k) {
+        const uint32_t lo = h.vrun_swar[k] & 0xFFu, hi = (h.vrun_swar[k] >> 8) & 0xFFu;
+        if (!lo || lo > hi || (lo < 0x80u) != (hi < 0x80u)) return bad("run range");
     }
     if (h.vrun_classes > 15 || (h.vrun_classes && (!(h.flags & PF_BYTEMAP_VAR) || h.vpool_bytes > 4096))) return bad("run form");
     if (h.lit_words) {

@@ -118,6 +118,11 @@ struct BlobHeader {
     // (gram_flags & 2) every match prints its own bytes moved by this constant mod 256 (word:WORD dictionaries: 0xE0):
     // k_gram then needs no output table
     uint32_t gram_delta;
+    // (vrun_classes > 0) vrun_swar_n = vrun_classes when every run class is ONE byte range (inside one half of the byte
+    // space) whose bytes print strings of one length: vrun_swar[k] = lo | hi << 8 | length << 16 for class k + 1 - the count
+    // pass then needs no per-byte entries (k_bmv_count<RUNS>); 0 otherwise
+    uint32_t vrun_swar_n;
+    uint32_t vrun_swar[4];
 };
 
 struct NftFlat {               // 12 bytes, device layout of trre_nft.c:334-340

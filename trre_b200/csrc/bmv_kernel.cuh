@@ -98,8 +98,19 @@ __device__ __forceinline__ uint32_t pairlen_word(uint32_t w, uint32_t tab) {
     return lo + hi;
 }
 
+// RUN form whose run classes are byte ranges that print strings of one length each (`[0-9]+:#`): the count needs no
+// per-byte entries - the pair-length table gives the sum over all bytes as before, and the bytes a run swallows (in the
+// class and so is the byte before: one SWAR range test per data word, AND-ed with itself moved up one byte) are taken back
+// out with a popcount.
+struct RunMap {
+    uint32_t n;              // run classes (<= 4); 0: none of this form
+    uint32_t add_lo[4], add_hi[4], half[4];      // the 7-bit range test of k_bytemap_swar per class
+    uint32_t len[4];         // what a byte of the class would print as a run start
+};
+
+template <bool RUNS>
 __global__ void __launch_bounds__(kBmvCountThreads, 1)
-k_bmv_count(BmvArgs a) {
+k_bmv_count(BmvArgs a, RunMap R) {
     extern __shared__ __align__(128) uint8_t smem_tab[];   // kPairLutBytes
     __shared__ __align__(8) uint64_t bar;
     if (threadIdx.x == 0) {
@@ -128,16 +139,55 @@ k_bmv_count(BmvArgs a) {
         unsigned long long sum = 0;
         for (size_t t = t0; t < t1; ++t) {
             const size_t pos = t * (size_t)kBmvTile + lane * 16;
-            if (pos + 16 <= n) {
-                const uint4 x = ld_stream(reinterpret_cast<const uint4 *>(a.in + pos));
-                sum += pairlen_word(x.x, tab) + pairlen_word(x.y, tab) + pairlen_word(x.z, tab) + pairlen_word(x.w, tab);
-                nul |= ((x.x - 0x01010101u) & ~x.x) | ((x.y - 0x01010101u) & ~x.y) | ((x.z - 0x01010101u) & ~x.z) | ((x.w - 0x01010101u) & ~x.w);
-            } else {
-                for (size_t k = pos; k < n; ++k) {
-                    const uint8_t c = a.in[k];
-                    if (!c) nul = 0x80u;
-                    sum += __ldg(a.vent + c) & 0xFFu;
+            if (!RUNS) {
+                if (pos + 16 <= n) {
+                    const uint4 x = ld_stream(reinterpret_cast<const uint4 *>(a.in + pos));
+                    sum += pairlen_word(x.x, tab) + pairlen_word(x.y, tab) + pairlen_word(x.z, tab) + pairlen_word(x.w, tab);
+                    nul |= ((x.x - 0x01010101u) & ~x.x) | ((x.y - 0x01010101u) & ~x.y) | ((x.z - 0x01010101u) & ~x.z) | ((x.w - 0x01010101u) & ~x.w);
+                } else {
+                    for (size_t k = pos; k < n; ++k) {
+                        const uint8_t c = a.in[k];
+                        if (!c) nul = 0x80u;
+                        sum += __ldg(a.vent + c) & 0xFFu;
+                    }
                 }
+            } else {
+                // every lane takes part (shuffles): bytes past the buffer read as '\n', which stands in no run class
+                uint4 x = make_uint4(0x0A0A0A0Au, 0x0A0A0A0Au, 0x0A0A0A0Au, 0x0A0A0A0Au);
+                uint32_t mine = 0;
+                if (pos + 16 <= n) {
+                    x = ld_stream(reinterpret_cast<const uint4 *>(a.in + pos));
+                    mine = pairlen_word(x.x, tab) + pairlen_word(x.y, tab) + pairlen_word(x.z, tab) + pairlen_word(x.w, tab);
+                } else if (pos < n) {
+                    uint32_t w[4] = {x.x, x.y, x.z, x.w};
+                    for (size_t k = pos; k < n; ++k) {
+                        const uint32_t c = a.in[k], j = (uint32_t)(k - pos);
+                        w[j >> 2] = (w[j >> 2] & ~(0xFFu << ((j & 3) * 8))) | (c << ((j & 3) * 8));
+                        mine += __ldg(a.vent + c) & 0xFFu;
+                    }
+                    x = make_uint4(w[0], w[1], w[2], w[3]);
+                }
+                nul |= ((x.x - 0x01010101u) & ~x.x) | ((x.y - 0x01010101u) & ~x.y) | ((x.z - 0x01010101u) & ~x.z) | ((x.w - 0x01010101u) & ~x.w);
+                // the byte before the lane's vector, in the top byte of a word (lane 0: the previous tile's last byte)
+                uint32_t before = __shfl_up_sync(0xFFFFFFFFu, x.w, 1);
+                if (lane == 0) before = (pos ? (uint32_t)__ldg(a.in + pos - 1) : (uint32_t)'\n') << 24;
+                const uint32_t W[5] = {before, x.x, x.y, x.z, x.w};
+                uint32_t swallowed = 0;
+#pragma unroll
+                for (int r = 0; r < 4; ++r) {
+                    if ((uint32_t)r >= R.n) break;
+                    uint32_t m[5];
+#pragma unroll
+                    for (int i = 0; i < 5; ++i) {
+                        const uint32_t l = W[i] & 0x7F7F7F7Fu;
+                        m[i] = (l + R.add_lo[r]) & ~(l + R.add_hi[r]) & (W[i] ^ R.half[r]) & 0x80808080u;   // bit 7: the byte is in the class
+                    }
+                    uint32_t cnt = 0;
+#pragma unroll
+                    for (int i = 1; i < 5; ++i) cnt += __popc(m[i] & __funnelshift_l(m[i - 1], m[i], 8));  // ... and so is the byte before
+                    swallowed += cnt * R.len[r];
+                }
+                sum += mine - swallowed;
             }
         }
 #pragma unroll

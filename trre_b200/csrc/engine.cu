@@ -103,6 +103,7 @@ struct DeviceState {
     LitMap lit{};                  // table-free word matcher (lit_words == 0: not of that form)
     uint32_t lit_words = 0, lit_len = 0;
     bool lit_eq = false;           // every position of every word accepts exactly one byte
+    RunMap runmap{};               // RUN form whose classes are ranges of one printed length: SWAR counting (n == 0: per byte)
     LitvArgs litv{};               // the same words printing strings of any length (k_litv_count / k_bmv_write<BMV_LIT>)
     bool litv_ok = false;
     // TRRE_EXEC_LAZY: device copies of the rows built so far (automaton.hpp, LazyDsa)
@@ -326,6 +327,16 @@ int get_state(const trre_prog *cp, int device, DeviceState **out) {
         if (!d->lit_eq)                                            // the range form tests 7-bit ranges below 0x80 only: k_gram serves
             for (uint32_t k = 0; k < h.lit_words * h.lit_len; ++k)
                 if (((h.lit[k] >> 8) & 0xFFu) >= 0x80u) d->lit_words = 0;
+    }
+    if (h.vrun_swar_n >= 1 && h.vrun_swar_n <= 4 && h.vrun_swar_n == h.vrun_classes && !std::getenv("TRRE_RUN_PER_BYTE")) {
+        d->runmap.n = h.vrun_swar_n;
+        for (uint32_t k = 0; k < h.vrun_swar_n; ++k) {
+            const uint32_t lo = h.vrun_swar[k] & 0xFFu, hi = (h.vrun_swar[k] >> 8) & 0xFFu;
+            d->runmap.add_lo[k] = (0x80u - (lo & 0x7Fu)) * 0x01010101u;
+            d->runmap.add_hi[k] = (0x7Fu - (hi & 0x7Fu)) * 0x01010101u;
+            d->runmap.half[k] = lo < 0x80u ? 0x80808080u : 0u;
+            d->runmap.len[k] = (h.vrun_swar[k] >> 16) & 0xFFu;
+        }
     }
     if (h.flags & PF_MATCHABLE) {
         int rc2 = plan_match(h, (size_t)kMatchWarps * kWarpSmem, 108 * 1024, d->sm_count, OP_INPLACE, &d->mp);
@@ -677,7 +688,8 @@ int launch_bmv(const trre_prog *p, DeviceState *d, const uint8_t *d_in, size_t n
     const uint32_t pool_bytes = src == BMV_LIT ? p->hdr.gpool_bytes : d->vpool_bytes;
     if (!d->bmv_attr) {
         d->bmv_smem = 256 * 32 * 4 + ((pool_bytes + 15) & ~15u) + (size_t)(kBmvWriteThreads / 32) * kBmvWarpSmem;
-        CUDA_TRY(cudaFuncSetAttribute(k_bmv_count, cudaFuncAttributeMaxDynamicSharedMemorySize, kPairLutBytes));
+        CUDA_TRY(cudaFuncSetAttribute(k_bmv_count<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kPairLutBytes));
+        CUDA_TRY(cudaFuncSetAttribute(k_bmv_count<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kPairLutBytes));
         CUDA_TRY(cudaFuncSetAttribute(k_bmv_write<BMV_PLAIN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)d->bmv_smem));
         CUDA_TRY(cudaFuncSetAttribute(k_bmv_write<BMV_RUN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)d->bmv_smem));
 #define LITV_ATTR(NW, L) CUDA_TRY(cudaFuncSetAttribute(k_bmv_write<BMV_LIT, NW, L>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)d->bmv_smem));
@@ -701,8 +713,9 @@ int launch_bmv(const trre_prog *p, DeviceState *d, const uint8_t *d_in, size_t n
                 default: g_last_error = "internal: literal word form out of range"; return TRRE_E_ARG;
             }
 #undef LITV_COUNT
-        } else if (src == BMV_RUN) k_bmv_count_run<<<d->sm_count, kBmvCountThreads, 256 * 32 * 4, st>>>(a);
-        else k_bmv_count<<<d->sm_count, kBmvCountThreads, kPairLutBytes, st>>>(a);
+        } else if (src == BMV_RUN && d->runmap.n) k_bmv_count<true><<<d->sm_count, kBmvCountThreads, kPairLutBytes, st>>>(a, d->runmap);
+        else if (src == BMV_RUN) k_bmv_count_run<<<d->sm_count, kBmvCountThreads, 256 * 32 * 4, st>>>(a);
+        else k_bmv_count<false><<<d->sm_count, kBmvCountThreads, kPairLutBytes, st>>>(a, d->runmap);
         k_scan_groups<<<1, kScanThreads, 0, st>>>(a.gsum, n_spans, const_cast<unsigned long long *>(a.total));
         *launches += 2;
         if (!ws) d->counts_kind = 2;
