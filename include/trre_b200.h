@@ -69,9 +69,10 @@ enum {
 enum {
     TRRE_FAST_NONE      = 0,   /* per-line kernels only (cycles, empty matches, DFS executor)                */
     TRRE_FAST_BYTEMAP   = 1,   /* k_bytemap: one byte in, one byte out                                       */
-    TRRE_FAST_MATCH     = 2,   /* k_match: length-preserving acyclic program, attempts <= 16 bytes           */
-    TRRE_FAST_BYTEMAP_VAR = 3, /* k_bmv_*: one byte in, 0..255 bytes out                                     */
-    TRRE_FAST_MATCH_VAR = 4,   /* k_match count/write: acyclic program, matches of any output length         */
+    TRRE_FAST_MATCH     = 2,   /* k_lit (literal_words > 0) / k_gram (gram_tables) / k_match: length-preserving  */
+                               /* program with short attempts                                                */
+    TRRE_FAST_BYTEMAP_VAR = 3, /* k_bmv_*: one byte in, 0..255 bytes out; also runs (`[0-9]+:#`: RUN form)       */
+    TRRE_FAST_MATCH_VAR = 4,   /* k_litv / k_gram_var / k_match count + write: matches of any output length     */
     TRRE_FAST_INPLACE   = 5    /* k_lines in place: other length-preserving programs                         */
 };
 
@@ -128,7 +129,9 @@ int  trre_lazy_view(const trre_prog *p, uint32_t *n_states, const uint64_t **row
  * These modes run the reference's priority DFS over the flat NFT on the GPU, one record per thread (k_lines with the DFS
  * executor), whatever tables the program has.  DFT flavour: -m prints one bare newline per record (trre_dft.c:1287-1292);
  * -a returns TRRE_E_UNSUPPORTED with the reference's text "Not supported yet" (trre_dft.c:1226).  The mode is not part
- * of the blob: set it again on a program made by trre_prog_from_blob. */
+ * of the blob: set it again on a program made by trre_prog_from_blob.  It is plain state of the program object: do not
+ * change it while a scan of the same program is running in another thread.  One record may take at most 2^26 DFS steps
+ * and, with all != 0, print at most 16 MiB (TRRE_E_UNSUPPORTED beyond: the reference would run for hours there). */
 int  trre_prog_set_mode(trre_prog *p, int match, int all);
 
 /* 256-entry map for TRRE_EXEC_BYTEMAP programs (returns TRRE_E_ARG otherwise). */

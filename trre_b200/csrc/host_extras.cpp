@@ -1,7 +1,8 @@
 // host_extras.cpp - host-only parts of the C ABI that are NOT the scan path:
-//   trre_match_host  : `-m`, `-ma` and scan-mode `-a` of the CLI (trre_nft.c:635-642, 791-797; the DFT
-//                      binary prints a bare newline per record, trre_dft.c:1287-1293).  SURVEY s8f ranks
-//                      match mode as a later row; the CLI keeps the flags working through this.
+//   trre_match_host  : `-m`, `-ma` and scan-mode `-a` on the HOST (trre_nft.c:635-642, 791-797; the DFT binary prints a
+//                      bare newline per record, trre_dft.c:1287-1293).  The CLI runs these modes on the GPU
+//                      (trre_prog_set_mode, the DFS executor); this restatement is what the tests cross-check that path
+//                      with when no reference binary is at hand.
 //   trre_synth_text  : the deterministic synthetic corpus of BASELINE.md s3 / SURVEY s8d.
 #include <cstdio>
 #include <cstdlib>
