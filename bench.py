@@ -538,6 +538,19 @@ def measure(ctx, name, nbytes, steps, warmup, collectives=False, tile_rank=None,
     return res
 
 
+def others_plan(world):
+    """(label, workload, bytes per GPU, collectives inside the clock) of the `others` block, in order."""
+    plan = [("cfg1", 1_000_000, False), ("cfg1_1GiB", 1 * GiB, False), ("cfg3_1GiB", 1 * GiB, False), ("cfg4_1GiB", 1 * GiB, False),
+            ("cfg5_1GiB", 1 * GiB, False)]
+    if world == 1:
+        plan += [("cfg3", 8 * GiB, False), ("cfg5_64GiB", 64 * GiB, False)]
+        # off-BASELINE programs: what the other kernel families and the DFS executor do (sizes: WORKLOADS)
+        plan += [(w, WORKLOADS[w][2], False) for w in ("del", "num", "sub", "dfs", "mode_a", "mode_m")]
+    else:
+        plan += [("cfg4", 8 * GiB, True), ("cfg5_64GiB_split", 64 * GiB // world, True)]
+    return [(label, label if label in WORKLOADS else label.split("_")[0], per_gpu, coll) for label, per_gpu, coll in plan]
+
+
 def kernel_label(T, info):
     if info.get("mode"):
         flags = ("-m" if info["mode"][0] else "") + ("-a" if info["mode"][1] else "")
@@ -783,17 +796,8 @@ def main():
     others = None
     if not args.no_others and name == "cfg2" and not args.bytes:
         others = {}
-        plan = [("cfg1", 1_000_000, False), ("cfg1_1GiB", 1 * GiB, False), ("cfg3_1GiB", 1 * GiB, False), ("cfg4_1GiB", 1 * GiB, False),
-                ("cfg5_1GiB", 1 * GiB, False)]
-        if world == 1:
-            plan += [("cfg3", 8 * GiB, False), ("cfg5_64GiB", 64 * GiB, False)]
-            # off-BASELINE programs: what the other kernel families and the DFS executor do (sizes: WORKLOADS)
-            plan += [(w, WORKLOADS[w][2], False) for w in ("del", "num", "sub", "dfs", "mode_a", "mode_m")]
-        else:
-            plan += [("cfg4", 8 * GiB, True), ("cfg5_64GiB_split", 64 * GiB // world, True)]
         free = torch.cuda.mem_get_info()[0]
-        for label, per_gpu, coll in plan:
-            wl = label if label in WORKLOADS else label.split("_")[0]
+        for label, wl, per_gpu, coll in others_plan(world):
             if 2 * per_gpu + (1 << 30) > free:
                 others[label] = {"skipped": "needs %d GiB of HBM" % ((2 * per_gpu) >> 30)}
                 continue

@@ -25,3 +25,19 @@ def test_non_zero_ranks_of_the_reference_arm_stay_silent():
     r = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--gpus", "2", "--steps", "1"],
                        capture_output=True, text=True, timeout=120, env=env)
     assert r.returncode == 0 and r.stdout.strip() == ""
+
+
+def test_others_plan_names_existing_workloads_and_labels_every_kernel():
+    """The `others` block runs after the headline inside try/except: a wrong workload name would only show up as an
+    {"error": ...} entry on the GPU box.  Check the plan and the kernel labels here."""
+    sys.path.insert(0, ROOT)
+    import bench
+    import trre_b200 as T
+    for world in (1, 2, 8):
+        for label, wl, per_gpu, coll in bench.others_plan(world):
+            assert wl in bench.WORKLOADS and wl in bench.DESCR and per_gpu > 0, (world, label, wl)
+    for name, spec in bench.WORKLOADS.items():
+        info = dict(T.compile(spec[0], spec[1]).info, mode=spec[8] if len(spec) > 8 else None)
+        assert isinstance(bench.kernel_label(T, info), str) and bench.kernel_label(T, info), name
+    assert bench.kernel_label(T, dict(T.compile("cat:dog", 0).info, mode=None)) == "k_lit"
+    assert "k_lines<dfs, -m>" in bench.kernel_label(T, dict(T.compile("cat:dog", 0).info, mode=(1, 0)))
