@@ -264,6 +264,42 @@ def test_run_form_of_variable_byte_maps():
     assert b.h["vrun_classes"] == 1 and b.h["vrun_swar_n"] == 0 and b.scan_vmap(text) == oracle_run(b"(a|c)+:x", text, flavor=NFT)[1]
     p = T.compile("a+:x|ab:y", NFT)                                 # the first alternative always wins: a run after all
     assert Blob(p.blob()).scan_vmap(text) == oracle_run(b"a+:x|ab:y", text, flavor=NFT)[1]
+    # random run programs: 1-3 run classes (single bytes, ranges, alternations) and plain byte-map entries beside them
+    got = 0
+    for _ in range(120):
+        parts, used = [], set()
+        for _k in range(rng.randint(1, 3)):
+            kind = rng.random()
+            if kind < 0.4:
+                c = rng.choice("abcd 7")
+                if c in used: continue
+                used.add(c); cls = c if c != " " else "( )"
+            elif kind < 0.7:
+                lo = rng.choice("02"); hi = chr(ord(lo) + rng.randint(1, 6))
+                if any(chr(x) in used for x in range(ord(lo), ord(hi) + 1)): continue
+                used.update(chr(x) for x in range(ord(lo), ord(hi) + 1)); cls = "[%s-%s]" % (lo, hi)
+            else:
+                a, b2 = rng.sample("abcd", 2)
+                if a in used or b2 in used: continue
+                used.update((a, b2)); cls = "(%s|%s)" % (a, b2)
+            parts.append("%s+:%s" % (cls, rng.choice(["", "#", "xy", "RUN"])))
+        for c in "xd2":
+            if c not in used and rng.random() < 0.4:
+                used.add(c); parts.append("%s:%s" % (c, rng.choice(["", "QQ", "z"])))
+        if not parts:
+            continue
+        expr = "|".join(parts)
+        try:
+            p = T.compile(expr, NFT)
+        except T.TrreError:
+            continue
+        b = Blob(p.blob())
+        if p.info["fast_path"] != 3:
+            continue
+        rc, want, _ = oracle_run(expr.encode(), text, flavor=NFT)
+        assert rc == 0 and b.scan_vmap(text) == want, expr
+        got += b.h["vrun_classes"] > 0
+    assert got > 60, got
     for expr in ("[0-9]+:#", "a+:x"):                               # trre_dft: shortest match - a plain byte map
         p = T.compile(expr, DFT)
         b = Blob(p.blob())
