@@ -23,7 +23,7 @@ def _free_port():
     return p
 
 
-def _worker(rank, world, port, expr, flavor, data, q):
+def _worker(rank, world, port, expr, flavor, data, q, mode=None):
     sys.path.insert(0, ROOT)
     sys.path.insert(0, os.path.join(ROOT, "tests"))
     import trre_b200 as T
@@ -45,7 +45,13 @@ def _worker(rank, world, port, expr, flavor, data, q):
         prog = T.from_blob(bytes(buf.numpy().tobytes()))            # no recompilation on rank > 0
         cuts = T.shard_lines(data, world)
         shard = data[cuts[rank]:cuts[rank + 1]]
-        out = Blob(prog.blob()).scan(shard)
+        if mode is None:
+            out = Blob(prog.blob()).scan(shard)
+        else:
+            # -m / -a are not part of the blob: every rank sets the mode on its own copy (on the GPU box the scan then runs
+            # the DFS executor; here the host restatement of the same modes stands in for it)
+            prog.set_mode(match=mode[0], all_=mode[1])
+            out = prog.match(shard, all_=mode[1], scan=not mode[0])
         sizes = [torch.zeros(1, dtype=torch.int64) for _ in range(world)]
         dist.all_gather(sizes, torch.tensor([len(out)], dtype=torch.int64))
         offsets = [0]
@@ -69,6 +75,32 @@ def test_two_ranks_equal_one(expr, flavor):
     q = ctx.Queue()
     port = _free_port()
     procs = [ctx.Process(target=_worker, args=(r, world, port, expr, flavor, data, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    got = sorted(q.get(timeout=120) for _ in range(world))
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    joined = bytearray(len(want))
+    for rank, off, out in got:
+        joined[off:off + len(out)] = out
+    assert bytes(joined) == want
+
+
+@pytest.mark.parametrize("expr,mode", [("(cat:dog|dog:cat|cat:CAT)", (False, True)), ("[a-z ]*(cat:dog)[a-z ]*", (True, False))])
+def test_two_ranks_equal_one_in_the_other_modes(expr, mode):
+    """-a / -m over line-aligned shards (records are independent in every mode, trre_nft.c:776-797)."""
+    sys.path.insert(0, ROOT)
+    import trre_b200 as T
+    from oracle_util import oracle_run, MATCH, SCAN
+    data = bytes(T.synth_text(98, 12000, ["cat", "dog", "catdog"], 0.3, True))
+    rc, want, _ = oracle_run(expr.encode(), data, flavor=0, mode=MATCH if mode[0] else SCAN, all_=mode[1])
+    assert rc == 0
+    world = 2
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_worker, args=(r, world, port, expr, 0, data, q, mode)) for r in range(world)]
     for p in procs:
         p.start()
     got = sorted(q.get(timeout=120) for _ in range(world))
